@@ -1,0 +1,264 @@
+"""CPU oracle for the shifted-correlation hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a NumPy restatement of the algorithm of the reference package
+(mdevaluate, read-only under /root/reference) for the one path this repository
+accelerates.  It exists so that the CUDA path can be checked on machines where
+the reference itself is absent (the GPU box).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it; nothing under ``mdevaluate_b200/`` does.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the real
+reference (with stubbed I/O dependencies) in the build container, runs it on
+seeded synthetic trajectories and stores inputs + outputs under
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function
+below against those vectors (bit-for-bit for integer results and for the float
+results that use the same NumPy expressions).
+
+Each function cites the reference lines it follows (paths relative to
+/root/reference/).  Arithmetic is delegated to NumPy/SciPy exactly as the
+reference does (numpy 2.3.5 / scipy 1.18.1 in this image; the reference pins
+neither, ``setup.py:26``).
+"""
+from __future__ import annotations
+
+from itertools import chain
+
+import numpy as np
+
+__all__ = [
+    "log_indices", "lin_indices", "schedule", "pairwise", "shifted_correlation",
+    "msd", "isf", "van_hove_self", "non_gaussian", "histogram", "runningmean",
+    "chi4", "jump_table", "image_counts", "unwrap_frame", "TimedFrame",
+    "ArrayTrajectory", "UnwrappedTrajectory",
+]
+
+
+# --------------------------------------------------------------------------- #
+# lag / origin schedule
+# --------------------------------------------------------------------------- #
+def log_indices(first, last, num=100):
+    """Log-spaced integer lags in [first, last].  mdevaluate/correlation.py:16-18."""
+    spaced = np.logspace(0, np.log10(last - first + 1), num=num)
+    return np.unique(np.int_(spaced) - 1 + first)
+
+
+def lin_indices(first, last):
+    """Dense linear lags (BASELINE config 5 passes ``lambda a, b: np.arange(a, b)``)."""
+    return np.arange(first, last)
+
+
+def schedule(n_frames, segments=10, window=0.5, skip=0.0):
+    """Origins and window length.  mdevaluate/correlation.py:136-142.
+
+    Returns ``(start_frames, num_frames)``; the caller applies
+    ``index_distribution(0, num_frames)`` (correlation.py:144).
+    """
+    assert window + skip < 1
+    starts = np.unique(np.linspace(
+        n_frames * skip, n_frames * (1 - window),
+        num=segments, endpoint=False, dtype=int,
+    ))
+    return starts, int(n_frames * window)
+
+
+def pairwise(function, frames):
+    """The default ``correlation`` strategy.  mdevaluate/correlation.py:21-24.
+
+    The first frame of the iterator is the origin; the origin is also the first
+    frame evaluated, so element 0 is always ``function(origin, origin)``.
+    """
+    it = iter(frames)
+    origin = next(it)
+    return map(lambda f: function(origin, f), chain([origin], it))
+
+
+def shifted_correlation(function, frames, index_distribution=log_indices,
+                        segments=10, window=0.5, skip=None, average=False):
+    """Driver without the ``has_counter`` branch.  mdevaluate/correlation.py:131-151,190-201."""
+    if skip is None:
+        try:
+            skip = frames._slice.start / len(frames)
+        except (TypeError, AttributeError):
+            skip = 0
+    starts, num_frames = schedule(len(frames), segments, window, skip)
+    idx = index_distribution(0, num_frames)
+
+    times = np.array([frames[i].time for i in idx]) - frames[0].time
+
+    result = 0 if average else []
+    for s in starts:
+        row = list(pairwise(function, map(frames.__getitem__, idx + s)))
+        if average:
+            result += np.array(row)
+        else:
+            result.append(row)
+    result = np.array(result)
+    if average:
+        result = result / len(starts)
+    return times, result
+
+
+# --------------------------------------------------------------------------- #
+# per-pair kernels
+# --------------------------------------------------------------------------- #
+def msd(start, frame):
+    """mdevaluate/correlation.py:203-208."""
+    vec = start - frame
+    return (vec ** 2).sum(axis=1).mean()
+
+
+def isf(start, frame, q, box=None):
+    """Isotropic incoherent scattering function.  mdevaluate/correlation.py:211-220."""
+    vec = start - frame
+    distance = (vec ** 2).sum(axis=1) ** .5
+    return np.sinc(distance * q / np.pi).mean()
+
+
+def runningmean(data, nav):
+    """mdevaluate/utils.py:150-161."""
+    return np.convolve(data, np.ones((nav,)) / nav, mode='valid')
+
+
+def histogram(data, bins):
+    """mdevaluate/utils.py:328-338 (bincount fast path / np.histogram)."""
+    widths = np.diff(bins)
+    dx = widths.mean()
+    if bins.min() == 0 and widths.std() < 1e-6:
+        hist = np.bincount((data // dx).astype(int), minlength=len(widths))[:len(widths)]
+    else:
+        hist = np.histogram(data, bins=bins)[0]
+    return hist, runningmean(bins, 2)
+
+
+def van_hove_self(start, end, bins):
+    """mdevaluate/correlation.py:239-248."""
+    vec = start - end
+    delta_r = ((vec) ** 2).sum(axis=-1) ** .5
+    return 1 / len(start) * histogram(delta_r, bins)[0]
+
+
+def non_gaussian(onset, frame):
+    """mdevaluate/correlation.py:355-362 (NaN at lag 0 is intended)."""
+    r_2 = ((frame - onset) ** 2).sum(axis=-1)
+    return 3 / 5 * (r_2 ** 2).mean() / r_2.mean() ** 2 - 1
+
+
+def chi4(n_atoms, fqt):
+    """examples/plot_chi4.py:29-37: ``len(OW[0]) * Fqt.var(axis=0)`` on the (S, L) ISF."""
+    return n_atoms * np.asarray(fqt).var(axis=0)
+
+
+# --------------------------------------------------------------------------- #
+# nojump: producer (reader.parse_jumps) and consumer (pbc.nojump)
+# --------------------------------------------------------------------------- #
+def jump_table(positions, box_diag, whole0=None):
+    """Per-step image jumps, dense.  mdevaluate/reader.py:165-186.
+
+    ``positions`` is (T, M, 3) in the reader's dtype (float32), ``box_diag`` the
+    diagonal of frame 0's box (reader.py:167: one box for ALL frames).  Row 0 is
+    taken against ``frame0.whole`` (reader.py:166); ``whole0=None`` means every
+    residue is a single atom, for which ``whole`` is the identity.
+    Returns int8 (T, M, 3); the reference stores the same numbers as three
+    (T x M) CSR matrices (reader.py:199-201).
+    """
+    positions = np.asarray(positions)
+    box_diag = np.asarray(box_diag)
+    prev = positions[0] if whole0 is None else np.asarray(whole0)
+    out = np.empty(positions.shape, dtype=np.int8)
+    for t in range(positions.shape[0]):
+        curr = positions[t]
+        out[t] = ((curr - prev) / box_diag).round().astype(np.int8)
+        prev = curr
+    return out
+
+
+def image_counts(jumps):
+    """Inclusive prefix sum over frames: ``m[:t+1].sum(axis=0)``.  mdevaluate/pbc.py:235-237,244-246."""
+    return np.cumsum(jumps, axis=0, dtype=np.int64)
+
+
+def unwrap_frame(frame, counts, box_diag):
+    """``frame - counts * box`` in float64.  mdevaluate/pbc.py:235-237,247.
+
+    ``counts`` is int64 (M, 3) (sum of the int8 CSR rows), ``box_diag`` the
+    CURRENT frame's box diagonal in its own dtype (float32 from the reader):
+    int64 * float32 promotes to float64, and so does float32 - float64.
+    """
+    delta = np.asarray(counts) * np.asarray(box_diag)
+    return frame - delta
+
+
+# --------------------------------------------------------------------------- #
+# minimal frames protocol (coordinates.py:105-189, 257-293) for in-memory data
+# --------------------------------------------------------------------------- #
+class TimedFrame(np.ndarray):
+    """(N, 3) array that carries ``.time`` / ``.step`` / ``.box`` like CoordinateFrame."""
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.time = getattr(obj, 'time', None)
+        self.step = getattr(obj, 'step', None)
+        self.box = getattr(obj, 'box', None)
+
+
+class ArrayTrajectory:
+    """Raw (wrapped) frames of an in-memory (T, N, 3) array; ``len`` is the full length."""
+
+    def __init__(self, positions, box_diag, times=None, selection=None):
+        self.positions = np.asarray(positions)
+        self.box_diag = np.asarray(box_diag)
+        T = self.positions.shape[0]
+        self.times = np.arange(T, dtype=float) if times is None else np.asarray(times)
+        self.selection = selection
+        self._slice = slice(None)
+
+    def __len__(self):
+        return self.positions.shape[0]
+
+    def _raw(self, i):
+        frame = self.positions[i]
+        if self.selection is not None:
+            frame = frame[self.selection]
+        return frame
+
+    def _wrap(self, arr, i):
+        out = np.asarray(arr).view(TimedFrame)
+        out.time = self.times[i]
+        out.step = i
+        box = self.box_diag if self.box_diag.ndim == 1 else self.box_diag[i]
+        out.box = np.diag(box)
+        return out
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            import copy
+            sl = copy.copy(self)
+            sl._slice = i
+            return sl
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        return self._wrap(self._raw(i), i)
+
+
+class UnwrappedTrajectory(ArrayTrajectory):
+    """``coords.nojump``: every frame is ``raw - image_counts * box`` (float64)."""
+
+    def __init__(self, positions, box_diag, times=None, selection=None, whole0=None):
+        super().__init__(positions, box_diag, times, selection)
+        box0 = self.box_diag if self.box_diag.ndim == 1 else self.box_diag[0]
+        self.jumps = jump_table(self.positions, box0, whole0)
+        self.counts = image_counts(self.jumps)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return super().__getitem__(i)
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        box = self.box_diag if self.box_diag.ndim == 1 else self.box_diag[i]
+        full = unwrap_frame(self.positions[i], self.counts[i], box)
+        if self.selection is not None:
+            full = full[self.selection]
+        return self._wrap(full, i)

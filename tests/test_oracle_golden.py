@@ -1,0 +1,132 @@
+"""Pin the CPU oracle (oracle/md_oracle.py) to vectors produced by the real reference.
+
+The fixtures under tests/golden/ were written by tests/golden/make_golden.py, which
+imports /root/reference/mdevaluate itself.  Integer results must be identical; float
+results use the same NumPy expressions and must be identical too (rtol 0).
+"""
+from functools import partial
+
+import numpy as np
+import pytest
+
+from oracle import md_oracle as orc
+from mdevaluate_b200.synthetic import random_walk
+
+
+def same(a, b):
+    np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_log_indices_golden(golden):
+    g = golden('schedule')
+    for key in g.files:
+        _, first, last = key.split('_')
+        same(orc.log_indices(int(first), int(last)), g[key])
+
+
+def test_histogram_golden(golden):
+    g = golden('histogram')
+    for k in ('b0', 'b1', 'b2'):
+        h, c = orc.histogram(g['data'], g[k])
+        same(h, g['h_' + k])
+        same(c, g['c_' + k])
+    same(orc.runningmean(g['data'][:40], 5), g['runmean5'])
+
+
+def test_histogram_matches_numpy_like_reference_test():
+    # the reference's own test (test/test_utils.py:36-46), seeded
+    data = np.random.default_rng(5).random(100)
+    for bins in (np.linspace(0, 1), np.linspace(0.3, 1.5)):
+        same(orc.histogram(data, bins)[0], np.histogram(data, bins=bins)[0])
+
+
+@pytest.fixture(scope='module')
+def small(golden):
+    g = golden('walk_small')
+    raw = orc.ArrayTrajectory(g['pos'], g['box'], g['times'])
+    unw = orc.UnwrappedTrajectory(g['pos'], g['box'], g['times'])
+    return g, raw, unw
+
+
+def test_jump_table_golden(small):
+    g, raw, unw = small
+    same(unw.jumps, g['jumps'])
+    assert np.count_nonzero(g['jumps']) > 500      # the fixture really exercises jumps
+
+
+def test_unwrapped_frames_golden(small):
+    g, raw, unw = small
+    for i in (0, 1, 17, 100, 239):
+        f = unw[i]
+        assert f.dtype == np.float64
+        same(f, g['nojump_%d' % i])
+
+
+def _functions(g):
+    return {
+        'msd': orc.msd,
+        'isf': partial(orc.isf, q=22.7),
+        'ng': orc.non_gaussian,
+        'vh': partial(orc.van_hove_self, bins=g['bins']),
+        'vh_off': partial(orc.van_hove_self, bins=g['bins_off']),
+        'vh_irr': partial(orc.van_hove_self, bins=g['bins_irr']),
+    }
+
+
+@pytest.mark.parametrize('name', ['msd', 'isf', 'ng', 'vh', 'vh_off', 'vh_irr'])
+@pytest.mark.parametrize('mode', ['nojump', 'raw'])
+def test_shifted_correlation_golden(small, name, mode):
+    g, raw, unw = small
+    frames = unw if mode == 'nojump' else raw
+    with np.errstate(all='ignore'):
+        t, r = orc.shifted_correlation(_functions(g)[name], frames, segments=12, window=0.4)
+    same(t, g['t_' + mode])
+    same(r, g['%s_%s' % (name, mode)])
+    assert r.dtype == g['%s_%s' % (name, mode)].dtype
+
+
+def test_chi4_average_slice_dense_golden(small):
+    g, raw, unw = small
+    fns = _functions(g)
+    t, r = orc.shifted_correlation(fns['isf'], unw, segments=20, window=0.2, skip=0.1, average=False)
+    same(r, g['chi4_fqt'])
+    same(t, g['chi4_t'])
+    same(orc.chi4(g['pos'].shape[1], r), g['chi4'])
+    t, r = orc.shifted_correlation(fns['msd'], unw, segments=7, window=0.3, average=True)
+    same(r, g['msd_avg'])
+    same(t, g['msd_avg_t'])
+    t, r = orc.shifted_correlation(fns['msd'], unw[24:], segments=7, window=0.3, average=True)
+    same(r, g['msd_slice24'])
+    t, r = orc.shifted_correlation(fns['isf'], unw, segments=5, window=0.25,
+                                   index_distribution=orc.lin_indices)
+    same(r, g['isf_dense'])
+
+
+def test_selection_golden(small):
+    g, raw, unw = small
+    sel = g['sel']
+    frames = orc.UnwrappedTrajectory(g['pos'], g['box'], g['times'], selection=sel)
+    t, r = orc.shifted_correlation(orc.msd, frames, segments=6, window=0.4)
+    same(r, g['msd_sel'])
+
+
+def test_config1_golden(golden):
+    """BASELINE config 1: MSD, 1000 atoms x 1000 frames, 100 origins, 70 log lags."""
+    g = golden('config1')
+    pos, box, times = random_walk(1000, 1000, seed=20240)
+    same(box, g['box'])
+    assert np.float64(pos.astype(np.float64).sum()) == g['pos_sum']
+    same(pos[::97, ::53], g['pos_probe'])
+    unw = orc.UnwrappedTrajectory(pos, box, times)
+    assert np.count_nonzero(unw.jumps) == g['jump_nnz']
+    same(unw.counts[-1], g['count_checksum'])
+    t, r = orc.shifted_correlation(orc.msd, unw, segments=100, window=0.5)
+    assert r.shape == (100, 70)
+    same(t, g['t'])
+    same(r, g['msd'])
+    raw = orc.ArrayTrajectory(pos, box, times)
+    t, r = orc.shifted_correlation(partial(orc.isf, q=22.7), raw, segments=100, window=0.5)
+    same(r, g['isf_raw'])
+    assert r.dtype == np.float32
+    t, r = orc.shifted_correlation(partial(orc.van_hove_self, bins=g['vh_bins']), unw, segments=10, window=0.5)
+    same(r, g['vh'])
