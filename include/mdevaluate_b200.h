@@ -1,0 +1,156 @@
+/*
+ * mdevaluate_b200 -- C ABI of the B200 (sm_100a) shifted-correlation path.
+ *
+ * The reference (mdevaluate, pure Python) has no FFI: its boundary for this path
+ * is three Python call protocols.  This header is the
+ * drop-in boundary underneath them: every entry point below replaces one NumPy
+ * loop of the reference and is what a maintainer would bind with ctypes (see
+ * INTEGRATION.md).  Rules of the ABI:
+ *
+ *   - plain `extern "C"`, pointers + sizes only, no C++/torch types;
+ *   - every function returns an `mdb_status` (0 = ok); nothing throws; the text
+ *     of the last error of the calling thread is `mdb_last_error()`;
+ *   - pointers documented as DEVICE are CUDA device pointers owned by the caller
+ *     and stay valid until the stream has drained; HOST pointers are read before
+ *     the call returns;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream); all
+ *     work is enqueued on it and the call does not synchronise unless stated;
+ *   - no hidden global state: calls are re-entrant per stream.
+ *
+ * Reference lines are relative to /root/reference/mdevaluate/.
+ */
+#ifndef MDEVALUATE_B200_H
+#define MDEVALUATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB_ABI_VERSION 1
+
+typedef enum mdb_status {
+    MDB_OK = 0,
+    MDB_ERR_ARGUMENT = 1,     /* NULL / negative size / misaligned / inconsistent arguments */
+    MDB_ERR_CUDA = 2,         /* a CUDA runtime call failed (text in mdb_last_error) */
+    MDB_ERR_UNSUPPORTED = 3,  /* valid request this build has no kernel for */
+    MDB_ERR_WORKSPACE = 4     /* workspace missing or too small */
+} mdb_status;
+
+/* coordinate element type */
+#define MDB_F32 0
+#define MDB_F64 1
+
+/* what one correlation launch accumulates per (origin, lag) */
+#define MDB_SUM_R2   1   /* sum_i |dr_i|^2              -> msd            correlation.py:203-208 */
+#define MDB_SUM_R4   2   /* sum_i |dr_i|^4              -> non_gaussian   correlation.py:355-362 */
+#define MDB_SUM_SINC 4   /* sum_i sin(q r_i)/(q r_i)    -> isf            correlation.py:211-220 */
+#define MDB_HIST     8   /* histogram of r_i            -> van_hove_self  correlation.py:239-248 */
+
+/* histogram binning rule (utils.py:328-338) */
+#define MDB_BINS_UNIFORM 0  /* bins.min()==0 and equal widths: bin = floor_divide(r, dx), r >= n_bins*dx dropped */
+#define MDB_BINS_EDGES   1  /* np.histogram(r, bins): half-open bins, last bin closed, outside dropped        */
+
+const char *mdb_last_error(void);
+int mdb_abi_version(void);
+
+/* Number of SMs / compute capability of the current device. */
+int mdb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Correlation over many origins and lags.
+ *
+ * Replaces the S x L Python loop of `shifted_correlation` (correlation.py:147-149,190-199)
+ * together with the per-pair kernels msd / isf / van_hove_self / non_gaussian
+ * (correlation.py:203-220,239-248,355-362) for one shard of atoms.
+ *
+ * Storage: `coords` is a row-major block of frame rows, row r = `coords + r*pitch` holding
+ * `3*n_atoms` interleaved xyz values (float32 as delivered by a trajectory reader, or float64
+ * for already unwrapped frames).  With `images` != NULL every row also has int8 cumulative
+ * periodic image counts n (row r at `images + r*img_pitch`, 3*n_atoms bytes) and a box diagonal
+ * `box[3*r .. 3*r+2]`; the kernels then use the unwrapped position  x - n*box  evaluated in
+ * float64, which is exactly the float64 frame `pbc.nojump` returns (pbc.py:235-247).
+ *
+ * `rows[s*n_lags + l]` is the storage row of frame  start_frames[s] + idx[l]; entry l == 0 is
+ * the origin of segment s (correlation.py:21-24: the origin is correlated with itself first).
+ *
+ * Output: `sums[(s*n_lags + l)*3 + {0,1,2}]` = sum over the shard's atoms of r^2, r^4 and
+ * sinc(q r) (unrequested slots are 0); `hist[(s*n_lags + l)*n_bins + b]` = integer counts.
+ * Division by N, the alpha_2 ratio, the average over origins and the variance for chi4 are
+ * done by the caller AFTER shards have been summed (correlation.py:194-199 averages values
+ * per origin, not moments).  Results are bit-reproducible run to run.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mdb_corr_args {
+    const void *coords;          /* DEVICE [n_rows][pitch] of coord_type                        */
+    int64_t pitch;               /* elements per row, >= 3*n_atoms                              */
+    int32_t coord_type;          /* MDB_F32 or MDB_F64                                           */
+    const int8_t *images;        /* DEVICE [n_rows][img_pitch] or NULL (raw / pre-unwrapped)     */
+    int64_t img_pitch;           /* bytes per image row, >= 3*n_atoms                            */
+    const double *box;           /* DEVICE [n_rows][3] box diagonals; required iff images        */
+    int32_t n_atoms;             /* atoms of this shard                                          */
+    int32_t n_origins;           /* S                                                            */
+    int32_t n_lags;              /* L                                                            */
+    const int32_t *rows;         /* DEVICE [S*L] storage row per (origin, lag)                   */
+    int32_t flags;               /* MDB_SUM_* | MDB_HIST                                         */
+    double q;                    /* scattering vector length for MDB_SUM_SINC                    */
+    int32_t n_bins;              /* B, for MDB_HIST                                              */
+    int32_t bin_mode;            /* MDB_BINS_UNIFORM / MDB_BINS_EDGES                            */
+    double dx;                   /* uniform bin width (np.diff(bins).mean())                     */
+    const double *edges;         /* DEVICE [B+1] bin edges for MDB_BINS_EDGES                    */
+    double *sums;                /* DEVICE out [S*L*3]                                           */
+    unsigned long long *hist;    /* DEVICE out [S*L*B] (zeroed by the call); NULL without HIST   */
+    void *workspace;             /* DEVICE scratch of mdb_corr_workspace_bytes()                 */
+    size_t workspace_bytes;
+} mdb_corr_args;
+
+int mdb_corr_workspace_bytes(const mdb_corr_args *args, size_t *bytes);
+int mdb_shifted_corr(const mdb_corr_args *args, void *stream);
+/* Number of kernel launches the last successful mdb_shifted_corr of this thread enqueued. */
+int mdb_corr_last_launches(void);
+/* Measurement aid: with profiling enabled (per calling thread) mdb_shifted_corr brackets its
+ * dominant kernel -- the correlation kernel, not the partial-sum reduction -- with CUDA events on
+ * the launch stream; mdb_corr_last_kernel_ms waits for that kernel and returns its duration. */
+int mdb_corr_profile(int enable);
+int mdb_corr_last_kernel_ms(float *ms);
+
+/* ------------------------------------------------------------------------------------------
+ * nojump, producer side: periodic-jump detection + running image count.
+ *
+ * Replaces `reader.parse_jumps` (reader.py:165-186: J_t = round((x_t - x_{t-1}) / box_0) as
+ * int8, round-half-even, float32 arithmetic when positions and box are float32) and the prefix
+ * sum `m[i0:step+1].sum(axis=0)` inside `pbc.nojump` (pbc.py:235-237).  A trajectory may be
+ * passed in consecutive time segments: `prev` / `cum` carry the last frame and the running
+ * counts from one call to the next.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mdb_nojump_args {
+    const float *coords;         /* DEVICE [n_frames][pitch] wrapped positions of this segment   */
+    int64_t pitch;               /* floats per row, >= 3*n_atoms                                 */
+    int32_t n_frames;
+    int32_t n_atoms;
+    double box0[3];              /* box diagonal of trajectory frame 0 (reader.py:167)           */
+    int32_t box_is_f32;          /* 1: divide in float32 (float32 box), 0: in float64            */
+    int32_t first_segment;       /* 1: row 0 is trajectory frame 0 (compared with whole0/itself) */
+    const float *whole0;         /* DEVICE [3*n_atoms] frame0.whole, or NULL (= frame 0)         */
+    float *prev;                 /* DEVICE [3*n_atoms] in/out carry: last frame seen             */
+    int32_t *cum;                /* DEVICE [3*n_atoms] in/out carry: running image counts        */
+    const int32_t *out_row;      /* DEVICE [n_frames] destination row per frame, <0 = drop; NULL = identity */
+    int8_t *images;              /* DEVICE out, cumulative counts per kept frame, or NULL        */
+    int64_t img_pitch;           /* bytes per row of images / jumps                              */
+    int8_t *jumps;               /* DEVICE out, per-step jumps J_t per kept frame, or NULL       */
+    float *coords_out;           /* DEVICE out, copy of kept frames (compaction), or NULL        */
+    int64_t pitch_out;           /* floats per row of coords_out                                 */
+    int32_t *overflow;           /* DEVICE int, set to 1 if a running count left int8 range      */
+} mdb_nojump_args;
+
+int mdb_nojump_scan(const mdb_nojump_args *args, void *stream);
+
+/* nojump, consumer side (pbc.py:235-247): out = x - n*box in float64 for one frame row. */
+int mdb_nojump_apply(const float *coords_row, const int8_t *images_row, const double box[3],
+                     int32_t n_atoms, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDEVALUATE_B200_H */

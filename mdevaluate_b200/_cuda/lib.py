@@ -1,0 +1,123 @@
+"""ctypes binding of libmdevaluate_b200.so (the C ABI in include/mdevaluate_b200.h).
+
+There is no CPU fallback: if the shared library cannot be loaded (and cannot be
+built because nvcc is absent) every compute entry point raises ``CudaPathError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libmdevaluate_b200.so')
+
+# flags (keep in sync with include/mdevaluate_b200.h)
+F32, F64 = 0, 1
+SUM_R2, SUM_R4, SUM_SINC, HIST = 1, 2, 4, 8
+BINS_UNIFORM, BINS_EDGES = 0, 1
+ABI_VERSION = 1
+
+EXPORTS = (
+    'mdb_last_error', 'mdb_abi_version', 'mdb_device_info',
+    'mdb_corr_workspace_bytes', 'mdb_shifted_corr', 'mdb_corr_last_launches',
+    'mdb_corr_profile', 'mdb_corr_last_kernel_ms',
+    'mdb_nojump_scan', 'mdb_nojump_apply',
+)
+
+
+class CudaPathError(RuntimeError):
+    """The CUDA path is unavailable or a C-ABI call failed."""
+
+
+class CorrArgs(C.Structure):
+    _fields_ = [
+        ('coords', C.c_void_p), ('pitch', C.c_int64), ('coord_type', C.c_int32),
+        ('images', C.c_void_p), ('img_pitch', C.c_int64), ('box', C.c_void_p),
+        ('n_atoms', C.c_int32), ('n_origins', C.c_int32), ('n_lags', C.c_int32),
+        ('rows', C.c_void_p), ('flags', C.c_int32), ('q', C.c_double),
+        ('n_bins', C.c_int32), ('bin_mode', C.c_int32), ('dx', C.c_double), ('edges', C.c_void_p),
+        ('sums', C.c_void_p), ('hist', C.c_void_p),
+        ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+class NojumpArgs(C.Structure):
+    _fields_ = [
+        ('coords', C.c_void_p), ('pitch', C.c_int64), ('n_frames', C.c_int32), ('n_atoms', C.c_int32),
+        ('box0', C.c_double * 3), ('box_is_f32', C.c_int32), ('first_segment', C.c_int32),
+        ('whole0', C.c_void_p), ('prev', C.c_void_p), ('cum', C.c_void_p), ('out_row', C.c_void_p),
+        ('images', C.c_void_p), ('img_pitch', C.c_int64), ('jumps', C.c_void_p),
+        ('coords_out', C.c_void_p), ('pitch_out', C.c_int64), ('overflow', C.c_void_p),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    lib.mdb_last_error.restype = C.c_char_p
+    lib.mdb_last_error.argtypes = []
+    lib.mdb_abi_version.restype = C.c_int
+    lib.mdb_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+    lib.mdb_corr_workspace_bytes.argtypes = [C.POINTER(CorrArgs), C.POINTER(C.c_size_t)]
+    lib.mdb_shifted_corr.argtypes = [C.POINTER(CorrArgs), C.c_void_p]
+    lib.mdb_corr_last_launches.restype = C.c_int
+    lib.mdb_corr_profile.argtypes = [C.c_int]
+    lib.mdb_corr_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
+    lib.mdb_nojump_scan.argtypes = [C.POINTER(NojumpArgs), C.c_void_p]
+    lib.mdb_nojump_apply.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_void_p,
+                                     C.c_void_p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ('mdb_abi_version', 'mdb_corr_last_launches'):
+            fn.restype = C.c_int
+
+
+def load(build_if_missing=True):
+    """Load (building first if the library is absent and nvcc exists) and return the CDLL."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH) and build_if_missing:
+            try:
+                from ..csrc.build import build
+                build()
+            except Exception as exc:  # pragma: no cover - depends on toolchain
+                raise CudaPathError(
+                    'libmdevaluate_b200.so is missing and could not be built (%s); run '
+                    '`python -m mdevaluate_b200.csrc.build`. There is no CPU fallback.' % exc) from exc
+        if not os.path.exists(LIB_PATH):
+            raise CudaPathError('libmdevaluate_b200.so not found at %s; there is no CPU fallback' % LIB_PATH)
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as exc:
+            raise CudaPathError('cannot load %s: %s' % (LIB_PATH, exc)) from exc
+        missing = [n for n in EXPORTS if not hasattr(lib, n)]
+        if missing:
+            raise CudaPathError('libmdevaluate_b200.so lacks symbols: %s' % ', '.join(missing))
+        _declare(lib)
+        if lib.mdb_abi_version() != ABI_VERSION:
+            raise CudaPathError('ABI version mismatch: library %d, binding %d'
+                                % (lib.mdb_abi_version(), ABI_VERSION))
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mdb_last_error()
+        raise CudaPathError('%s failed (status %d): %s' % (what, rc, msg.decode() if msg else ''))
+
+
+def require_cuda():
+    """Torch with a visible CUDA device, or a loud error (no CPU fallback on the product path)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise CudaPathError('no CUDA device visible: mdevaluate_b200 has no CPU fallback '
+                            '(the CPU oracle lives in oracle/ and is test infrastructure only)')
+    return torch

@@ -1,0 +1,297 @@
+"""Bringing a trajectory into HBM: dense residency, compaction of needed frames, nojump scan.
+
+One ``Resident`` exists per (reader, atom selection).  It answers "give me a DeviceStore that
+holds these frames (with image counts if nojump)" with the cheapest of:
+
+* dense   -- every frame of the trajectory is (or is made) resident; image counts for every
+             frame come from ONE scan over the trajectory.  Chosen when it fits the memory budget
+             (always for a trajectory that already lives in HBM).
+* compact -- only the frames a schedule touches are kept.  The trajectory is streamed through
+             the GPU in time segments (pinned host memory -> HBM, copy overlapped with the scan of
+             the previous segment); the scan carries (prev, cum) across segments and writes the
+             kept frames and their image counts straight into the compact store.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine
+from . import lib as _lib
+from ..logging import logger
+
+
+def _mem_budget(torch, device):
+    free, _total = torch.cuda.mem_get_info(device)
+    return int(free * 0.70)
+
+
+class Resident:
+    SEGMENT_BYTES = 512 << 20        # staging buffer per stream slot for host -> HBM streaming
+
+    def __init__(self, reader, atom_filter, device=None):
+        torch = _lib.require_cuda()
+        self.reader = reader
+        self.n_frames = len(reader)
+        first = reader[0].positions
+        m_all = len(first)
+        self.atom_filter = None
+        if atom_filter is not None:
+            atom_filter = np.asarray(atom_filter)
+            if atom_filter.dtype == bool:
+                if not atom_filter.all():
+                    self.atom_filter = np.nonzero(atom_filter)[0]
+            else:
+                self.atom_filter = atom_filter.astype(np.int64)
+        self.n_atoms = m_all if self.atom_filter is None else len(self.atom_filter)
+        self.dtype = np.asarray(first).dtype
+        block = getattr(reader, 'device_block', None)
+        if device is None:
+            device = block.device if block is not None else torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.pitch = engine.row_pitch(self.n_atoms)
+        self._dense = None              # DeviceStore with all frames (raw)
+        self._dense_images = False
+        self._compact = {}              # (mode, hash of frame ids) -> DeviceStore
+        self.force_compact = False
+
+    # -- box / time helpers --------------------------------------------------------------------
+    def _box_of(self, i):
+        if hasattr(self.reader, 'box_of'):
+            return np.asarray(self.reader.box_of(i))
+        return np.asarray(self.reader[i].box).diagonal()
+
+    def _box_rows(self, frame_ids):
+        torch = _lib.require_cuda()
+        if getattr(self.reader, 'box_constant', False):
+            b = np.tile(np.asarray(self.reader.box_diag, dtype=np.float64), (len(frame_ids), 1))
+        else:
+            b = np.stack([np.asarray(self._box_of(int(i)), dtype=np.float64) for i in frame_ids])
+        return torch.from_numpy(np.ascontiguousarray(b)).to(self.device)
+
+    # -- segment source: a device float32 (n, pitch') view of frames [t0, t1) -------------------
+    def _segment_frames(self):
+        per_frame = self.pitch * 4
+        return max(1, min(self.n_frames, self.SEGMENT_BYTES // per_frame))
+
+    def _host_segment(self, t0, t1, out):
+        """Fill pinned ``out[:t1-t0, :3N]`` with frames [t0, t1) of the selected atoms."""
+        n3 = 3 * self.n_atoms
+        block = getattr(self.reader, 'host_block', None)
+        view = out[:t1 - t0, :n3].numpy().reshape(t1 - t0, self.n_atoms, 3)
+        if block is not None:
+            if self.atom_filter is None:
+                np.copyto(view, block[t0:t1], casting='same_kind')
+            else:
+                np.take(block[t0:t1], self.atom_filter, axis=1, out=view)
+        else:
+            for t in range(t0, t1):
+                pos = np.asarray(self.reader[t].positions)
+                view[t - t0] = pos if self.atom_filter is None else pos[self.atom_filter]
+
+    def _segments(self):
+        """Yield ``(t0, t1, device_tensor)`` over the whole trajectory, double-buffered."""
+        torch = _lib.require_cuda()
+        block = getattr(self.reader, 'device_block', None)
+        if block is not None and self.atom_filter is None and block.dtype == torch.float32:
+            seg = max(1, min(self.n_frames, (2 << 30) // (block.stride(0) * 4)))
+            for t0 in range(0, self.n_frames, seg):
+                t1 = min(self.n_frames, t0 + seg)
+                yield t0, t1, block[t0:t1]
+            return
+        if self.dtype != np.float32:
+            raise _lib.CudaPathError('nojump needs float32 wrapped positions (got %s)' % self.dtype)
+        seg = self._segment_frames()
+        main = torch.cuda.current_stream(self.device)
+        copy_stream = torch.cuda.Stream(self.device)
+        n3 = 3 * self.n_atoms
+        direct = None
+        host_block = getattr(self.reader, 'host_block', None)
+        if host_block is not None and self.atom_filter is None and host_block.flags.c_contiguous:
+            as_t = torch.from_numpy(host_block).view(self.n_frames, n3)
+            if as_t.is_pinned():
+                direct = as_t
+        pinned = ([] if direct is not None else
+                  [torch.empty((seg, self.pitch), dtype=torch.float32).pin_memory() for _ in range(2)])
+        staged = [torch.empty((seg, self.pitch), dtype=torch.float32, device=self.device) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        starts = list(range(0, self.n_frames, seg))
+
+        def issue(k):
+            slot = k % 2
+            t0 = starts[k]
+            t1 = min(self.n_frames, t0 + seg)
+            if k >= 2:
+                consumed[slot].synchronize()      # host buffer and device slot are free again
+            with torch.cuda.stream(copy_stream):
+                if direct is not None:
+                    # the trajectory itself is page-locked: DMA straight out of it
+                    staged[slot][:t1 - t0, :n3].copy_(direct[t0:t1], non_blocking=True)
+                else:
+                    self._host_segment(t0, t1, pinned[slot])
+                    staged[slot][:t1 - t0].copy_(pinned[slot][:t1 - t0], non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        if starts:
+            issue(0)
+        for k, t0 in enumerate(starts):
+            slot = k % 2
+            t1 = min(self.n_frames, t0 + seg)
+            if k + 1 < len(starts):
+                issue(k + 1)
+            main.wait_event(ready[slot])
+            yield t0, t1, staged[slot][:t1 - t0]
+            consumed[slot].record(main)
+        main.synchronize()
+
+    # -- dense residency -------------------------------------------------------------------------
+    def _dense_bytes(self, with_images):
+        per = self.pitch * 4 + (self.pitch if with_images else 0)
+        return per * self.n_frames
+
+    def _ensure_dense(self):
+        torch = _lib.require_cuda()
+        if self._dense is not None:
+            return self._dense
+        block = getattr(self.reader, 'device_block', None)
+        if block is not None and self.atom_filter is None:
+            coords = block
+        else:
+            if self.dtype not in (np.float32, np.float64):
+                raise _lib.CudaPathError('positions must be float32 or float64')
+            tdt = torch.float32 if self.dtype == np.float32 else torch.float64
+            coords = torch.empty((self.n_frames, self.pitch), dtype=tdt, device=self.device)
+            if tdt == torch.float32:
+                for t0, t1, seg in self._segments():
+                    coords[t0:t1].copy_(seg, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+            else:
+                n3 = 3 * self.n_atoms
+                for t in range(self.n_frames):
+                    pos = np.asarray(self.reader[t].positions)
+                    pos = pos if self.atom_filter is None else pos[self.atom_filter]
+                    coords[t, :n3] = torch.from_numpy(np.ascontiguousarray(pos).reshape(-1)).to(self.device)
+        self._dense = engine.DeviceStore(coords, self.n_atoms, n_frames=self.n_frames)
+        return self._dense
+
+    def _scan_all(self, images=None, jumps=None, out_row=None, coords_out=None):
+        """Run the jump scan over the whole trajectory (segment by segment, carrying state)."""
+        torch = _lib.require_cuda()
+        n3 = 3 * self.n_atoms
+        prev = torch.zeros((n3,), dtype=torch.float32, device=self.device)
+        cum = torch.zeros((n3,), dtype=torch.int32, device=self.device)
+        overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        box0 = self._box_of(0)
+        box_is_f32 = box0.dtype == np.float32
+        dense = self._dense
+        if dense is not None and dense.coords.dtype == torch.float32:
+            source = ((0, self.n_frames, dense.coords),)
+        else:
+            source = self._segments()
+        for t0, t1, seg in source:
+            rows = None
+            if out_row is not None:
+                rows = out_row[t0:t1]
+                img_seg, jmp_seg = images, jumps
+            else:
+                img_seg = images[t0:t1] if images is not None else None
+                jmp_seg = jumps[t0:t1] if jumps is not None else None
+            engine.nojump_scan(seg, self.n_atoms, box0, box_is_f32, prev, cum, first_segment=(t0 == 0),
+                               images=img_seg, jumps=jmp_seg, out_row=rows, coords_out=coords_out,
+                               overflow=overflow)
+        if int(overflow.item()):
+            raise _lib.CudaPathError('an atom crossed more than 127 periodic images; int8 image counts overflow')
+
+    def _ensure_dense_images(self):
+        torch = _lib.require_cuda()
+        store = self._ensure_dense()
+        if store.images is None:
+            if store.coords.dtype != torch.float32:
+                raise _lib.CudaPathError('nojump needs float32 wrapped positions')
+            images = torch.empty((self.n_frames, self.pitch), dtype=torch.int8, device=self.device)
+            self._scan_all(images=images)
+            store.images = images
+            store.box = self._box_rows(range(self.n_frames))
+        return store
+
+    def dense_jumps(self):
+        """Per-step jumps of every frame as a host int8 array (T, N, 3) -- for parse_jumps."""
+        torch = _lib.require_cuda()
+        n3 = 3 * self.n_atoms
+        jumps = torch.empty((self.n_frames, self.pitch), dtype=torch.int8, device=self.device)
+        self._scan_all(jumps=jumps)
+        return jumps[:, :n3].cpu().numpy().reshape(self.n_frames, self.n_atoms, 3)
+
+    # -- compact residency -------------------------------------------------------------------------
+    def _build_compact(self, frame_ids, nojump):
+        torch = _lib.require_cuda()
+        frame_ids = np.asarray(frame_ids, dtype=np.int64)
+        n_rows = len(frame_ids)
+        f2r = np.full((self.n_frames,), -1, dtype=np.int32)
+        f2r[frame_ids] = np.arange(n_rows, dtype=np.int32)
+        n3 = 3 * self.n_atoms
+        if nojump:
+            coords = torch.empty((n_rows, self.pitch), dtype=torch.float32, device=self.device)
+            images = torch.empty((n_rows, self.pitch), dtype=torch.int8, device=self.device)
+            out_row = torch.from_numpy(f2r).to(self.device)
+            self._scan_all(images=images, out_row=out_row, coords_out=coords)
+            store = engine.DeviceStore(coords, self.n_atoms, images=images, box=self._box_rows(frame_ids),
+                                       frame_to_row=f2r, n_frames=self.n_frames)
+        else:
+            tdt = torch.float32 if self.dtype == np.float32 else torch.float64
+            coords = torch.empty((n_rows, self.pitch), dtype=tdt, device=self.device)
+            block = getattr(self.reader, 'device_block', None)
+            if block is not None and self.atom_filter is None:
+                idx = torch.from_numpy(frame_ids).to(self.device)
+                w = min(block.shape[1], self.pitch)
+                coords[:, :w] = block.index_select(0, idx)[:, :w]
+            else:
+                chunk = max(1, (256 << 20) // (self.pitch * coords.element_size()))
+                host = torch.empty((min(chunk, n_rows), self.pitch), dtype=tdt).pin_memory()
+                for r0 in range(0, n_rows, chunk):
+                    r1 = min(n_rows, r0 + chunk)
+                    view = host[:r1 - r0, :n3].numpy().reshape(r1 - r0, self.n_atoms, 3)
+                    for r in range(r0, r1):
+                        pos = np.asarray(self.reader[int(frame_ids[r])].positions)
+                        view[r - r0] = pos if self.atom_filter is None else pos[self.atom_filter]
+                    coords[r0:r1].copy_(host[:r1 - r0], non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()
+            store = engine.DeviceStore(coords, self.n_atoms, frame_to_row=f2r, n_frames=self.n_frames)
+        return store
+
+    # -- public ---------------------------------------------------------------------------------
+    def store_for(self, frame_ids, nojump):
+        """A DeviceStore holding (at least) ``frame_ids``; with image counts if ``nojump``."""
+        torch = _lib.require_cuda()
+        frame_ids = np.unique(np.asarray(frame_ids, dtype=np.int64))
+        if frame_ids.size and (frame_ids[0] < 0 or frame_ids[-1] >= self.n_frames):
+            raise IndexError('frame index out of range')
+        if not self.force_compact:
+            block = getattr(self.reader, 'device_block', None)
+            on_device = self._dense is not None or (block is not None and self.atom_filter is None)
+            have_images = self._dense is not None and self._dense.images is not None
+            extra = 0 if on_device else self._dense_bytes(False)
+            if nojump and not have_images:
+                extra += self.pitch * self.n_frames
+            if extra <= _mem_budget(torch, self.device):
+                return self._ensure_dense_images() if nojump else self._ensure_dense()
+        key = ('nojump' if nojump else 'raw', hash(frame_ids.tobytes()))
+        store = self._compact.get(key)
+        if store is None:
+            logger.debug('building compact store of %d frames (nojump=%s)', len(frame_ids), nojump)
+            self._compact.clear()        # one compact store at a time: they are large
+            store = self._build_compact(frame_ids, nojump)
+            self._compact[key] = store
+        return store
+
+    def unwrapped_frame(self, i):
+        """float64 (N, 3) nojump frame ``x - n*box`` (pbc.py:235-247) as a host array."""
+        store = self.store_for([i], nojump=True)
+        row = int(store.rows_for([i])[0])
+        n3 = 3 * self.n_atoms
+        out = engine.nojump_apply(store.coords[row], store.images[row], store.box[row].cpu().numpy(), self.n_atoms)
+        return out.cpu().numpy().reshape(self.n_atoms, 3)
+
+    def raw_frame(self, i):
+        pos = np.asarray(self.reader[i].positions)
+        return pos if self.atom_filter is None else pos[self.atom_filter]

@@ -1,0 +1,192 @@
+"""Coordinates / CoordinateFrame: the frames protocol ``shifted_correlation`` consumes.
+
+Mirrors the part of mdevaluate/coordinates.py the hot path touches (``CoordinateFrame``
+105-189, ``Coordinates`` 192-311): ``len`` is the FULL trajectory length even for a sliced
+object (292-293), ``coords[i]`` is a ``CoordinateFrame`` with ``.time/.box/.step/.mode``,
+``coords[a:b:c]`` is a copy carrying ``_slice`` (286-290), ``coords.nojump`` is a copy in
+``'nojump'`` mode (199-215).  Selections, maps and KD-trees are out of scope.
+
+Frames handed back to Python are host NumPy arrays; the correlation kernels never go through
+them -- ``shifted_correlation`` asks ``_resident()`` for the HBM store directly.
+"""
+from copy import copy
+
+import numpy as np
+
+from .logging import logger
+from .pbc import nojump
+
+
+class UnknownCoordinatesMode(Exception):
+    pass
+
+
+class CoordinateFrame(np.ndarray):
+    _known_modes = ('pbc', 'whole', 'nojump')
+
+    @property
+    def box(self):
+        return np.array(self.coordinates.frames[self.step].box)
+
+    @property
+    def volume(self):
+        return self.box.diagonal().cumprod()[-1]
+
+    @property
+    def time(self):
+        return self.coordinates.frames[self.step].time
+
+    @property
+    def selection(self):
+        return self.coordinates.atom_filter
+
+    @property
+    def pbc(self):
+        frame = self % self.box.diagonal()
+        frame.mode = 'pbc'
+        return frame
+
+    @property
+    def whole(self):
+        # single-atom residues: ``whole`` is the identity (pbc.py:163-209 only moves bonded atoms)
+        frame = self.copy()
+        frame.mode = 'whole'
+        return frame
+
+    @property
+    def nojump(self):
+        if self.mode != 'nojump':
+            if self.mode is not None:
+                logger.warning('Combining Nojump with other Coordinate modes is not supported and '
+                               'may cause unexpected results.')
+            frame = nojump(self)
+            frame.mode = 'nojump'
+            return frame
+        return self
+
+    def __new__(subtype, shape, dtype=float, buffer=None, offset=0, strides=None, order=None,
+                coordinates=None, step=None, box=None, mode=None):
+        obj = np.ndarray.__new__(subtype, shape, dtype, buffer, offset, strides)
+        obj.coordinates = coordinates
+        obj.step = step
+        obj.mode = mode
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.coordinates = getattr(obj, 'coordinates', None)
+        self.step = getattr(obj, 'step', None)
+        self.mode = getattr(obj, 'mode', None)
+
+
+class Coordinates:
+    """Trajectory data for the evaluation functions, backed by an HBM store.
+
+    Args:
+        frames: a reader (``len``, ``reader[i].positions/.box/.time``), e.g. ``reader.MemoryReader``
+        atom_filter (opt.): boolean mask or index array selecting atoms
+        atom_subset (opt.): object with a ``.selection`` mask (the reference's AtomSubset)
+        mode (opt.): ``None`` or ``'nojump'``
+    """
+
+    def __init__(self, frames, atom_filter=None, atom_subset=None, mode=None):
+        self._mode = mode
+        self.frames = frames
+        self._slice = slice(None)
+        self.comm = None            # set by parallel.shard_atoms: (process group, global atom count)
+        assert atom_filter is None or atom_subset is None, "Cannot use both: subset and filter"
+        if atom_filter is not None:
+            self.atom_filter = np.asarray(atom_filter)
+            self.atom_subset = None
+        elif atom_subset is not None:
+            self.atom_filter = np.asarray(atom_subset.selection)
+            self.atom_subset = atom_subset
+            self.atoms = getattr(atom_subset, 'atoms', None)
+        else:
+            self.atom_filter = np.ones(shape=(len(frames[0].coordinates),), dtype=bool)
+            self.atom_subset = None
+
+    @classmethod
+    def from_arrays(cls, positions, box, times=None, n_atoms=None, mode=None):
+        """Build Coordinates over an in-memory trajectory (host NumPy or a CUDA tensor)."""
+        from .reader import MemoryReader
+        return cls(MemoryReader(positions, box, times, n_atoms=n_atoms), mode=mode)
+
+    # -- modes ------------------------------------------------------------------------------
+    def get_mode(self, mode):
+        if mode not in (None, 'nojump'):
+            raise UnknownCoordinatesMode('mode %r is outside the CUDA path (only None / nojump)' % (mode,))
+        other = copy(self)
+        other._mode = mode
+        return other
+
+    @property
+    def nojump(self):
+        return self.get_mode('nojump')
+
+    @property
+    def mode(self):
+        return self._mode
+
+    @mode.setter
+    def mode(self, val):
+        if val in CoordinateFrame._known_modes:
+            logger.warning('Changing the Coordinates mode directly is deprecated. '
+                           'Use Coordinates.%s instead, which returns a copy.', val)
+            if val != 'nojump':
+                raise UnknownCoordinatesMode('mode %r is outside the CUDA path' % (val,))
+            self._mode = val
+        else:
+            raise UnknownCoordinatesMode('No such mode: {}'.format(val))
+
+    # -- HBM residency ------------------------------------------------------------------------
+    def _resident(self):
+        """The HBM residency manager shared by every view of (reader, selection)."""
+        from ._cuda.resident import Resident
+        cache = self.frames.__dict__.setdefault('_mdb_resident', {}) if hasattr(self.frames, '__dict__') else {}
+        key = hash(np.asarray(self.atom_filter).tobytes()) if self.atom_filter is not None else None
+        res = cache.get(key)
+        if res is None:
+            res = Resident(self.frames, self.atom_filter)
+            cache[key] = res
+        return res
+
+    # -- frames protocol ----------------------------------------------------------------------
+    def get_frame(self, fnr):
+        fnr = int(fnr)
+        n = len(self)
+        if not -n <= fnr < n:
+            raise IndexError('frame %d out of range' % fnr)
+        pos = np.asarray(self.frames[fnr].positions)
+        if self.atom_filter is not None:
+            pos = pos[self.atom_filter]
+        frame = pos.view(CoordinateFrame)
+        frame.coordinates = self
+        frame.step = fnr
+        if self.mode is not None:
+            frame = getattr(frame, self.mode)
+        return frame
+
+    def __iter__(self):
+        for i in range(len(self))[self._slice]:
+            yield self[i]
+
+    def __getitem__(self, item):
+        if isinstance(item, slice):
+            sliced = copy(self)
+            sliced._slice = item
+            return sliced
+        return self.get_frame(item)
+
+    def __len__(self):
+        return len(self.frames)
+
+    def __repr__(self):
+        return "Coordinates <{}>: {} atoms, mode={}".format(
+            getattr(self.frames, 'filename', '?'), int(np.count_nonzero(self.atom_filter))
+            if self.atom_filter.dtype == bool else len(self.atom_filter), self._mode)
+
+    @property
+    def description(self):
+        return getattr(self.atom_subset, 'description', '')

@@ -1,0 +1,348 @@
+"""``shifted_correlation`` and its per-atom correlation functions on the B200.
+
+Drop-in for the part of mdevaluate/correlation.py that SURVEY.md section 8 puts on the hot path:
+``shifted_correlation`` (86-201), ``log_indices`` (16-18), the ``correlation`` strategy (21-24),
+``msd`` (203-208), ``isf`` (211-220), ``van_hove_self`` (239-248), ``non_gaussian`` (355-362) and
+the chi4 recipe of examples/plot_chi4.py:29-37.
+
+The schedule (origins, lags, times) is computed on the host with the SAME NumPy expressions as
+the reference, so it is reproduced bit for bit.  The S x L x N evaluation loop runs in ONE CUDA
+launch (csrc/corr_kernels.cu) that returns per-(origin, lag) sums; ratios, 1/N, the average over
+origins and variances are taken afterwards, as the reference averages function values per origin
+(correlation.py:191-199), not moments.
+
+There is no CPU fallback: functions other than the four kernels (or a custom ``correlation``
+strategy) raise ``NotImplementedError``; a missing CUDA library or device raises
+``CudaPathError``.
+"""
+from __future__ import annotations
+
+import functools
+from itertools import chain
+
+import numpy as np
+
+from ._cuda import engine
+from ._cuda import lib as _lib
+from ._cuda.lib import CudaPathError  # noqa: F401  (re-exported)
+from .utils import bin_rule, runningmean  # noqa: F401
+
+__all__ = ['log_indices', 'correlation', 'shifted_correlation', 'msd', 'isf', 'van_hove_self',
+           'non_gaussian', 'chi4', 'shifted_correlation_multi']
+
+
+# --------------------------------------------------------------------------------------------
+# schedule
+# --------------------------------------------------------------------------------------------
+def log_indices(first, last, num=100):
+    """Logarithmically spaced integer lags in ``[first, last]`` (correlation.py:16-18)."""
+    ls = np.logspace(0, np.log10(last - first + 1), num=num)
+    return np.unique(np.int_(ls) - 1 + first)
+
+
+def correlation(function, frames):
+    """The default pairing strategy: first frame of ``frames`` against all, itself first
+    (correlation.py:21-24).  ``shifted_correlation`` recognises this object and runs the whole
+    origin x lag loop on the GPU; calling it directly evaluates pair by pair (each pair is one
+    small kernel launch)."""
+    iterator = iter(frames)
+    start_frame = next(iterator)
+    return map(lambda f: function(start_frame, f), chain([start_frame], iterator))
+
+
+# --------------------------------------------------------------------------------------------
+# the four per-atom functions: markers for shifted_correlation, GPU-evaluated when called
+# --------------------------------------------------------------------------------------------
+def msd(start, frame):
+    """Mean square displacement (correlation.py:203-208)."""
+    return _pair_value(_Spec('msd'), start, frame)
+
+
+def isf(start, frame, q, box=None):
+    """Incoherent intermediate scattering function, isotropic average ``sin(qr)/(qr)``
+    (correlation.py:211-220).  Bind ``q`` with ``functools.partial(isf, q=22.7)``."""
+    return _pair_value(_Spec('isf', q=q), start, frame)
+
+
+def van_hove_self(start, end, bins):
+    """Self part of the van Hove function: histogram of ``|r_i(0) - r_i(t)|`` over ``bins``,
+    divided by the number of atoms (correlation.py:239-248)."""
+    return _pair_value(_Spec('van_hove_self', bins=bins), start, end)
+
+
+def non_gaussian(onset, frame):
+    """Non-Gaussian parameter ``3/5 <r^4>/<r^2>^2 - 1`` (correlation.py:355-362); NaN at lag 0."""
+    return _pair_value(_Spec('non_gaussian'), onset, frame)
+
+
+_KNOWN = {'msd': msd, 'isf': isf, 'van_hove_self': van_hove_self, 'non_gaussian': non_gaussian}
+
+
+class _Spec:
+    """A recognised correlation function with its bound parameters."""
+
+    def __init__(self, name, q=None, bins=None):
+        self.name = name
+        self.q = q
+        self.bins = None if bins is None else np.asarray(bins)
+        if name == 'isf':
+            if q is None:
+                raise TypeError("isf() missing required argument 'q' (bind it with functools.partial)")
+            self.corr = engine.CorrSpec(_lib.SUM_SINC, q=float(q))
+        elif name == 'msd':
+            self.corr = engine.CorrSpec(_lib.SUM_R2)
+        elif name == 'non_gaussian':
+            self.corr = engine.CorrSpec(_lib.SUM_R2 | _lib.SUM_R4)
+        elif name == 'van_hove_self':
+            if bins is None:
+                raise TypeError("van_hove_self() missing required argument 'bins'")
+            mode, dx, nb = bin_rule(self.bins)
+            self.corr = engine.CorrSpec(_lib.HIST, n_bins=nb, bin_mode=mode, dx=dx,
+                                        edges=self.bins.astype(np.float64))
+        else:  # pragma: no cover
+            raise NotImplementedError(name)
+
+    def finalize(self, sums, hist, n_atoms, float32):
+        """Per-(origin, lag) function values from the shard-summed kernel output."""
+        with np.errstate(divide='ignore', invalid='ignore'):
+            if self.name == 'msd':
+                out = sums[..., 0] / n_atoms
+            elif self.name == 'isf':
+                out = sums[..., 2] / n_atoms
+            elif self.name == 'non_gaussian':
+                m2 = sums[..., 0] / n_atoms
+                m4 = sums[..., 1] / n_atoms
+                out = 3 / 5 * m4 / m2 ** 2 - 1
+            else:
+                return 1 / n_atoms * hist          # always float64 (correlation.py:248)
+        # the reference computes in the frames' dtype: float32 frames give float32 results
+        return out.astype(np.float32) if float32 else out
+
+
+def _kernel_spec(function):
+    """Map a user callable (one of the four functions, possibly wrapped in ``partial``) to a _Spec."""
+    kwargs = {}
+    fn = function
+    while isinstance(fn, functools.partial):
+        if fn.args:
+            raise NotImplementedError('positional partial arguments are not supported; bind q / bins by keyword')
+        merged = dict(fn.keywords)
+        merged.update(kwargs)
+        kwargs = merged
+        fn = fn.func
+    name = getattr(fn, '__name__', None)
+    module = getattr(fn, '__module__', '') or ''
+    ours = _KNOWN.get(name) is fn
+    # the reference's own functions (and restatements of them) carry the same names
+    theirs = name in _KNOWN and (module.endswith('correlation') or module.endswith('md_oracle'))
+    if not (ours or theirs):
+        raise NotImplementedError(
+            'shifted_correlation on the B200 path supports msd, isf, van_hove_self and non_gaussian '
+            '(optionally via functools.partial); got %r. There is no CPU fallback.' % (function,))
+    kwargs.pop('box', None)      # isf's ``box`` argument is unused by the reference (correlation.py:211)
+    if name == 'isf':
+        extra = set(kwargs) - {'q'}
+    elif name == 'van_hove_self':
+        extra = set(kwargs) - {'bins'}
+    else:
+        extra = set(kwargs)
+    if extra:
+        raise TypeError('%s() got unexpected keyword arguments %s' % (name, sorted(extra)))
+    return _Spec(name, **kwargs)
+
+
+# --------------------------------------------------------------------------------------------
+# frame providers: where the frames come from
+# --------------------------------------------------------------------------------------------
+def _store_from_host_frames(frame_list):
+    """Upload a list of host (N, 3) arrays as the rows of a compact store (generic frames objects)."""
+    torch = _lib.require_cuda()
+    first = np.asarray(frame_list[0])
+    if first.ndim != 2 or first.shape[1] != 3:
+        raise ValueError('frames must be (N, 3) arrays')
+    dtype = np.float32 if first.dtype == np.float32 else np.float64
+    n_atoms = first.shape[0]
+    pitch = engine.row_pitch(n_atoms)
+    host = torch.zeros((len(frame_list), pitch), dtype=torch.float32 if dtype == np.float32 else torch.float64)
+    view = host[:, :3 * n_atoms].numpy().reshape(len(frame_list), n_atoms, 3)
+    for r, f in enumerate(frame_list):
+        f = np.asarray(f)
+        if f.shape != first.shape:
+            raise ValueError('all frames must have the same shape')
+        view[r] = f
+    dev = torch.device('cuda', torch.cuda.current_device())
+    return engine.DeviceStore(host.to(dev), n_atoms), dtype == np.float32
+
+
+def _provider(frames, frame_ids):
+    """Return ``(store, rows (S,L) int32, n_atoms, float32_results, comm)`` for the needed frames."""
+    from .coordinates import Coordinates
+    ids = np.asarray(frame_ids)
+    if isinstance(frames, Coordinates):
+        res = frames._resident()
+        nojump = frames.mode == 'nojump'
+        store = res.store_for(ids.ravel(), nojump=nojump)
+        if not nojump:
+            store = store.without_images()
+        rows = store.rows_for(ids)
+        float32 = (not nojump) and res.dtype == np.float32
+        return store, rows, res.n_atoms, float32, frames.comm
+    # generic frames protocol (coordinates.py:257-293): pull the needed frames through __getitem__
+    uniq, inverse = np.unique(ids.ravel(), return_inverse=True)
+    store, float32 = _store_from_host_frames([frames[int(i)] for i in uniq])
+    rows = inverse.reshape(ids.shape).astype(np.int32)
+    return store, rows, store.n_atoms, float32, getattr(frames, 'comm', None)
+
+
+def _times(frames, idx):
+    reader = getattr(frames, 'frames', None)
+    times = getattr(reader, 'times', None)
+    if times is not None:
+        return np.asarray(times)[idx] - np.asarray(times)[0]
+    return np.array([frames[int(i)].time for i in idx]) - frames[0].time       # correlation.py:151
+
+
+def _schedule(frames, index_distribution, segments, window, skip):
+    """Origins and lags, the reference's expressions verbatim (correlation.py:131-144)."""
+    if skip is None:
+        try:
+            skip = frames._slice.start / len(frames)
+        except (TypeError, AttributeError):
+            skip = 0
+    assert window + skip < 1
+
+    start_frames = np.unique(np.linspace(
+        len(frames) * skip, len(frames) * (1 - window),
+        num=segments, endpoint=False, dtype=int
+    ))
+    num_frames = int(len(frames) * (window))
+    idx = np.asarray(index_distribution(0, num_frames))
+    return start_frames, idx
+
+
+def _run(frames, frame_ids, specs):
+    """Kernel launch + shard reduction; returns host ``(sums, hist, n_atoms_global, float32)``."""
+    flags = 0
+    hist_spec = None
+    q = 0.0
+    for sp in specs:
+        flags |= sp.corr.flags
+        if sp.corr.flags & _lib.HIST:
+            if hist_spec is not None:
+                raise NotImplementedError('one histogram per launch')
+            hist_spec = sp.corr
+        if sp.corr.flags & _lib.SUM_SINC:
+            q = sp.corr.q
+    corr = engine.CorrSpec(flags, q=q)
+    if hist_spec is not None:
+        corr.n_bins, corr.bin_mode, corr.dx, corr.edges = (hist_spec.n_bins, hist_spec.bin_mode, hist_spec.dx,
+                                                           hist_spec.edges)
+    store, rows, n_atoms, float32, comm = _provider(frames, frame_ids)
+    sums, hist = engine.correlate_device(store, rows, corr)
+    if comm is not None:
+        from . import parallel
+        sums, hist, n_atoms = parallel.allreduce_partials(sums, hist, n_atoms, comm)
+    sums = sums.cpu().numpy()
+    hist = hist.cpu().numpy() if hist is not None else None
+    return sums, hist, n_atoms, float32
+
+
+def _average(values, n_origins, average):
+    if not average:
+        return values
+    result = 0
+    for row in values:                      # correlation.py:191-199: sequential sum, then / S
+        result = result + row
+    return result / n_origins
+
+
+def shifted_correlation(function, frames, index_distribution=log_indices, correlation=correlation,
+                        segments=10, window=0.5, skip=None, average=False,
+                        description=None, autoload=None):
+    """Calculate the time series of a correlation function over shifted time origins.
+
+    Same call as the reference (correlation.py:86-201); ``description`` / ``autoload`` are the
+    keyword arguments its autosave decorator accepts (autosave.py:157-158) and are ignored.
+
+    Returns ``(times, result)`` with ``result`` of shape ``(segments, lags[, bins])`` or, with
+    ``average=True``, ``(lags[, bins])``.
+    """
+    if correlation is not globals()['correlation']:
+        raise NotImplementedError('custom correlation strategies (subensemble / has_counter) are not on the '
+                                  'B200 path yet; there is no CPU fallback')
+    spec = _kernel_spec(function)
+    start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
+    frame_ids = start_frames[:, None] + idx[None, :]
+    if frame_ids.size and frame_ids.max() >= len(frames):
+        raise IndexError('shifted_correlation: frame %d beyond the trajectory (%d frames)'
+                         % (frame_ids.max(), len(frames)))
+    times = _times(frames, idx)
+    sums, hist, n_atoms, float32 = _run(frames, frame_ids, [spec])
+    values = spec.finalize(sums, hist, n_atoms, float32)
+    return times, _average(values, len(start_frames), average)
+
+
+def shifted_correlation_multi(functions, frames, index_distribution=log_indices, segments=10, window=0.5,
+                              skip=None, average=False):
+    """Several correlation functions over the SAME schedule from one pass over the coordinates.
+
+    Extension of the reference API: ``functions`` is a dict ``name -> callable``; the kernel
+    accumulates everything in one launch (e.g. van Hove histogram + non-Gaussian parameter,
+    BASELINE config 3).  Returns ``(times, {name: result})``.
+    """
+    specs = {k: _kernel_spec(f) for k, f in functions.items()}
+    start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
+    frame_ids = start_frames[:, None] + idx[None, :]
+    if frame_ids.size and frame_ids.max() >= len(frames):
+        raise IndexError('shifted_correlation: frame beyond the trajectory')
+    qs = {sp.q for sp in specs.values() if sp.name == 'isf'}
+    if len(qs) > 1:
+        raise NotImplementedError('one q per launch')
+    times = _times(frames, idx)
+    sums, hist, n_atoms, float32 = _run(frames, frame_ids, list(specs.values()))
+    out = {k: _average(sp.finalize(sums, hist, n_atoms, float32), len(start_frames), average)
+           for k, sp in specs.items()}
+    return times, out
+
+
+def chi4(frames, q, index_distribution=log_indices, segments=20, window=0.2, skip=0.1, smooth=None):
+    """Four-point susceptibility from the per-origin ISF spread (examples/plot_chi4.py:29-37):
+    ``N * Fqt.var(axis=0)`` of the non-averaged ISF; ``smooth=k`` applies ``runningmean(chi4, k)``."""
+    t, fqt = shifted_correlation(functools.partial(isf, q=q), frames, index_distribution=index_distribution,
+                                 segments=segments, window=window, skip=skip, average=False)
+    n_atoms = len(frames[0]) if getattr(frames, 'comm', None) is None else frames.comm[1]
+    x4 = n_atoms * fqt.var(axis=0)
+    if smooth:
+        return t, x4, runningmean(x4, smooth)
+    return t, x4
+
+
+# --------------------------------------------------------------------------------------------
+# direct pair evaluation (calling msd(a, b) etc. like plain functions)
+# --------------------------------------------------------------------------------------------
+def _pair_store(start, frame):
+    start = np.asarray(start)
+    frame = np.asarray(frame)
+    if start.shape != frame.shape:
+        raise ValueError('start and frame must have the same shape')
+    common = np.float32 if (start.dtype == np.float32 and frame.dtype == np.float32) else np.float64
+    return _store_from_host_frames([start.astype(common, copy=False), frame.astype(common, copy=False)])
+
+
+def _pair_value(spec, start, frame):
+    store, float32 = _pair_store(start, frame)
+    rows = np.array([[0, 1]], dtype=np.int32)
+    sums, hist = engine.correlate_device(store, rows, spec.corr)
+    sums = sums.cpu().numpy()
+    hist = hist.cpu().numpy() if hist is not None else None
+    value = spec.finalize(sums, hist, store.n_atoms, float32)[0, 1]
+    return value if value.ndim else value[()]
+
+
+def _pair_counts(start, end, bins):
+    """Integer histogram of ``|start - end|`` (used by utils.histogram)."""
+    spec = _Spec('van_hove_self', bins=bins)
+    store, _ = _pair_store(start, end)
+    rows = np.array([[0, 1]], dtype=np.int32)
+    _, hist = engine.correlate_device(store, rows, spec.corr)
+    return hist.cpu().numpy()[0, 1]

@@ -1,0 +1,72 @@
+"""Build libmdevaluate_b200.so (sm_100a) in-tree with nvcc.
+
+    python -m mdevaluate_b200.csrc.build [--force] [--verbose]
+
+The shared library lands in mdevaluate_b200/_cuda/ (git-ignored, shipped to the GPU box with the
+repository snapshot).  nvcc cross-compiles without a GPU.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+OUT_DIR = os.path.join(PKG, '_cuda')
+LIB = os.path.join(OUT_DIR, 'libmdevaluate_b200.so')
+SOURCES = ['abi.cu', 'corr_kernels.cu', 'nojump_kernels.cu']
+HEADERS = ['common.cuh', os.path.join('..', '..', 'include', 'mdevaluate_b200.h')]
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+
+
+def nvcc_path():
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found (set NVCC=/path/to/nvcc)')
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    built = os.path.getmtime(LIB)
+    deps = [os.path.join(HERE, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    obj_dir = os.path.join(HERE, 'build')
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = nvcc_path()
+    common = [nvcc, '-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--ftz=false', '--prec-div=true',
+              '--prec-sqrt=true', '--fmad=true'] + ARCH
+    if verbose:
+        common += ['-Xptxas', '-v']
+    procs = []
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
+        objs.append(obj)
+        cmd = common + ['-c', os.path.join(HERE, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, proc in procs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            failed = True
+            sys.stderr.write('nvcc failed for %s:\n%s\n' % (src, out))
+        elif verbose:
+            sys.stdout.write(out)
+    if failed:
+        raise RuntimeError('nvcc compilation failed')
+    link = [nvcc, '-shared', '-o', LIB] + objs + ARCH + ['-lcudart_static', '-ldl', '-lrt', '-lpthread']
+    subprocess.run(link, check=True)
+    return LIB
+
+
+if __name__ == '__main__':
+    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
+    print(path)

@@ -1,0 +1,229 @@
+// nojump kernels: periodic-jump detection + running image counts, and the float64 unwrap.
+//
+// Producer (reader.py:165-186 + the prefix sum of pbc.py:235-237).  Every (atom, dimension) is an
+// independent running sum over time, so the kernel is parallel over the 3N components and
+// sequential over frames: a thread owns 4 consecutive floats of the row (one 128-bit load per
+// frame, warps read 512 contiguous bytes), keeps `prev` and the running count in registers and
+// walks the frames of the segment; the loads of the next frames do not depend on the running
+// state, so several rows are in flight per thread.  The jump itself must be bit-exact with
+//     ((curr - prev) / box).round().astype(int8)          (reader.py:178)
+// in the dtype NumPy uses: float32 subtract, IEEE float32 divide (float64 divide when the box is
+// float64), round-half-even.  A division-free test decides the common case: |curr - prev| <
+// 0.49 * box implies |quotient| < 0.5 after rounding, i.e. a jump of 0.
+#include "common.cuh"
+
+namespace mdb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBatch = 8;
+
+struct NojumpDev {
+    const float *coords;
+    long long pitch;
+    int n_frames;
+    int n_vals;  // 3 * n_atoms
+    float boxf[3];
+    double boxd[3];
+    int first_segment;
+    const float *whole0;
+    float *prev;
+    int *cum;
+    const int *out_row;
+    int8_t *images;
+    long long img_pitch;
+    int8_t *jumps;
+    float *coords_out;
+    long long pitch_out;
+    int *overflow;
+};
+
+template <bool BOXF32>
+__device__ __forceinline__ int jump_of(float curr, float prev, float bf, double bd, float safe) {
+    const float diff = __fsub_rn(curr, prev);
+    if (fabsf(diff) < safe) return 0;
+    if (BOXF32) return (int)(int8_t)(int)rintf(__fdiv_rn(diff, bf));
+    return (int)(int8_t)(int)rint(__ddiv_rn((double)diff, bd));
+}
+
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+    return ((uint32_t)a & 0xffu) | (((uint32_t)b & 0xffu) << 8) | (((uint32_t)c & 0xffu) << 16) |
+           (((uint32_t)d & 0xffu) << 24);
+}
+
+// VEC: rows are 16-byte aligned and n_vals is handled in whole float4s by full threads; the last
+// partial float4 (n_vals % 4 != 0) and unaligned layouts use the guarded scalar path.
+template <bool BOXF32, bool VEC>
+__global__ void __launch_bounds__(kThreads) nojump_scan_kernel(const NojumpDev p) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    const int e0 = 4 * i;
+    if (e0 >= p.n_vals) return;
+    const int nv = min(4, p.n_vals - e0);
+    const bool full = VEC && nv == 4;
+
+    float bf[4], safe[4];
+    double bd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int d = (e0 + j) % 3;
+        bf[j] = p.boxf[d];
+        bd[j] = p.boxd[d];
+        safe[j] = 0.49f * fabsf(BOXF32 ? p.boxf[d] : (float)p.boxd[d]);
+    }
+
+    float prev[4];
+    int cum[4];
+    bool overflow = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        prev[j] = 0.f;
+        cum[j] = 0;
+        if (j < nv) {
+            if (p.first_segment) {
+                // reader.py:166: prev = trajectory[0].whole (frame 0 itself for single-atom residues)
+                prev[j] = p.whole0 ? p.whole0[e0 + j] : p.coords[e0 + j];
+            } else {
+                prev[j] = p.prev[e0 + j];
+                cum[j] = p.cum[e0 + j];
+            }
+        }
+    }
+
+    // kBatch rows are loaded before any of them is processed: the running state does not feed the
+    // addresses, so a thread keeps kBatch independent 128-bit loads in flight.
+    for (int tb = 0; tb < p.n_frames; tb += kBatch) {
+        float buf[kBatch][4];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int t = min(tb + u, p.n_frames - 1);
+            const float *row = p.coords + (long long)t * p.pitch + e0;
+            if (full) {
+                const float4 v = ld_stream(reinterpret_cast<const float4 *>(row));
+                buf[u][0] = v.x; buf[u][1] = v.y; buf[u][2] = v.z; buf[u][3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) buf[u][j] = (j < nv) ? __ldg(row + j) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int t = tb + u;
+            if (t < p.n_frames) {
+                int jmp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    jmp[j] = (j < nv) ? jump_of<BOXF32>(buf[u][j], prev[j], bf[j], bd[j], safe[j]) : 0;
+                    cum[j] += jmp[j];
+                    prev[j] = buf[u][j];
+                    overflow |= (cum[j] > 127 || cum[j] < -128);
+                }
+                const int orow = p.out_row ? p.out_row[t] : t;
+                if (orow >= 0) {
+                    if (p.images) {
+                        int8_t *dst = p.images + (long long)orow * p.img_pitch + e0;
+                        if (full) *reinterpret_cast<uint32_t *>(dst) = pack4(cum[0], cum[1], cum[2], cum[3]);
+                        else
+                            for (int j = 0; j < nv; ++j) dst[j] = (int8_t)cum[j];
+                    }
+                    if (p.jumps) {
+                        int8_t *dst = p.jumps + (long long)orow * p.img_pitch + e0;
+                        if (full) *reinterpret_cast<uint32_t *>(dst) = pack4(jmp[0], jmp[1], jmp[2], jmp[3]);
+                        else
+                            for (int j = 0; j < nv; ++j) dst[j] = (int8_t)jmp[j];
+                    }
+                    if (p.coords_out) {
+                        float *dst = p.coords_out + (long long)orow * p.pitch_out + e0;
+                        if (full && (p.pitch_out % 4 == 0))
+                            *reinterpret_cast<float4 *>(dst) = make_float4(buf[u][0], buf[u][1], buf[u][2], buf[u][3]);
+                        else
+                            for (int j = 0; j < nv; ++j) dst[j] = buf[u][j];
+                    }
+                }
+            }
+        }
+    }
+
+    for (int j = 0; j < nv; ++j) {
+        p.prev[e0 + j] = prev[j];
+        p.cum[e0 + j] = cum[j];
+    }
+    if (overflow && p.overflow) atomicExch(p.overflow, 1);
+}
+
+__global__ void nojump_apply_kernel(const float *__restrict__ x, const int8_t *__restrict__ n, double b0, double b1,
+                                    double b2, int n_vals, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vals) return;
+    const int d = i % 3;
+    const double b = d == 0 ? b0 : (d == 1 ? b1 : b2);
+    // pbc.py:235-247: frame - counts * box, float64 (the product is exact, so fma == mul then sub)
+    out[i] = fma(-(double)n[i], b, (double)x[i]);
+}
+
+}  // namespace
+}  // namespace mdb
+
+using namespace mdb;
+
+extern "C" int mdb_nojump_scan(const mdb_nojump_args *a, void *stream) {
+    if (!a) return fail(MDB_ERR_ARGUMENT, "args is NULL");
+    if (a->n_frames < 0 || a->n_atoms <= 0) return fail(MDB_ERR_ARGUMENT, "bad n_frames / n_atoms");
+    if (!a->coords || !a->prev || !a->cum) return fail(MDB_ERR_ARGUMENT, "coords, prev and cum are required");
+    if (a->pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "pitch < 3*n_atoms");
+    if ((a->images || a->jumps) && a->img_pitch < 3ll * a->n_atoms)
+        return fail(MDB_ERR_ARGUMENT, "img_pitch < 3*n_atoms");
+    if (a->coords_out && a->pitch_out < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "pitch_out < 3*n_atoms");
+    for (int d = 0; d < 3; ++d)
+        if (!(a->box0[d] > 0.0)) return fail(MDB_ERR_ARGUMENT, "box0 must be positive");
+    if (a->n_frames == 0) return MDB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    NojumpDev p;
+    p.coords = a->coords;
+    p.pitch = a->pitch;
+    p.n_frames = a->n_frames;
+    p.n_vals = 3 * a->n_atoms;
+    for (int d = 0; d < 3; ++d) {
+        p.boxd[d] = a->box0[d];
+        p.boxf[d] = (float)a->box0[d];
+    }
+    p.first_segment = a->first_segment;
+    p.whole0 = a->whole0;
+    p.prev = a->prev;
+    p.cum = a->cum;
+    p.out_row = a->out_row;
+    p.images = a->images;
+    p.img_pitch = a->img_pitch;
+    p.jumps = a->jumps;
+    p.coords_out = a->coords_out;
+    p.pitch_out = a->pitch_out;
+    p.overflow = a->overflow;
+
+    bool vec = (reinterpret_cast<uintptr_t>(a->coords) % 16 == 0) && (a->pitch % 4 == 0);
+    if (a->images) vec = vec && (reinterpret_cast<uintptr_t>(a->images) % 4 == 0) && (a->img_pitch % 4 == 0);
+    if (a->jumps) vec = vec && (reinterpret_cast<uintptr_t>(a->jumps) % 4 == 0) && (a->img_pitch % 4 == 0);
+    if (a->coords_out) vec = vec && (reinterpret_cast<uintptr_t>(a->coords_out) % 16 == 0);
+
+    const int n_threads = (p.n_vals + 3) / 4;
+    const unsigned blocks = (unsigned)((n_threads + kThreads - 1) / kThreads);
+    if (a->box_is_f32) {
+        if (vec) nojump_scan_kernel<true, true><<<blocks, kThreads, 0, st>>>(p);
+        else nojump_scan_kernel<true, false><<<blocks, kThreads, 0, st>>>(p);
+    } else {
+        if (vec) nojump_scan_kernel<false, true><<<blocks, kThreads, 0, st>>>(p);
+        else nojump_scan_kernel<false, false><<<blocks, kThreads, 0, st>>>(p);
+    }
+    MDB_CUDA_CHECK(cudaGetLastError());
+    return MDB_OK;
+}
+
+extern "C" int mdb_nojump_apply(const float *coords_row, const int8_t *images_row, const double box[3],
+                                int32_t n_atoms, double *out, void *stream) {
+    if (!coords_row || !images_row || !box || !out || n_atoms <= 0)
+        return fail(MDB_ERR_ARGUMENT, "mdb_nojump_apply: NULL pointer or n_atoms <= 0");
+    const int n_vals = 3 * n_atoms;
+    nojump_apply_kernel<<<(n_vals + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        coords_row, images_row, box[0], box[1], box[2], n_vals, out);
+    MDB_CUDA_CHECK(cudaGetLastError());
+    return MDB_OK;
+}

@@ -1,0 +1,269 @@
+"""Parity of the CUDA path with the CPU oracle / the reference's golden vectors (needs a GPU).
+
+Bars (BASELINE.json north_star):
+* integer image shifts: bit-exact;
+* van Hove counts: exact (the kernel replays the reference's float64 / float32 operations,
+  so not even bin-edge ties are allowed to move here);
+* scalar correlations: |a - b| <= 1e-5 |ref| + atol, atol = 1e-7 * scale of the quantity
+  (the oracle's own float32 <-> float64 spread is 1e-7 abs on the ISF).
+  In nojump mode the displacement arithmetic is float64 like the oracle's, so MSD / alpha_2
+  are additionally held to 1e-11.
+"""
+from functools import partial
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import md_oracle as orc
+
+RTOL = 1e-5
+
+
+def close(ours, ref, scale=1.0, rtol=RTOL, atol=1e-7):
+    ours = np.asarray(ours, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert ours.shape == ref.shape
+    nan = np.isnan(ref)
+    assert (np.isnan(ours) == nan).all()
+    err = np.abs(ours - ref)[~nan]
+    tol = (rtol * np.abs(ref) + atol * scale)[~nan]
+    assert (err <= tol).all(), 'max excess %.3e (max err %.3e)' % ((err - tol).max(), err.max())
+
+
+@pytest.fixture(scope='module')
+def md():
+    import mdevaluate_b200
+    return mdevaluate_b200
+
+
+@pytest.fixture(scope='module')
+def small(golden, md):
+    g = golden('walk_small')
+    coords = md.Coordinates.from_arrays(g['pos'], g['box'], g['times'])
+    return g, coords
+
+
+def _fns(md, g):
+    c = md.correlation
+    return {
+        'msd': c.msd,
+        'isf': partial(c.isf, q=22.7),
+        'ng': c.non_gaussian,
+        'vh': partial(c.van_hove_self, bins=g['bins']),
+        'vh_off': partial(c.van_hove_self, bins=g['bins_off']),
+        'vh_irr': partial(c.van_hove_self, bins=g['bins_irr']),
+    }
+
+
+def test_image_counts_bit_exact(small, md):
+    g, coords = small
+    res = coords._resident()
+    jumps = res.dense_jumps()
+    assert jumps.dtype == np.int8
+    np.testing.assert_array_equal(jumps, g['jumps'])
+    store = res.store_for(np.arange(len(coords)), nojump=True)
+    n3 = 3 * res.n_atoms
+    images = store.images[:, :n3].cpu().numpy().reshape(len(coords), -1, 3)
+    np.testing.assert_array_equal(images, np.cumsum(g['jumps'], axis=0, dtype=np.int64))
+
+
+def test_parse_jumps_api(small, md):
+    g, coords = small
+    from scipy import sparse
+    md.reader.generate_nojump_matrixes(coords)
+    mats = coords.frames.nojump_matrixes
+    assert len(mats) == 3 and all(sparse.issparse(m) for m in mats)
+    dense = np.stack([m.toarray() for m in mats], axis=-1)
+    np.testing.assert_array_equal(dense, g['jumps'])
+
+
+def test_unwrapped_frames_bit_exact(small, md):
+    g, coords = small
+    for i in (0, 1, 17, 100, 239):
+        f = coords.nojump[i]
+        assert isinstance(f, md.CoordinateFrame) and f.dtype == np.float64 and f.mode == 'nojump'
+        np.testing.assert_array_equal(np.asarray(f), g['nojump_%d' % i])
+        assert f.time == g['times'][i] and f.step == i
+
+
+@pytest.mark.parametrize('mode', ['nojump', 'raw'])
+@pytest.mark.parametrize('name', ['msd', 'isf', 'ng'])
+def test_scalar_correlations_golden(small, md, name, mode):
+    g, coords = small
+    frames = coords.nojump if mode == 'nojump' else coords
+    t, r = md.correlation.shifted_correlation(_fns(md, g)[name], frames, segments=12, window=0.4)
+    ref = g['%s_%s' % (name, mode)]
+    np.testing.assert_array_equal(t, g['t_' + mode])
+    assert r.dtype == ref.dtype
+    scale = {'msd': float(np.nanmax(g['msd_nojump'])), 'isf': 1.0, 'ng': 1.0}[name]
+    # raw float32 frames: the reference itself computes in float32, alpha_2 = O(1) ratio of float32 means
+    close(r, ref, scale=scale, atol=1e-6 if (mode == 'raw' and name == 'ng') else 1e-7)
+    if mode == 'nojump' and name != 'isf':
+        close(r, ref, scale=scale, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize('mode', ['nojump', 'raw'])
+@pytest.mark.parametrize('name', ['vh', 'vh_off', 'vh_irr'])
+def test_van_hove_exact(small, md, name, mode):
+    g, coords = small
+    frames = coords.nojump if mode == 'nojump' else coords
+    t, r = md.correlation.shifted_correlation(_fns(md, g)[name], frames, segments=12, window=0.4)
+    ref = g['%s_%s' % (name, mode)]
+    assert r.dtype == np.float64 and r.shape == ref.shape
+    n = g['pos'].shape[1]
+    np.testing.assert_array_equal(np.rint(r * n).astype(np.int64), np.rint(ref * n).astype(np.int64))
+    np.testing.assert_array_equal(r, ref)
+
+
+def test_chi4_average_slice_dense(small, md):
+    g, coords = small
+    c = md.correlation
+    t, fqt = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=20, window=0.2, skip=0.1,
+                                   average=False)
+    np.testing.assert_array_equal(t, g['chi4_t'])
+    close(fqt, g['chi4_fqt'])
+    close(len(coords[0]) * fqt.var(axis=0), g['chi4'], atol=1e-6)
+    t2, x4 = c.chi4(coords.nojump, 22.7)
+    np.testing.assert_array_equal(x4, len(coords[0]) * fqt.var(axis=0))
+    t, r = c.shifted_correlation(c.msd, coords.nojump, segments=7, window=0.3, average=True)
+    np.testing.assert_array_equal(t, g['msd_avg_t'])
+    close(r, g['msd_avg'], rtol=1e-11, atol=1e-13)
+    t, r = c.shifted_correlation(c.msd, coords.nojump[24:], segments=7, window=0.3, average=True)
+    close(r, g['msd_slice24'], rtol=1e-11, atol=1e-13)
+    t, r = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=5, window=0.25,
+                                 index_distribution=lambda a, b: np.arange(a, b))
+    close(r, g['isf_dense'])
+
+
+def test_selection(small, md):
+    g, _ = small
+    coords = md.Coordinates(md.MemoryReader(g['pos'], g['box'], g['times']), atom_filter=g['sel'])
+    t, r = md.correlation.shifted_correlation(md.correlation.msd, coords.nojump, segments=6, window=0.4)
+    close(r, g['msd_sel'], rtol=1e-11, atol=1e-13)
+
+
+def test_config1_golden(golden, md):
+    """BASELINE config 1 against the reference's own output: MSD 1000 x 1000, S=100, L=70."""
+    from mdevaluate_b200.synthetic import random_walk
+    g = golden('config1')
+    pos, box, times = random_walk(1000, 1000, seed=20240)
+    coords = md.Coordinates.from_arrays(pos, box, times)
+    c = md.correlation
+    t, r = c.shifted_correlation(c.msd, coords.nojump, segments=100, window=0.5)
+    assert r.shape == (100, 70)
+    np.testing.assert_array_equal(t, g['t'])
+    close(r, g['msd'], scale=float(g['msd'].max()), rtol=1e-11, atol=1e-13)
+    t, r = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=100, window=0.5)
+    close(r, g['isf'])
+    print('config1 isf max abs err %.3e' % np.abs(r - g['isf']).max())
+    t, r = c.shifted_correlation(c.non_gaussian, coords.nojump, segments=100, window=0.5)
+    close(r, g['ng'], rtol=1e-10, atol=1e-12)
+    t, r = c.shifted_correlation(partial(c.isf, q=22.7), coords, segments=100, window=0.5)
+    assert r.dtype == np.float32
+    close(r, g['isf_raw'], atol=2e-7)
+    t, r = c.shifted_correlation(partial(c.van_hove_self, bins=g['vh_bins']), coords.nojump, segments=10,
+                                 window=0.5)
+    np.testing.assert_array_equal(r, g['vh'])
+    t, r = c.shifted_correlation(partial(c.van_hove_self, bins=g['vh_bins']), coords, segments=10, window=0.5)
+    np.testing.assert_array_equal(r, g['vh_raw'])
+    # dense jump statistics of the whole trajectory
+    res = coords._resident()
+    store = res.store_for(np.arange(1000), nojump=True)
+    last = store.images[999, :3000].cpu().numpy().reshape(1000, 3).astype(np.int64)
+    np.testing.assert_array_equal(last, g['count_checksum'])
+
+
+def test_multi_function_single_pass(small, md):
+    g, coords = small
+    c = md.correlation
+    fns = _fns(md, g)
+    t, out = c.shifted_correlation_multi({'vh': fns['vh'], 'ng': fns['ng'], 'msd': fns['msd'], 'isf': fns['isf']},
+                                         coords.nojump, segments=12, window=0.4)
+    np.testing.assert_array_equal(out['vh'], g['vh_nojump'])
+    close(out['ng'], g['ng_nojump'], rtol=1e-11, atol=1e-13)
+    close(out['msd'], g['msd_nojump'], rtol=1e-11, atol=1e-13)
+    close(out['isf'], g['isf_nojump'])
+
+
+def test_direct_pair_calls_and_histogram(golden, md):
+    g = golden('walk_small')
+    a = g['nojump_17']
+    b = g['nojump_100']
+    c = md.correlation
+    with np.errstate(all='ignore'):
+        close(c.msd(a, b), orc.msd(a, b), rtol=1e-12, atol=0)
+        close(c.isf(a, b, q=22.7), orc.isf(a, b, 22.7))
+        close(c.non_gaussian(a, b), orc.non_gaussian(a, b), rtol=1e-11)
+        np.testing.assert_array_equal(c.van_hove_self(a, b, bins=g['bins']), orc.van_hove_self(a, b, g['bins']))
+        assert np.isnan(c.non_gaussian(a, a))
+        assert c.isf(a, a, q=22.7) == 1.0 and c.msd(a, a) == 0.0
+    h = golden('histogram')
+    for k in ('b0', 'b1', 'b2'):
+        hist, centres = md.utils.histogram(h['data'], h[k])
+        np.testing.assert_array_equal(hist, h['h_' + k])
+        np.testing.assert_array_equal(centres, h['c_' + k])
+
+
+def test_generic_frames_protocol(golden, md):
+    """Any object with len / [i] -> (N,3) array with .time works (float64 unwrapped frames here)."""
+    g = golden('walk_small')
+    unw = orc.UnwrappedTrajectory(g['pos'], g['box'], g['times'])
+    c = md.correlation
+    t, r = c.shifted_correlation(c.msd, unw, segments=12, window=0.4)
+    np.testing.assert_array_equal(t, g['t_nojump'])
+    close(r, g['msd_nojump'], rtol=1e-11, atol=1e-13)
+    t, r = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), unw, segments=12, window=0.4)
+    np.testing.assert_array_equal(r, g['vh_nojump'])
+
+
+def test_ragged_sizes_and_streaming(md):
+    """Atom counts that are not multiples of 4, unaligned rows, the compact/streamed store."""
+    from mdevaluate_b200.synthetic import random_walk
+    c = md.correlation
+    for n in (1, 3, 5, 31, 130):
+        pos, box, times = random_walk(n, 60, seed=n, sigma=0.2, box=2.0)
+        unw = orc.UnwrappedTrajectory(pos, box, times)
+        for forced in (False, True):
+            coords = md.Coordinates.from_arrays(pos, box, times)
+            coords._resident().force_compact = forced
+            coords._resident().SEGMENT_BYTES = 4096          # many tiny segments: carried scan state
+            with np.errstate(all='ignore'):
+                t0, ref = orc.shifted_correlation(orc.msd, unw, segments=5, window=0.5)
+                t, r = c.shifted_correlation(c.msd, coords.nojump, segments=5, window=0.5)
+                close(r, ref, rtol=1e-11, atol=1e-13)
+                bins = np.linspace(0, 3.0, 41)
+                _, ref = orc.shifted_correlation(partial(orc.van_hove_self, bins=bins), unw, segments=5, window=0.5)
+                _, r = c.shifted_correlation(partial(c.van_hove_self, bins=bins), coords.nojump, segments=5,
+                                             window=0.5)
+                np.testing.assert_array_equal(r, ref)
+
+
+def test_errors(md, small):
+    g, coords = small
+    c = md.correlation
+    with pytest.raises(AssertionError):
+        c.shifted_correlation(c.msd, coords, window=0.6, skip=0.5)
+    with pytest.raises(NotImplementedError):
+        c.shifted_correlation(lambda a, b: 0.0, coords)
+    with pytest.raises(TypeError):
+        c.shifted_correlation(c.isf, coords)
+    with pytest.raises(IndexError):
+        coords[len(coords)]
+    with pytest.raises(IndexError):
+        c.shifted_correlation(c.msd, coords, index_distribution=lambda a, b: np.array([0, 10 * b]))
+    # autosave keyword arguments of the reference decorator are accepted and ignored
+    c.shifted_correlation(c.msd, coords, description='x', autoload=False)
+
+
+def test_c_abi_argument_checks(md):
+    import ctypes as C
+    from mdevaluate_b200._cuda import lib as L
+    lib = L.load()
+    a = L.CorrArgs()
+    assert lib.mdb_shifted_corr(C.byref(a), None) == 1
+    assert b'positive' in lib.mdb_last_error()
+    sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+    assert lib.mdb_device_info(C.byref(sm), C.byref(major), C.byref(minor)) == 0
+    assert sm.value > 0 and major.value >= 10
