@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--function', default='isf', choices=['isf', 'msd'])
+    ap.add_argument('--pyprofile', action='store_true', help='cProfile the host side of 20 resident steps')
     return ap.parse_args()
 
 
@@ -249,6 +250,16 @@ def ours_arm(a):
     evals_step = N * world * S * L
     for _ in range(a.warmup):
         c.shifted_correlation(fn, frames, segments=a.segments, window=0.5)
+
+    if a.pyprofile and rank == 0:
+        import cProfile
+        import pstats
+        prof = cProfile.Profile()
+        prof.enable()
+        for _ in range(20):
+            c.shifted_correlation(fn, frames, segments=a.segments, window=0.5)
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(25)
 
     # ---- timed region: K steps, inputs resident in HBM ---------------------------------------------
     engine.profile_kernels(True)

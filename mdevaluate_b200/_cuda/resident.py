@@ -262,6 +262,9 @@ class Resident:
     # -- public ---------------------------------------------------------------------------------
     def store_for(self, frame_ids, nojump):
         """A DeviceStore holding (at least) ``frame_ids``; with image counts if ``nojump``."""
+        if (self._dense is not None and not self.force_compact
+                and (not nojump or self._dense.images is not None)):
+            return self._dense                      # hot path: everything is resident already
         torch = _lib.require_cuda()
         frame_ids = np.unique(np.asarray(frame_ids, dtype=np.int64))
         if frame_ids.size and (frame_ids[0] < 0 or frame_ids[-1] >= self.n_frames):

@@ -62,18 +62,18 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
 
 // sin(sqrt(y)) / sqrt(y) for y >= 0 in float32, |error| ~1e-7 for sqrt(y) up to a few 1e4.
 //   one MUFU.RSQ + a Newton step give 1/x and x = y/x;
-//   x is reduced by multiples of pi (3-term Cody-Waite with FMA), sin on [-pi/2, pi/2] is an odd
+//   x is reduced by multiples of pi (2-term Cody-Waite with FMA), sin on [-pi/2, pi/2] is an odd
 //   degree-11 polynomial (near-minimax, 1e-10), the sign comes from the parity of the multiple.
 __device__ __forceinline__ float sinc_of_square(float y) {
-    float rs = rsqrtf(y);
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(y));   // bare MUFU.RSQ; y < 1e-30 is handled below
     rs = rs * fmaf(-0.5f * y * rs, rs, 1.5f);
     const float x = y * rs;
     const float kf_biased = fmaf(x, 0.318309886183790672f, 12582912.0f);
     const uint32_t sign = ((uint32_t)__float_as_int(kf_biased)) << 31;
     const float kf = kf_biased - 12582912.0f;
     float z = fmaf(-kf, 3.140625f, x);
-    z = fmaf(-kf, 9.676535846665502e-4f, z);
-    z = fmaf(-kf, 5.126688136514179e-12f, z);
+    z = fmaf(-kf, 9.676535846665502e-4f, z);   // pi - 3.140625 - this = 5e-12: below float32 for k < 1e4
     const float s = z * z;
     float p = -2.4061128200969506e-08f;
     p = fmaf(p, s, 2.7535631943464978e-06f);

@@ -1,11 +1,10 @@
 // Correlation kernels: per-(origin, lag) sums of r^2, r^4, sinc(q r) and van Hove histograms.
 //
 // Work decomposition (one CTA = one (origin s, lag chunk c, atom block ab)):
-//   * a thread owns groups of 4 consecutive atoms = 12 interleaved xyz values = three 128-bit
-//     loads per frame row, fully coalesced (a warp reads 1536 contiguous bytes per row);
+//   * a thread owns groups of 4 consecutive atoms = 12 interleaved xyz values = 48 bytes per frame
+//     row (three 128-bit accesses, a warp covers 1536 contiguous bytes);
 //   * the unwrapped origin positions of the group are kept in registers (12 doubles) and reused
-//     for the up to kLagChunk lag frames of the chunk; the lag rows are streamed with
-//     L1::no_allocate loads, all chunk rows of a group are independent loads in flight;
+//     for the up to kLagChunk lag frames of the chunk;
 //   * CTAs of the same (s, ab) and different chunks are adjacent in launch order, so the origin
 //     row is fetched from HBM once and re-read from L2 by the other chunks;
 //   * per-lag accumulators live in registers for the whole atom loop; there is ONE block
@@ -13,6 +12,16 @@
 //     partials of the atom blocks in fixed order (bit-reproducible, no float atomics);
 //   * histograms are accumulated in shared memory (u32, one table per lag of the chunk) and
 //     flushed with integer atomics.
+//
+// Two data paths feed the same arithmetic:
+//   corr_bulk_kernel  (the product path for float32 rows with 16-byte aligned pitch): a producer
+//       warp streams row tiles (1024 atoms = 12 KiB coordinates + 3 KiB image counts) from HBM
+//       into a ring of shared-memory stages with cp.async.bulk (the TMA engine, SASS UBLKCP),
+//       completion on mbarriers; 8 consumer warps read their 48+12 bytes per stage with
+//       conflict-free LDS and release the stage as soon as the values are in registers.  Memory
+//       parallelism is the ring depth, not the register file.
+//   corr_ldg_kernel   (fallback: float64 rows, unaligned pitch): the same loop with direct
+//       128-bit / scalar global loads.
 //
 // Arithmetic: positions are widened to float64, unwrapped as fma(-n, box, x) (bit-identical to
 // pbc.nojump's float64 frame, pbc.py:235-247), the displacement and r^2 are float64.  sinc is
@@ -25,9 +34,13 @@
 namespace mdb {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;           // compute threads per CTA (both kernels)
 constexpr int kLagChunk = 8;
 constexpr int kWarps = kThreads / 32;
+constexpr int kTileAtoms = 4 * kThreads;          // atoms per bulk tile
+constexpr int kCoordTileBytes = kTileAtoms * 12;  // 12288
+constexpr int kImgTileBytes = kTileAtoms * 3;     // 3072
+constexpr int kBulkThreads = kThreads + 32;       // + one producer warp
 
 struct CorrDev {
     const void *coords;
@@ -51,72 +64,23 @@ struct CorrDev {
     unsigned long long *hist;
 };
 
-// ---- loading one group of 4 atoms as 12 unwrapped float64 components --------------------------
-template <typename CT, bool IMG, bool VEC, bool STREAM>
-struct GroupLoader;
-
-template <bool IMG, bool VEC, bool STREAM>
-struct GroupLoader<float, IMG, VEC, STREAM> {
-    // raw values kept for the float32-semantics histogram of raw frames
-    __device__ static __forceinline__ void load(const CorrDev &p, int row, int g, int nv, const double *bx,
-                                                double (&u)[12], float (&raw)[12]) {
-        const float *base = static_cast<const float *>(p.coords) + (long long)row * p.pitch + 12ll * g;
-        if (VEC && nv == 4) {
-            const float4 *b4 = reinterpret_cast<const float4 *>(base);
-            float4 a, b, c;
-            if (STREAM) { a = ld_stream(b4); b = ld_stream(b4 + 1); c = ld_stream(b4 + 2); }
-            else { a = __ldg(b4); b = __ldg(b4 + 1); c = __ldg(b4 + 2); }
-            raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
-            raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
-            raw[8] = c.x; raw[9] = c.y; raw[10] = c.z; raw[11] = c.w;
-        } else {
+// ---- unwrap: 12 raw float32 components (+ packed int8 image counts) -> 12 float64 -------------
+template <bool IMG>
+__device__ __forceinline__ void unwrap12(const float (&raw)[12], const uint32_t (&w)[3], const double *bx,
+                                         double (&u)[12]) {
+    if (IMG) {
+        const double b0 = bx[0], b1 = bx[1], b2 = bx[2];
 #pragma unroll
-            for (int c = 0; c < 12; ++c) raw[c] = (c < 3 * nv) ? __ldg(base + c) : 0.0f;
+        for (int c = 0; c < 12; ++c) {
+            const double n = int_to_double(sbyte(w[c >> 2], c & 3));
+            const double b = (c % 3 == 0) ? b0 : ((c % 3 == 1) ? b1 : b2);
+            u[c] = fma(-n, b, (double)raw[c]);
         }
-        if (IMG) {
-            const int8_t *ib = p.images + (long long)row * p.img_pitch + 12ll * g;
-            uint32_t w[3];
-            if (VEC && nv == 4) {
-                const uint32_t *iw = reinterpret_cast<const uint32_t *>(ib);
-                if (STREAM) { w[0] = ld_stream(iw); w[1] = ld_stream(iw + 1); w[2] = ld_stream(iw + 2); }
-                else { w[0] = __ldg(iw); w[1] = __ldg(iw + 1); w[2] = __ldg(iw + 2); }
-            } else {
-                w[0] = w[1] = w[2] = 0u;
+    } else {
 #pragma unroll
-                for (int c = 0; c < 12; ++c)
-                    if (c < 3 * nv) w[c >> 2] |= ((uint32_t)(uint8_t)ib[c]) << (8 * (c & 3));
-            }
-#pragma unroll
-            for (int c = 0; c < 12; ++c) {
-                const double n = int_to_double(sbyte(w[c >> 2], c & 3));
-                u[c] = fma(-n, bx[c % 3], (double)raw[c]);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 12; ++c) u[c] = (double)raw[c];
-        }
+        for (int c = 0; c < 12; ++c) u[c] = (double)raw[c];
     }
-};
-
-template <bool VEC, bool STREAM>
-struct GroupLoader<double, false, VEC, STREAM> {
-    __device__ static __forceinline__ void load(const CorrDev &p, int row, int g, int nv, const double *,
-                                                double (&u)[12], float (&)[12]) {
-        const double *base = static_cast<const double *>(p.coords) + (long long)row * p.pitch + 12ll * g;
-        if (VEC && nv == 4) {
-            const double2 *b2 = reinterpret_cast<const double2 *>(base);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const double2 v = STREAM ? ld_stream(b2 + j) : __ldg(b2 + j);
-                u[2 * j] = v.x;
-                u[2 * j + 1] = v.y;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 12; ++c) u[c] = (c < 3 * nv) ? __ldg(base + c) : 0.0;
-        }
-    }
-};
+}
 
 // ---- histogram binning ------------------------------------------------------------------------
 // np.floor_divide(r, dx) for r >= 0, dx > 0: floor of the exact real quotient (npy_divmod is
@@ -140,38 +104,114 @@ __device__ __forceinline__ int edge_bin(double r, const double *edges, int n_bin
     return lo;
 }
 
-template <typename CT, bool IMG, int FLAGS, bool VEC>
-__global__ void __launch_bounds__(kThreads, 2) corr_kernel(const CorrDev p) {
+__device__ __forceinline__ double r2_unfused(double ddx, double ddy, double ddz) {
+    // (vec ** 2).sum(axis=-1) as NumPy evaluates it: three rounded squares, summed left to right
+    return __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+}
+
+// Accumulators of one thread for the lags of its chunk.
+template <int FLAGS>
+struct Accum {
+    static constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    static constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
+    static constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
+    double r2[kR2 ? kLagChunk : 1];
+    double r4[kR4 ? kLagChunk : 1];
+    double sc[kSinc ? kLagChunk : 1];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < kLagChunk; ++k) {
+            if constexpr (kR2) r2[k] = 0.0;
+            if constexpr (kR4) r4[k] = 0.0;
+            if constexpr (kSinc) sc[k] = 0.0;
+        }
+    }
+};
+
+// One group of 4 atoms against one lag frame.  Atoms beyond `nv` (only in the last group of the
+// shard) carry zeroed inputs on both sides: they add exactly 0 to the r^2 / r^4 sums and exactly
+// 1.0f each to the sinc sum, which is taken off again; the histogram skips them.
+template <int FLAGS, bool HIST_F32>
+__device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[12], const float (&raw0)[12],
+                                           const double (&ut)[12], const float (&rawt)[12], int nv, const int K,
+                                           Accum<FLAGS> &acc, unsigned int *s_hist, const double *s_edges) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
-    // raw float32 frames: the reference computes r in float32 (correlation.py:246-247 on float32
-    // arrays), so the histogram replays those float32 operations to land in the same bins.
-    constexpr bool kHistF32 = kHist && sizeof(CT) == 4 && !IMG;
+    float sinc4 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const double ddx = u0[3 * a] - ut[3 * a];
+        const double ddy = u0[3 * a + 1] - ut[3 * a + 1];
+        const double ddz = u0[3 * a + 2] - ut[3 * a + 2];
+        const double r2 = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
+        if constexpr (kR2) acc.r2[K] += r2;
+        if constexpr (kR4) acc.r4[K] = fma(r2, r2, acc.r4[K]);
+        if constexpr (kSinc) sinc4 += sinc_of_square((float)(r2 * p.q2));
+        if constexpr (kHist) {
+            if (a < nv) {
+                int bin = -1;
+                if (HIST_F32) {
+                    // raw float32 frames: the reference computes r in float32 (correlation.py:246-247
+                    // on float32 arrays); replay vec = start - end; (vec**2).sum(-1) ** .5 in float32
+                    const float vx = __fsub_rn(raw0[3 * a], rawt[3 * a]);
+                    const float vy = __fsub_rn(raw0[3 * a + 1], rawt[3 * a + 1]);
+                    const float vz = __fsub_rn(raw0[3 * a + 2], rawt[3 * a + 2]);
+                    const float q = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+                    const double r = (double)__fsqrt_rn(q);
+                    if (p.bin_mode == MDB_BINS_UNIFORM) {
+                        const long long kk = exact_floor_div(r, p.dx, p.inv_dx);
+                        bin = (kk < p.n_bins) ? (int)kk : -1;
+                    } else {
+                        bin = edge_bin(r, s_edges, p.n_bins);
+                    }
+                } else if (p.bin_mode == MDB_BINS_UNIFORM) {
+                    // float32 estimate; exact path only near a bin edge
+                    const float t = __fsqrt_rn((float)r2) * p.inv_dx_f;
+                    const float fl = floorf(t);
+                    const float fr = t - fl;
+                    const float margin = fmaf(t, 6.0e-7f, 1.0e-6f);
+                    if (fr > margin && fr < 1.0f - margin) {
+                        bin = (t < (float)p.n_bins) ? (int)fl : -1;
+                    } else {
+                        const long long kk = exact_floor_div(sqrt(r2_unfused(ddx, ddy, ddz)), p.dx, p.inv_dx);
+                        bin = (kk < p.n_bins) ? (int)kk : -1;
+                    }
+                } else {
+                    bin = edge_bin(sqrt(r2_unfused(ddx, ddy, ddz)), s_edges, p.n_bins);
+                }
+                if (bin >= 0) atomicAdd(&s_hist[K * p.n_bins + bin], 1u);
+            }
+        }
+    }
+    if constexpr (kSinc) acc.sc[K] += (double)(sinc4 - (float)(4 - nv));
+}
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_row[kLagChunk + 1];
-    __shared__ double s_box[kLagChunk + 1][3];
-    __shared__ double s_red[kWarps][kLagChunk * 3];
+// CTA prologue shared by both kernels: which (origin, chunk, atom block) am I, rows and boxes.
+struct CtaWork {
+    int s, ab, l0, nl;
+};
 
+__device__ __forceinline__ CtaWork cta_work(const CorrDev &p) {
+    CtaWork w;
     const int bid = blockIdx.x;
     const int c = bid % p.n_chunks;
     const int rest = bid / p.n_chunks;
-    const int ab = rest % p.n_ablocks;
-    const int s = rest / p.n_ablocks;
-    const int l0 = (int)((long long)c * p.L / p.n_chunks);
-    const int l1 = (int)((long long)(c + 1) * p.L / p.n_chunks);
-    const int nl = l1 - l0;
-    const int tid = threadIdx.x;
+    w.ab = rest % p.n_ablocks;
+    w.s = rest / p.n_ablocks;
+    w.l0 = (int)((long long)c * p.L / p.n_chunks);
+    w.nl = (int)((long long)(c + 1) * p.L / p.n_chunks) - w.l0;
+    return w;
+}
 
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem_raw);
-    double *s_edges = reinterpret_cast<double *>(smem_raw + (size_t)kLagChunk * p.n_bins * sizeof(unsigned int));
-
+template <bool IMG>
+__device__ __forceinline__ void load_rows(const CorrDev &p, const CtaWork &w, int tid, int *s_row,
+                                          double (*s_box)[3]) {
     if (tid <= kLagChunk) {
         // slot 0: the origin row, slots 1..nl: the lag rows of this chunk
-        const int l = (tid == 0) ? 0 : l0 + tid - 1;
-        const int row = (tid == 0 || tid - 1 < nl) ? p.rows[(long long)s * p.L + l] : 0;
+        const int l = (tid == 0) ? 0 : w.l0 + tid - 1;
+        const int row = (tid == 0 || tid - 1 < w.nl) ? p.rows[(long long)w.s * p.L + l] : 0;
         s_row[tid] = row;
         if (IMG) {
             s_box[tid][0] = p.box[3ll * row];
@@ -179,95 +219,25 @@ __global__ void __launch_bounds__(kThreads, 2) corr_kernel(const CorrDev p) {
             s_box[tid][2] = p.box[3ll * row + 2];
         }
     }
-    if (kHist) {
-        for (int i = tid; i < kLagChunk * p.n_bins; i += kThreads) s_hist[i] = 0u;
-        if (p.bin_mode == MDB_BINS_EDGES)
-            for (int i = tid; i <= p.n_bins; i += kThreads) s_edges[i] = p.edges[i];
-    }
-    __syncthreads();
+}
 
-    double acc2[kLagChunk], acc4[kLagChunk], accs[kLagChunk];
-#pragma unroll
-    for (int k = 0; k < kLagChunk; ++k) acc2[k] = acc4[k] = accs[k] = 0.0;
-
-    const int g_begin = ab * p.groups_per_block;
-    const int g_end = min(p.n_groups, g_begin + p.groups_per_block);
-    const float q2f_unused = 0.f; (void)q2f_unused;
-
-    for (int g = g_begin + tid; g < g_end; g += kThreads) {
-        const int nv = min(4, p.n_atoms - 4 * g);
-        double u0[12];
-        float raw0[12];
-        GroupLoader<CT, IMG, VEC, false>::load(p, s_row[0], g, nv, s_box[0], u0, raw0);
-#pragma unroll
-        for (int k = 0; k < kLagChunk; ++k) {
-            if (k < nl) {
-                double ut[12];
-                float rawt[12];
-                GroupLoader<CT, IMG, VEC, true>::load(p, s_row[k + 1], g, nv, s_box[k + 1], ut, rawt);
-                float sinc4 = 0.0f;
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    if (a < nv) {
-                        const double ddx = u0[3 * a] - ut[3 * a];
-                        const double ddy = u0[3 * a + 1] - ut[3 * a + 1];
-                        const double ddz = u0[3 * a + 2] - ut[3 * a + 2];
-                        const double r2 = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
-                        if (kR2) acc2[k] += r2;
-                        if (kR4) acc4[k] = fma(r2, r2, acc4[k]);
-                        if (kSinc) sinc4 += sinc_of_square((float)(r2 * p.q2));
-                        if (kHist) {
-                            int bin = -1;
-                            if (kHistF32) {
-                                // float32 replay: vec = start - end; (vec**2).sum(-1) ** .5, all float32
-                                const float vx = __fsub_rn(raw0[3 * a], rawt[3 * a]);
-                                const float vy = __fsub_rn(raw0[3 * a + 1], rawt[3 * a + 1]);
-                                const float vz = __fsub_rn(raw0[3 * a + 2], rawt[3 * a + 2]);
-                                const float q = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)),
-                                                          __fmul_rn(vz, vz));
-                                const double r = (double)__fsqrt_rn(q);
-                                if (p.bin_mode == MDB_BINS_UNIFORM) {
-                                    const long long kk = exact_floor_div(r, p.dx, p.inv_dx);
-                                    bin = (kk < p.n_bins) ? (int)kk : -1;
-                                } else {
-                                    bin = edge_bin(r, s_edges, p.n_bins);
-                                }
-                            } else if (p.bin_mode == MDB_BINS_UNIFORM) {
-                                // float32 estimate; exact path only near a bin edge
-                                const float t = __fsqrt_rn((float)r2) * p.inv_dx_f;
-                                const float fl = floorf(t);
-                                const float fr = t - fl;
-                                const float margin = fmaf(t, 6.0e-7f, 1.0e-6f);
-                                if (fr > margin && fr < 1.0f - margin) {
-                                    bin = (t < (float)p.n_bins) ? (int)fl : -1;
-                                } else {
-                                    const double r2x = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
-                                                                 __dmul_rn(ddz, ddz));
-                                    const long long kk = exact_floor_div(sqrt(r2x), p.dx, p.inv_dx);
-                                    bin = (kk < p.n_bins) ? (int)kk : -1;
-                                }
-                            } else {
-                                const double r2x = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)),
-                                                             __dmul_rn(ddz, ddz));
-                                bin = edge_bin(sqrt(r2x), s_edges, p.n_bins);
-                            }
-                            if (bin >= 0) atomicAdd(&s_hist[k * p.n_bins + bin], 1u);
-                        }
-                    }
-                }
-                if (kSinc) accs[k] += (double)sinc4;
-            }
-        }
-    }
-
-    // ---- one block reduction per CTA --------------------------------------------------------
+// CTA epilogue: one block reduction, partial sums out, histogram flush.  Called by the kThreads
+// compute threads only; `sync` is the barrier that joins exactly those threads.
+template <int FLAGS, typename Sync>
+__device__ __forceinline__ void cta_epilogue(const CorrDev &p, const CtaWork &w, int tid, Accum<FLAGS> &acc,
+                                             double (*s_red)[kLagChunk * 3], const unsigned int *s_hist, Sync sync) {
+    constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
+    constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
+    constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int k = 0; k < kLagChunk; ++k) {
-        if (k < nl) {
-            const double v2 = kR2 ? warp_sum(acc2[k]) : 0.0;
-            const double v4 = kR4 ? warp_sum(acc4[k]) : 0.0;
-            const double vs = kSinc ? warp_sum(accs[k]) : 0.0;
+        if (k < w.nl) {
+            double v2 = 0.0, v4 = 0.0, vs = 0.0;
+            if constexpr (kR2) v2 = warp_sum(acc.r2[k]);
+            if constexpr (kR4) v4 = warp_sum(acc.r4[k]);
+            if constexpr (kSinc) vs = warp_sum(acc.sc[k]);
             if (lane == 0) {
                 s_red[warp][3 * k] = v2;
                 s_red[warp][3 * k + 1] = v4;
@@ -275,23 +245,289 @@ __global__ void __launch_bounds__(kThreads, 2) corr_kernel(const CorrDev p) {
             }
         }
     }
-    __syncthreads();
-    if (tid < 3 * nl) {
+    sync();
+    if (tid < 3 * w.nl) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) v += s_red[w][tid];
+        for (int wi = 0; wi < kWarps; ++wi) v += s_red[wi][tid];
         const int k = tid / 3, comp = tid - 3 * k;
-        p.partial[(((long long)s * p.L + l0 + k) * p.n_ablocks + ab) * 3 + comp] = v;
+        p.partial[(((long long)w.s * p.L + w.l0 + k) * p.n_ablocks + w.ab) * 3 + comp] = v;
     }
     if (kHist) {
-        for (int i = tid; i < nl * p.n_bins; i += kThreads) {
+        for (int i = tid; i < w.nl * p.n_bins; i += kThreads) {
             const unsigned int cnt = s_hist[i];
             if (cnt) {
                 const int k = i / p.n_bins, b = i - k * p.n_bins;
-                atomicAdd(&p.hist[((long long)s * p.L + l0 + k) * p.n_bins + b], (unsigned long long)cnt);
+                atomicAdd(&p.hist[((long long)w.s * p.L + w.l0 + k) * p.n_bins + b], (unsigned long long)cnt);
             }
         }
     }
+}
+
+// =================================================================================================
+// fallback path: direct global loads (float64 rows, unaligned pitch)
+// =================================================================================================
+template <typename CT, bool IMG, bool VEC, bool STREAM>
+struct GroupLoader;
+
+template <bool IMG, bool VEC, bool STREAM>
+struct GroupLoader<float, IMG, VEC, STREAM> {
+    __device__ static __forceinline__ void load(const CorrDev &p, int row, int g, int nv, const double *bx,
+                                                double (&u)[12], float (&raw)[12]) {
+        const float *base = static_cast<const float *>(p.coords) + (long long)row * p.pitch + 12ll * g;
+        uint32_t w[3] = {0u, 0u, 0u};
+        if (VEC && nv == 4) {
+            const float4 *b4 = reinterpret_cast<const float4 *>(base);
+            float4 a, b, c;
+            if (STREAM) { a = ld_stream(b4); b = ld_stream(b4 + 1); c = ld_stream(b4 + 2); }
+            else { a = __ldg(b4); b = __ldg(b4 + 1); c = __ldg(b4 + 2); }
+            raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
+            raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+            raw[8] = c.x; raw[9] = c.y; raw[10] = c.z; raw[11] = c.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 12; ++c) raw[c] = (c < 3 * nv) ? __ldg(base + c) : 0.0f;
+        }
+        if (IMG) {
+            const int8_t *ib = p.images + (long long)row * p.img_pitch + 12ll * g;
+            if (VEC && nv == 4) {
+                const uint32_t *iw = reinterpret_cast<const uint32_t *>(ib);
+                if (STREAM) { w[0] = ld_stream(iw); w[1] = ld_stream(iw + 1); w[2] = ld_stream(iw + 2); }
+                else { w[0] = __ldg(iw); w[1] = __ldg(iw + 1); w[2] = __ldg(iw + 2); }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 12; ++c)
+                    if (c < 3 * nv) w[c >> 2] |= ((uint32_t)(uint8_t)ib[c]) << (8 * (c & 3));
+            }
+        }
+        unwrap12<IMG>(raw, w, bx, u);
+    }
+};
+
+template <bool VEC, bool STREAM>
+struct GroupLoader<double, false, VEC, STREAM> {
+    __device__ static __forceinline__ void load(const CorrDev &p, int row, int g, int nv, const double *,
+                                                double (&u)[12], float (&)[12]) {
+        const double *base = static_cast<const double *>(p.coords) + (long long)row * p.pitch + 12ll * g;
+        if (VEC && nv == 4) {
+            const double2 *b2 = reinterpret_cast<const double2 *>(base);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const double2 v = STREAM ? ld_stream(b2 + j) : __ldg(b2 + j);
+                u[2 * j] = v.x;
+                u[2 * j + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 12; ++c) u[c] = (c < 3 * nv) ? __ldg(base + c) : 0.0;
+        }
+    }
+};
+
+template <typename CT, bool IMG, int FLAGS, bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) {
+    constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
+    constexpr bool kHistF32 = kHist && sizeof(CT) == 4 && !IMG;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_row[kLagChunk + 1];
+    __shared__ double s_box[kLagChunk + 1][3];
+    __shared__ double s_red[kWarps][kLagChunk * 3];
+
+    const CtaWork w = cta_work(p);
+    const int tid = threadIdx.x;
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem_raw);
+    double *s_edges = reinterpret_cast<double *>(smem_raw + (size_t)kLagChunk * p.n_bins * sizeof(unsigned int));
+
+    load_rows<IMG>(p, w, tid, s_row, s_box);
+    if (kHist) {
+        for (int i = tid; i < kLagChunk * p.n_bins; i += kThreads) s_hist[i] = 0u;
+        if (p.bin_mode == MDB_BINS_EDGES)
+            for (int i = tid; i <= p.n_bins; i += kThreads) s_edges[i] = p.edges[i];
+    }
+    __syncthreads();
+
+    Accum<FLAGS> acc;
+    acc.clear();
+    const int g_begin = w.ab * p.groups_per_block;
+    const int g_end = min(p.n_groups, g_begin + p.groups_per_block);
+    for (int g = g_begin + tid; g < g_end; g += kThreads) {
+        const int nv = min(4, p.n_atoms - 4 * g);
+        double u0[12];
+        float raw0[12];
+        GroupLoader<CT, IMG, VEC, false>::load(p, s_row[0], g, nv, s_box[0], u0, raw0);
+#pragma unroll
+        for (int k = 0; k < kLagChunk; ++k) {
+            if (k < w.nl) {
+                double ut[12];
+                float rawt[12];
+                GroupLoader<CT, IMG, VEC, true>::load(p, s_row[k + 1], g, nv, s_box[k + 1], ut, rawt);
+                eval_group<FLAGS, kHistF32>(p, u0, raw0, ut, rawt, nv, k, acc, s_hist, s_edges);
+            }
+        }
+    }
+    cta_epilogue<FLAGS>(p, w, tid, acc, s_red, s_hist, [] { __syncthreads(); });
+}
+
+// =================================================================================================
+// product path: cp.async.bulk (TMA) -> shared-memory ring -> compute warps
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) {
+    return (uint32_t)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy executed by the TMA engine; completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void compute_barrier() {  // named barrier 1: the kThreads compute threads
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+}
+
+template <bool IMG, int FLAGS, int NS>
+__global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDev p) {
+    constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
+    constexpr bool kHistF32 = kHist && !IMG;
+    constexpr int kStageBytes = kCoordTileBytes + (IMG ? kImgTileBytes : 0);
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];   // [NS stages][hist][edges]
+    __shared__ int s_row[kLagChunk + 1];
+    __shared__ double s_box[kLagChunk + 1][3];
+    __shared__ double s_red[kWarps][kLagChunk * 3];
+    __shared__ __align__(8) uint64_t s_full[NS];
+    __shared__ __align__(8) uint64_t s_empty[NS];
+
+    const CtaWork w = cta_work(p);
+    const int tid = threadIdx.x;
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem_raw + (size_t)NS * kStageBytes);
+    double *s_edges = reinterpret_cast<double *>(smem_raw + (size_t)NS * kStageBytes +
+                                                 (size_t)kLagChunk * p.n_bins * sizeof(unsigned int));
+
+    load_rows<IMG>(p, w, tid, s_row, s_box);
+    if (tid == kThreads) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&s_full[i], 1);          // one arrive.expect_tx by the producer
+            mbar_init(&s_empty[i], kWarps);    // one arrive per compute warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (kHist) {
+        for (int i = tid; i < kLagChunk * p.n_bins; i += kBulkThreads) s_hist[i] = 0u;
+        if (p.bin_mode == MDB_BINS_EDGES)
+            for (int i = tid; i <= p.n_bins; i += kBulkThreads) s_edges[i] = p.edges[i];
+    }
+    __syncthreads();
+
+    // atom range of this CTA in tiles of kTileAtoms (groups_per_block is a multiple of kThreads)
+    const int g_begin = w.ab * p.groups_per_block;
+    const int g_end = min(p.n_groups, g_begin + p.groups_per_block);
+    const int n_tiles = (g_end - g_begin + kThreads - 1) / kThreads;
+    const int n_units = w.nl + 1;   // origin + lag rows per tile
+
+    if (tid >= kThreads) {
+        // ===== producer warp: one elected lane feeds the ring =====
+        if (tid == kThreads) {
+            const long long row_floats = p.pitch;
+            uint32_t stage = 0, phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const long long first_float = 12ll * (g_begin + (long long)t * kThreads);
+                // the padded row end bounds the copy; both sizes stay multiples of 16 bytes
+                const uint32_t cbytes = (uint32_t)min((long long)kCoordTileBytes, (row_floats - first_float) * 4);
+                const uint32_t ibytes = IMG ? (uint32_t)min((long long)kImgTileBytes, p.img_pitch - first_float) : 0u;
+                for (int u = 0; u < n_units; ++u) {
+                    const int row = s_row[u];
+                    mbar_wait(&s_empty[stage], phase ^ 1);
+                    unsigned char *dst = smem_raw + (size_t)stage * kStageBytes;
+                    mbar_expect_tx(&s_full[stage], cbytes + ibytes);
+                    bulk_g2s(dst, static_cast<const float *>(p.coords) + (long long)row * row_floats + first_float,
+                             cbytes, &s_full[stage]);
+                    if (IMG)
+                        bulk_g2s(dst + kCoordTileBytes, p.images + (long long)row * p.img_pitch + first_float, ibytes,
+                                 &s_full[stage]);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== compute warps =====
+    Accum<FLAGS> acc;
+    acc.clear();
+    const int lane = tid & 31;
+    uint32_t stage = 0, phase = 0;
+
+    auto fetch = [&](int nv, const double *bx, double (&u)[12], float (&raw)[12]) {
+        mbar_wait(&s_full[stage], phase);
+        const unsigned char *src = smem_raw + (size_t)stage * kStageBytes;
+        const float4 *c4 = reinterpret_cast<const float4 *>(src) + 3 * tid;
+        const float4 a = c4[0], b = c4[1], c = c4[2];
+        uint32_t wds[3] = {0u, 0u, 0u};
+        if (IMG) {
+            const uint32_t *iw = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes) + 3 * tid;
+            wds[0] = iw[0]; wds[1] = iw[1]; wds[2] = iw[2];
+        }
+        raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
+        raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+        raw[8] = c.x; raw[9] = c.y; raw[10] = c.z; raw[11] = c.w;
+        // values are in registers: hand the stage back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+        if (nv < 4) {
+            // last group of the shard: whatever lies beyond atom n_atoms-1 becomes (0,0,0), n = 0
+#pragma unroll
+            for (int cc = 0; cc < 12; ++cc)
+                if (cc >= 3 * nv) {
+                    raw[cc] = 0.0f;
+                    wds[cc >> 2] &= ~(0xffu << (8 * (cc & 3)));
+                }
+        }
+        unwrap12<IMG>(raw, wds, bx, u);
+    };
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int g = g_begin + t * kThreads + tid;
+        const int nv = max(0, min(4, p.n_atoms - 4 * g));
+        double u0[12];
+        float raw0[12];
+        fetch(nv, s_box[0], u0, raw0);
+#pragma unroll
+        for (int k = 0; k < kLagChunk; ++k) {
+            if (k < w.nl) {
+                double ut[12];
+                float rawt[12];
+                fetch(nv, s_box[k + 1], ut, rawt);
+                eval_group<FLAGS, kHistF32>(p, u0, raw0, ut, rawt, nv, k, acc, s_hist, s_edges);
+            }
+        }
+    }
+    cta_epilogue<FLAGS>(p, w, tid, acc, s_red, s_hist, [] { compute_barrier(); });
 }
 
 __global__ void reduce_partials_kernel(const double *__restrict__ partial, double *__restrict__ sums,
@@ -305,10 +541,18 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, doubl
     sums[i] = v;
 }
 
+// =================================================================================================
+// host side
+// =================================================================================================
 struct Plan {
     int n_groups, n_chunks, n_ablocks, groups_per_block;
+    bool bulk;           // cp.async.bulk path
+    bool vec;            // 128-bit loads in the fallback path
+    int stages;
     size_t smem;
 };
+
+constexpr int kStagesImg = 6, kStagesRaw = 7;
 
 int make_plan(const mdb_corr_args *a, Plan *plan) {
     if (!a) return fail(MDB_ERR_ARGUMENT, "args is NULL");
@@ -319,26 +563,46 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
     if (a->pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "pitch < 3*n_atoms");
     plan->n_groups = (a->n_atoms + 3) / 4;
     plan->n_chunks = (a->n_lags + kLagChunk - 1) / kLagChunk;
+
+    const size_t esz = a->coord_type == MDB_F32 ? 4 : 8;
+    plan->vec = (reinterpret_cast<uintptr_t>(a->coords) % 16 == 0) && ((a->pitch * esz) % 16 == 0);
+    if (a->images)
+        plan->vec = plan->vec && (reinterpret_cast<uintptr_t>(a->images) % 4 == 0) && (a->img_pitch % 4 == 0);
+    // bulk copies need 16-byte aligned sources and sizes: float32 rows with pitch % 4 == 0 and, for the
+    // image rows, pitch % 16 == 0 (engine.row_pitch pads rows to 128 bytes, so stores built by the
+    // package always qualify)
+    plan->bulk = a->coord_type == MDB_F32 && plan->vec;
+    if (a->images)
+        plan->bulk = plan->bulk && (reinterpret_cast<uintptr_t>(a->images) % 16 == 0) && (a->img_pitch % 16 == 0);
+
+    size_t hist_smem = 0;
+    if (a->flags & MDB_HIST) {
+        if (a->n_bins <= 0) return fail(MDB_ERR_ARGUMENT, "n_bins must be positive with MDB_HIST");
+        hist_smem = (size_t)kLagChunk * a->n_bins * sizeof(unsigned int);
+        if (a->bin_mode == MDB_BINS_EDGES) hist_smem += (size_t)(a->n_bins + 1) * sizeof(double);
+    }
+    plan->stages = a->images ? kStagesImg : kStagesRaw;
+    const size_t stage_bytes = kCoordTileBytes + (a->images ? kImgTileBytes : 0);
+    size_t bulk_smem = plan->stages * stage_bytes + hist_smem;
+    if (plan->bulk && bulk_smem > 220 * 1024) plan->bulk = false;   // huge histograms: fall back
+    plan->smem = plan->bulk ? bulk_smem : hist_smem;
+    if (plan->smem > 220 * 1024)
+        return fail(MDB_ERR_UNSUPPORTED, "n_bins=%d needs %zu bytes of shared memory (limit 220 KiB)", a->n_bins,
+                    plan->smem);
+
     int sms = 148;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // enough CTAs for ~8 per SM, but at least ~4 iterations of work per thread
+    // atom blocks: enough CTAs for ~8 per SM, each a whole number of 1024-atom tiles
     const long long base = (long long)a->n_origins * plan->n_chunks;
     long long want = (8ll * sms + base - 1) / base;
-    const long long max_blocks = (plan->n_groups + 4ll * kThreads - 1) / (4ll * kThreads);
+    const long long n_tiles = (plan->n_groups + kThreads - 1) / kThreads;
+    const long long max_blocks = (n_tiles + 3) / 4;                  // at least ~4 tiles per CTA
     if (want > max_blocks) want = max_blocks;
     if (want < 1) want = 1;
-    plan->n_ablocks = (int)want;
-    plan->groups_per_block = (plan->n_groups + plan->n_ablocks - 1) / plan->n_ablocks;
-    plan->smem = 0;
-    if (a->flags & MDB_HIST) {
-        if (a->n_bins <= 0) return fail(MDB_ERR_ARGUMENT, "n_bins must be positive with MDB_HIST");
-        plan->smem = (size_t)kLagChunk * a->n_bins * sizeof(unsigned int);
-        if (a->bin_mode == MDB_BINS_EDGES) plan->smem += (size_t)(a->n_bins + 1) * sizeof(double);
-        if (plan->smem > 200 * 1024)
-            return fail(MDB_ERR_UNSUPPORTED, "n_bins=%d needs %zu bytes of shared memory (limit 200 KiB)",
-                        a->n_bins, plan->smem);
-    }
+    const long long tiles_per_block = (n_tiles + want - 1) / want;
+    plan->groups_per_block = (int)(tiles_per_block * kThreads);
+    plan->n_ablocks = (int)((n_tiles + tiles_per_block - 1) / tiles_per_block);
     return MDB_OK;
 }
 
@@ -352,16 +616,15 @@ Profile &profile() {
     return pr;
 }
 
-template <typename CT, bool IMG, int FLAGS>
-int launch_flags(const CorrDev &p, const Plan &plan, bool vec, cudaStream_t st) {
+template <typename Kernel>
+int launch_kernel(Kernel kern, const CorrDev &p, const Plan &plan, int threads, cudaStream_t st) {
     const long long blocks = (long long)p.S * p.n_chunks * p.n_ablocks;
     if (blocks > 2147483647ll) return fail(MDB_ERR_UNSUPPORTED, "grid too large");
-    auto kern = vec ? corr_kernel<CT, IMG, FLAGS, true> : corr_kernel<CT, IMG, FLAGS, false>;
     if (plan.smem > 40 * 1024)
         MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     Profile &pr = profile();
     if (pr.enabled) MDB_CUDA_CHECK(cudaEventRecord(pr.start, st));
-    kern<<<(unsigned)blocks, kThreads, plan.smem, st>>>(p);
+    kern<<<(unsigned)blocks, threads, plan.smem, st>>>(p);
     MDB_CUDA_CHECK(cudaGetLastError());
     if (pr.enabled) {
         MDB_CUDA_CHECK(cudaEventRecord(pr.stop, st));
@@ -370,18 +633,30 @@ int launch_flags(const CorrDev &p, const Plan &plan, bool vec, cudaStream_t st) 
     return MDB_OK;
 }
 
+template <typename CT, bool IMG, int FLAGS>
+int launch_flags(const CorrDev &p, const Plan &plan, cudaStream_t st) {
+    if constexpr (sizeof(CT) == 4) {
+        if (plan.bulk) {
+            if (IMG) return launch_kernel(corr_bulk_kernel<IMG, FLAGS, kStagesImg>, p, plan, kBulkThreads, st);
+            return launch_kernel(corr_bulk_kernel<IMG, FLAGS, kStagesRaw>, p, plan, kBulkThreads, st);
+        }
+    }
+    if (plan.vec) return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, true>, p, plan, kThreads, st);
+    return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, false>, p, plan, kThreads, st);
+}
+
 template <typename CT, bool IMG>
-int launch_typed(const CorrDev &p, const Plan &plan, int flags, bool vec, cudaStream_t st) {
+int launch_typed(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st) {
     constexpr int R2 = MDB_SUM_R2, R4 = MDB_SUM_R4, SC = MDB_SUM_SINC, H = MDB_HIST;
     switch (flags) {
-        case R2: return launch_flags<CT, IMG, R2>(p, plan, vec, st);
-        case SC: return launch_flags<CT, IMG, SC>(p, plan, vec, st);
-        case R2 | R4: return launch_flags<CT, IMG, R2 | R4>(p, plan, vec, st);
-        case H: return launch_flags<CT, IMG, H>(p, plan, vec, st);
+        case R2: return launch_flags<CT, IMG, R2>(p, plan, st);
+        case SC: return launch_flags<CT, IMG, SC>(p, plan, st);
+        case R2 | R4: return launch_flags<CT, IMG, R2 | R4>(p, plan, st);
+        case H: return launch_flags<CT, IMG, H>(p, plan, st);
         default:
             // any other mix: the scalar sums together, optionally with the histogram
-            if (flags & H) return launch_flags<CT, IMG, R2 | R4 | SC | H>(p, plan, vec, st);
-            return launch_flags<CT, IMG, R2 | R4 | SC>(p, plan, vec, st);
+            if (flags & H) return launch_flags<CT, IMG, R2 | R4 | SC | H>(p, plan, st);
+            return launch_flags<CT, IMG, R2 | R4 | SC>(p, plan, st);
     }
 }
 
@@ -444,21 +719,15 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     p.partial = static_cast<double *>(a->workspace);
     p.hist = a->hist;
 
-    const size_t esz = a->coord_type == MDB_F32 ? 4 : 8;
-    // 128-bit loads need 16-byte aligned rows: base pointer and pitch (and the image rows: 4 bytes)
-    bool vec = (reinterpret_cast<uintptr_t>(a->coords) % 16 == 0) && ((a->pitch * esz) % 16 == 0);
-    if (a->images)
-        vec = vec && (reinterpret_cast<uintptr_t>(a->images) % 4 == 0) && (a->img_pitch % 4 == 0);
-
     int launches = 0;
     if (hist) {
         MDB_CUDA_CHECK(cudaMemsetAsync(a->hist, 0,
                                        (size_t)a->n_origins * a->n_lags * a->n_bins * sizeof(unsigned long long), st));
     }
     int rc;
-    if (a->coord_type == MDB_F64) rc = launch_typed<double, false>(p, plan, a->flags, vec, st);
-    else if (a->images) rc = launch_typed<float, true>(p, plan, a->flags, vec, st);
-    else rc = launch_typed<float, false>(p, plan, a->flags, vec, st);
+    if (a->coord_type == MDB_F64) rc = launch_typed<double, false>(p, plan, a->flags, st);
+    else if (a->images) rc = launch_typed<float, true>(p, plan, a->flags, st);
+    else rc = launch_typed<float, false>(p, plan, a->flags, st);
     if (rc) return rc;
     ++launches;
     const long long n_out = (long long)a->n_origins * a->n_lags * 3;
