@@ -128,29 +128,34 @@ struct Accum {
     }
 };
 
-// One group of 4 atoms against one lag frame.  Atoms beyond `nv` (only in the last group of the
-// shard) carry zeroed inputs on both sides: they add exactly 0 to the r^2 / r^4 sums and exactly
-// 1.0f each to the sinc sum, which is taken off again; the histogram skips them.
-template <int FLAGS, bool HIST_F32>
+// One group of 4 atoms against one lag frame: partial sums of r^2, r^4 (float64) and sinc (float32)
+// over the group, histogram counts straight into shared memory.  MASKED is only instantiated for
+// the last group(s) of a shard: atoms beyond `nv` carry zeroed inputs on both sides, so they add
+// exactly 0 to the r^2 / r^4 sums and exactly 1.0f each to the sinc sum, which is taken off again;
+// the histogram skips them.
+template <int FLAGS, bool HIST_F32, bool MASKED>
 __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[12], const float (&raw0)[12],
-                                           const double (&ut)[12], const float (&rawt)[12], int nv, const int K,
-                                           Accum<FLAGS> &acc, unsigned int *s_hist, const double *s_edges) {
+                                           const double (&ut)[12], const float (&rawt)[12], int nv,
+                                           double &sum2, double &sum4, float &sums, unsigned int *s_hist_k,
+                                           const double *s_edges) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
-    float sinc4 = 0.0f;
+    sum2 = 0.0;
+    sum4 = 0.0;
+    sums = 0.0f;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const double ddx = u0[3 * a] - ut[3 * a];
         const double ddy = u0[3 * a + 1] - ut[3 * a + 1];
         const double ddz = u0[3 * a + 2] - ut[3 * a + 2];
         const double r2 = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
-        if constexpr (kR2) acc.r2[K] += r2;
-        if constexpr (kR4) acc.r4[K] = fma(r2, r2, acc.r4[K]);
-        if constexpr (kSinc) sinc4 += sinc_of_square((float)(r2 * p.q2));
+        if constexpr (kR2) sum2 += r2;
+        if constexpr (kR4) sum4 = fma(r2, r2, sum4);
+        if constexpr (kSinc) sums += sinc_of_square((float)(r2 * p.q2));
         if constexpr (kHist) {
-            if (a < nv) {
+            if (!MASKED || a < nv) {
                 int bin = -1;
                 if (HIST_F32) {
                     // raw float32 frames: the reference computes r in float32 (correlation.py:246-247
@@ -181,11 +186,11 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
                 } else {
                     bin = edge_bin(sqrt(r2_unfused(ddx, ddy, ddz)), s_edges, p.n_bins);
                 }
-                if (bin >= 0) atomicAdd(&s_hist[K * p.n_bins + bin], 1u);
+                if (bin >= 0) atomicAdd(&s_hist_k[bin], 1u);
             }
         }
     }
-    if constexpr (kSinc) acc.sc[K] += (double)(sinc4 - (float)(4 - nv));
+    if constexpr (kSinc && MASKED) sums -= (float)(4 - nv);
 }
 
 // CTA prologue shared by both kernels: which (origin, chunk, atom block) am I, rows and boxes.
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) 
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
     constexpr bool kHistF32 = kHist && sizeof(CT) == 4 && !IMG;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_row[kLagChunk + 1];
     __shared__ double s_box[kLagChunk + 1][3];
     __shared__ double s_red[kWarps][kLagChunk * 3];
@@ -362,7 +367,13 @@ __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) 
                 double ut[12];
                 float rawt[12];
                 GroupLoader<CT, IMG, VEC, true>::load(p, s_row[k + 1], g, nv, s_box[k + 1], ut, rawt);
-                eval_group<FLAGS, kHistF32>(p, u0, raw0, ut, rawt, nv, k, acc, s_hist, s_edges);
+                double s2, s4;
+                float ss;
+                eval_group<FLAGS, kHistF32, true>(p, u0, raw0, ut, rawt, nv, s2, s4, ss, s_hist + k * p.n_bins,
+                                                  s_edges);
+                if constexpr (Accum<FLAGS>::kR2) acc.r2[k] += s2;
+                if constexpr (Accum<FLAGS>::kR4) acc.r4[k] += s4;
+                if constexpr (Accum<FLAGS>::kSinc) acc.sc[k] += (double)ss;
             }
         }
     }
@@ -378,13 +389,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void *ptr) {
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// arrive executed by the lanes with pred != 0 (predicated, no divergent branch)
+__device__ __forceinline__ void mbar_arrive_if(uint32_t bar, uint32_t pred) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.u32 P1, %1, 0;\n"
+        "@P1 mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}" ::"r"(bar),
+        "r"(pred)
+        : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -393,49 +412,129 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
+        "}" ::"r"(bar),
         "r"(parity)
         : "memory");
 }
 // global -> shared bulk copy executed by the TMA engine; completes `bytes` on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 __device__ __forceinline__ void compute_barrier() {  // named barrier 1: the kThreads compute threads
     asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
 }
 
-template <bool IMG, int FLAGS, int NS>
-__global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDev p) {
+constexpr int kMaxStages = 8;
+
+// Ring position of a compute thread / the producer.
+struct Ring {
+    uint32_t stage, phase, n_stages;
+    __device__ __forceinline__ void advance() {
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+    }
+};
+
+// Take the calling thread's 4 atoms out of the current stage, release the stage, unwrap.
+template <bool IMG, bool MASKED>
+__device__ __forceinline__ void fetch_group(Ring &ring, uint32_t full0, uint32_t empty0, const unsigned char *stages,
+                                            int stage_bytes, int tid, int nv, const double *bx, double (&u)[12],
+                                            float (&raw)[12]) {
+    mbar_wait(full0 + 8 * ring.stage, ring.phase);
+    const unsigned char *src = stages + (size_t)ring.stage * stage_bytes;
+    const float4 *c4 = reinterpret_cast<const float4 *>(src) + 3 * tid;
+    const float4 a = c4[0], b = c4[1], c = c4[2];
+    uint32_t wds[3] = {0u, 0u, 0u};
+    if (IMG) {
+        const uint32_t *iw = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes) + 3 * tid;
+        wds[0] = iw[0]; wds[1] = iw[1]; wds[2] = iw[2];
+    }
+    raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
+    raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+    raw[8] = c.x; raw[9] = c.y; raw[10] = c.z; raw[11] = c.w;
+    // the values are in registers: hand the stage back (one arrive per warp; the warp's loads are a
+    // single converged instruction ahead of it in program order)
+    mbar_arrive_if(empty0 + 8 * ring.stage, (tid & 31) == 0);
+    ring.advance();
+    if (MASKED) {
+        // last tile of the shard: whatever lies beyond atom n_atoms-1 becomes (0,0,0), n = 0
+#pragma unroll
+        for (int cc = 0; cc < 12; ++cc)
+            if (cc >= 3 * nv) {
+                raw[cc] = 0.0f;
+                wds[cc >> 2] &= ~(0xffu << (8 * (cc & 3)));
+            }
+    }
+    unwrap12<IMG>(raw, wds, bx, u);
+}
+
+// One tile of 1024 atoms: origin group into registers, then the lag rows of the chunk one by one.
+// The loop over lags is NOT unrolled (the body is 4 evaluations, ~1 KiB of code, and stays in the
+// instruction cache); per-lag accumulators live in shared memory, one private column per thread.
+template <bool IMG, int FLAGS, bool MASKED>
+__device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
+                                             const unsigned char *stages, int stage_bytes, int tid, int nv, int nl,
+                                             const double (*s_box)[3], double *s_acc, unsigned int *s_hist,
+                                             const double *s_edges) {
+    constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
+    constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
     constexpr bool kHistF32 = kHist && !IMG;
+    constexpr int NV = (kR2 ? 1 : 0) + (kR4 ? 1 : 0) + (kSinc ? 1 : 0);
+    double u0[12];
+    float raw0[12];
+    fetch_group<IMG, MASKED>(ring, full0, empty0, stages, stage_bytes, tid, nv, s_box[0], u0, raw0);
+#pragma unroll 1
+    for (int k = 0; k < nl; ++k) {
+        double ut[12];
+        float rawt[12];
+        fetch_group<IMG, MASKED>(ring, full0, empty0, stages, stage_bytes, tid, nv, s_box[k + 1], ut, rawt);
+        double s2, s4;
+        float ss;
+        eval_group<FLAGS, kHistF32, MASKED>(p, u0, raw0, ut, rawt, nv, s2, s4, ss, s_hist + k * p.n_bins, s_edges);
+        double *col = s_acc + (size_t)k * NV * kThreads + tid;
+        int v = 0;
+        if constexpr (kR2) { col[v * kThreads] += s2; ++v; }
+        if constexpr (kR4) { col[v * kThreads] += s4; ++v; }
+        if constexpr (kSinc) { col[v * kThreads] += (double)ss; ++v; }
+    }
+}
+
+template <bool IMG, int FLAGS>
+__global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDev p, const int n_stages) {
+    constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
+    constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
+    constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
+    constexpr int NV = (kR2 ? 1 : 0) + (kR4 ? 1 : 0) + (kSinc ? 1 : 0);
     constexpr int kStageBytes = kCoordTileBytes + (IMG ? kImgTileBytes : 0);
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];   // [NS stages][hist][edges]
+    // dynamic shared memory: [n_stages stages][accumulators NV*kLagChunk*kThreads doubles][hist][edges]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_row[kLagChunk + 1];
     __shared__ double s_box[kLagChunk + 1][3];
     __shared__ double s_red[kWarps][kLagChunk * 3];
-    __shared__ __align__(8) uint64_t s_full[NS];
-    __shared__ __align__(8) uint64_t s_empty[NS];
+    __shared__ __align__(8) uint64_t s_full[kMaxStages];
+    __shared__ __align__(8) uint64_t s_empty[kMaxStages];
 
     const CtaWork w = cta_work(p);
     const int tid = threadIdx.x;
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem_raw + (size_t)NS * kStageBytes);
-    double *s_edges = reinterpret_cast<double *>(smem_raw + (size_t)NS * kStageBytes +
-                                                 (size_t)kLagChunk * p.n_bins * sizeof(unsigned int));
+    double *s_acc = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * kStageBytes);
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_acc + (size_t)NV * kLagChunk * kThreads);
+    double *s_edges = reinterpret_cast<double *>(s_hist + (size_t)kLagChunk * p.n_bins);
 
     load_rows<IMG>(p, w, tid, s_row, s_box);
     if (tid == kThreads) {
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
+        for (int i = 0; i < n_stages; ++i) {
             mbar_init(&s_full[i], 1);          // one arrive.expect_tx by the producer
             mbar_init(&s_empty[i], kWarps);    // one arrive per compute warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < kThreads)
+        for (int i = 0; i < NV * kLagChunk; ++i) s_acc[(size_t)i * kThreads + tid] = 0.0;
     if (kHist) {
         for (int i = tid; i < kLagChunk * p.n_bins; i += kBulkThreads) s_hist[i] = 0u;
         if (p.bin_mode == MDB_BINS_EDGES)
@@ -448,12 +547,14 @@ __global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDe
     const int g_end = min(p.n_groups, g_begin + p.groups_per_block);
     const int n_tiles = (g_end - g_begin + kThreads - 1) / kThreads;
     const int n_units = w.nl + 1;   // origin + lag rows per tile
+    const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
+    Ring ring{0u, 0u, (uint32_t)n_stages};
 
     if (tid >= kThreads) {
         // ===== producer warp: one elected lane feeds the ring =====
         if (tid == kThreads) {
             const long long row_floats = p.pitch;
-            uint32_t stage = 0, phase = 0;
+            const uint32_t stages0 = smem_u32(smem_raw);
             for (int t = 0; t < n_tiles; ++t) {
                 const long long first_float = 12ll * (g_begin + (long long)t * kThreads);
                 // the padded row end bounds the copy; both sizes stay multiples of 16 bytes
@@ -461,15 +562,16 @@ __global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDe
                 const uint32_t ibytes = IMG ? (uint32_t)min((long long)kImgTileBytes, p.img_pitch - first_float) : 0u;
                 for (int u = 0; u < n_units; ++u) {
                     const int row = s_row[u];
-                    mbar_wait(&s_empty[stage], phase ^ 1);
-                    unsigned char *dst = smem_raw + (size_t)stage * kStageBytes;
-                    mbar_expect_tx(&s_full[stage], cbytes + ibytes);
+                    mbar_wait(empty0 + 8 * ring.stage, ring.phase ^ 1);
+                    const uint32_t dst = stages0 + ring.stage * kStageBytes;
+                    const uint32_t bar = full0 + 8 * ring.stage;
+                    mbar_expect_tx(bar, cbytes + ibytes);
                     bulk_g2s(dst, static_cast<const float *>(p.coords) + (long long)row * row_floats + first_float,
-                             cbytes, &s_full[stage]);
+                             cbytes, bar);
                     if (IMG)
                         bulk_g2s(dst + kCoordTileBytes, p.images + (long long)row * p.img_pitch + first_float, ibytes,
-                                 &s_full[stage]);
-                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                                 bar);
+                    ring.advance();
                 }
             }
         }
@@ -477,55 +579,27 @@ __global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDe
     }
 
     // ===== compute warps =====
-    Accum<FLAGS> acc;
-    acc.clear();
-    const int lane = tid & 31;
-    uint32_t stage = 0, phase = 0;
-
-    auto fetch = [&](int nv, const double *bx, double (&u)[12], float (&raw)[12]) {
-        mbar_wait(&s_full[stage], phase);
-        const unsigned char *src = smem_raw + (size_t)stage * kStageBytes;
-        const float4 *c4 = reinterpret_cast<const float4 *>(src) + 3 * tid;
-        const float4 a = c4[0], b = c4[1], c = c4[2];
-        uint32_t wds[3] = {0u, 0u, 0u};
-        if (IMG) {
-            const uint32_t *iw = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes) + 3 * tid;
-            wds[0] = iw[0]; wds[1] = iw[1]; wds[2] = iw[2];
-        }
-        raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
-        raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
-        raw[8] = c.x; raw[9] = c.y; raw[10] = c.z; raw[11] = c.w;
-        // values are in registers: hand the stage back to the producer
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[stage]);
-        if (++stage == NS) { stage = 0; phase ^= 1; }
-        if (nv < 4) {
-            // last group of the shard: whatever lies beyond atom n_atoms-1 becomes (0,0,0), n = 0
-#pragma unroll
-            for (int cc = 0; cc < 12; ++cc)
-                if (cc >= 3 * nv) {
-                    raw[cc] = 0.0f;
-                    wds[cc >> 2] &= ~(0xffu << (8 * (cc & 3)));
-                }
-        }
-        unwrap12<IMG>(raw, wds, bx, u);
-    };
-
     for (int t = 0; t < n_tiles; ++t) {
-        const int g = g_begin + t * kThreads + tid;
-        const int nv = max(0, min(4, p.n_atoms - 4 * g));
-        double u0[12];
-        float raw0[12];
-        fetch(nv, s_box[0], u0, raw0);
-#pragma unroll
-        for (int k = 0; k < kLagChunk; ++k) {
-            if (k < w.nl) {
-                double ut[12];
-                float rawt[12];
-                fetch(nv, s_box[k + 1], ut, rawt);
-                eval_group<FLAGS, kHistF32>(p, u0, raw0, ut, rawt, nv, k, acc, s_hist, s_edges);
-            }
+        const int g_last = g_begin + t * kThreads + kThreads - 1;          // last group of this tile
+        if (4 * g_last + 3 < p.n_atoms) {
+            process_tile<IMG, FLAGS, false>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, 4, w.nl, s_box, s_acc,
+                                            s_hist, s_edges);
+        } else {
+            const int g = g_begin + t * kThreads + tid;
+            const int nv = max(0, min(4, p.n_atoms - 4 * g));
+            process_tile<IMG, FLAGS, true>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, nv, w.nl, s_box, s_acc,
+                                           s_hist, s_edges);
         }
+    }
+
+    Accum<FLAGS> acc;
+#pragma unroll
+    for (int k = 0; k < kLagChunk; ++k) {
+        const double *col = s_acc + (size_t)k * NV * kThreads + tid;
+        int v = 0;
+        if constexpr (kR2) { acc.r2[k] = col[v * kThreads]; ++v; }
+        if constexpr (kR4) { acc.r4[k] = col[v * kThreads]; ++v; }
+        if constexpr (kSinc) { acc.sc[k] = col[v * kThreads]; ++v; }
     }
     cta_epilogue<FLAGS>(p, w, tid, acc, s_red, s_hist, [] { compute_barrier(); });
 }
@@ -552,7 +626,15 @@ struct Plan {
     size_t smem;
 };
 
-constexpr int kStagesImg = 6, kStagesRaw = 7;
+constexpr size_t kSmemBudgetPerCta = 110 * 1024;   // two CTAs per SM
+
+// The kernel instantiation that serves a request: the four single-purpose kernels, or the
+// all-sums kernel (optionally with the histogram) for any other mix.
+int kernel_flags(int flags) {
+    constexpr int R2 = MDB_SUM_R2, R4 = MDB_SUM_R4, SC = MDB_SUM_SINC, H = MDB_HIST;
+    if (flags == R2 || flags == SC || flags == (R2 | R4) || flags == H) return flags;
+    return (flags & H) ? (R2 | R4 | SC | H) : (R2 | R4 | SC);
+}
 
 int make_plan(const mdb_corr_args *a, Plan *plan) {
     if (!a) return fail(MDB_ERR_ARGUMENT, "args is NULL");
@@ -581,10 +663,19 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
         hist_smem = (size_t)kLagChunk * a->n_bins * sizeof(unsigned int);
         if (a->bin_mode == MDB_BINS_EDGES) hist_smem += (size_t)(a->n_bins + 1) * sizeof(double);
     }
-    plan->stages = a->images ? kStagesImg : kStagesRaw;
     const size_t stage_bytes = kCoordTileBytes + (a->images ? kImgTileBytes : 0);
-    size_t bulk_smem = plan->stages * stage_bytes + hist_smem;
-    if (plan->bulk && bulk_smem > 220 * 1024) plan->bulk = false;   // huge histograms: fall back
+    const int kf = kernel_flags(a->flags);
+    const int nv_kernel = ((kf & MDB_SUM_R2) ? 1 : 0) + ((kf & MDB_SUM_R4) ? 1 : 0) + ((kf & MDB_SUM_SINC) ? 1 : 0);
+    const size_t acc_smem = (size_t)nv_kernel * kLagChunk * kThreads * sizeof(double);
+    // ring depth: what fits next to the accumulators / histogram with two CTAs per SM, 3..8 stages
+    plan->stages = 0;
+    if (acc_smem + hist_smem + 3 * stage_bytes <= kSmemBudgetPerCta)
+        plan->stages = (int)((kSmemBudgetPerCta - acc_smem - hist_smem) / stage_bytes);
+    else if (acc_smem + hist_smem + 3 * stage_bytes <= 220 * 1024)
+        plan->stages = (int)((220 * 1024 - acc_smem - hist_smem) / stage_bytes);   // one CTA per SM
+    if (plan->stages > kMaxStages) plan->stages = kMaxStages;
+    if (plan->stages < 3) plan->bulk = false;                      // huge histograms: fall back
+    const size_t bulk_smem = plan->stages * stage_bytes + acc_smem + hist_smem;
     plan->smem = plan->bulk ? bulk_smem : hist_smem;
     if (plan->smem > 220 * 1024)
         return fail(MDB_ERR_UNSUPPORTED, "n_bins=%d needs %zu bytes of shared memory (limit 220 KiB)", a->n_bins,
@@ -616,15 +707,15 @@ Profile &profile() {
     return pr;
 }
 
-template <typename Kernel>
-int launch_kernel(Kernel kern, const CorrDev &p, const Plan &plan, int threads, cudaStream_t st) {
+template <typename Kernel, typename... Extra>
+int launch_kernel(Kernel kern, const CorrDev &p, const Plan &plan, int threads, cudaStream_t st, Extra... extra) {
     const long long blocks = (long long)p.S * p.n_chunks * p.n_ablocks;
     if (blocks > 2147483647ll) return fail(MDB_ERR_UNSUPPORTED, "grid too large");
     if (plan.smem > 40 * 1024)
         MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     Profile &pr = profile();
     if (pr.enabled) MDB_CUDA_CHECK(cudaEventRecord(pr.start, st));
-    kern<<<(unsigned)blocks, threads, plan.smem, st>>>(p);
+    kern<<<(unsigned)blocks, threads, plan.smem, st>>>(p, extra...);
     MDB_CUDA_CHECK(cudaGetLastError());
     if (pr.enabled) {
         MDB_CUDA_CHECK(cudaEventRecord(pr.stop, st));
@@ -636,10 +727,7 @@ int launch_kernel(Kernel kern, const CorrDev &p, const Plan &plan, int threads, 
 template <typename CT, bool IMG, int FLAGS>
 int launch_flags(const CorrDev &p, const Plan &plan, cudaStream_t st) {
     if constexpr (sizeof(CT) == 4) {
-        if (plan.bulk) {
-            if (IMG) return launch_kernel(corr_bulk_kernel<IMG, FLAGS, kStagesImg>, p, plan, kBulkThreads, st);
-            return launch_kernel(corr_bulk_kernel<IMG, FLAGS, kStagesRaw>, p, plan, kBulkThreads, st);
-        }
+        if (plan.bulk) return launch_kernel(corr_bulk_kernel<IMG, FLAGS>, p, plan, kBulkThreads, st, plan.stages);
     }
     if (plan.vec) return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, true>, p, plan, kThreads, st);
     return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, false>, p, plan, kThreads, st);
@@ -648,15 +736,13 @@ int launch_flags(const CorrDev &p, const Plan &plan, cudaStream_t st) {
 template <typename CT, bool IMG>
 int launch_typed(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st) {
     constexpr int R2 = MDB_SUM_R2, R4 = MDB_SUM_R4, SC = MDB_SUM_SINC, H = MDB_HIST;
-    switch (flags) {
+    switch (kernel_flags(flags)) {
         case R2: return launch_flags<CT, IMG, R2>(p, plan, st);
         case SC: return launch_flags<CT, IMG, SC>(p, plan, st);
         case R2 | R4: return launch_flags<CT, IMG, R2 | R4>(p, plan, st);
         case H: return launch_flags<CT, IMG, H>(p, plan, st);
-        default:
-            // any other mix: the scalar sums together, optionally with the histogram
-            if (flags & H) return launch_flags<CT, IMG, R2 | R4 | SC | H>(p, plan, st);
-            return launch_flags<CT, IMG, R2 | R4 | SC>(p, plan, st);
+        case R2 | R4 | SC | H: return launch_flags<CT, IMG, R2 | R4 | SC | H>(p, plan, st);
+        default: return launch_flags<CT, IMG, R2 | R4 | SC>(p, plan, st);
     }
 }
 
