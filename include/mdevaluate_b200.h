@@ -39,6 +39,9 @@ typedef enum mdb_status {
     MDB_ERR_WORKSPACE = 4     /* workspace missing or too small */
 } mdb_status;
 
+/* image counts are stored as uint8 = count + MDB_IMAGE_BIAS */
+#define MDB_IMAGE_BIAS 128
+
 /* coordinate element type */
 #define MDB_F32 0
 #define MDB_F64 1
@@ -68,8 +71,9 @@ int mdb_device_info(int *sm_count, int *cc_major, int *cc_minor);
  *
  * Storage: `coords` is a row-major block of frame rows, row r = `coords + r*pitch` holding
  * `3*n_atoms` interleaved xyz values (float32 as delivered by a trajectory reader, or float64
- * for already unwrapped frames).  With `images` != NULL every row also has int8 cumulative
- * periodic image counts n (row r at `images + r*img_pitch`, 3*n_atoms bytes) and a box diagonal
+ * for already unwrapped frames).  With `images` != NULL every row also has cumulative periodic
+ * image counts n, one byte per component stored excess-128 (uint8 = n + MDB_IMAGE_BIAS; row r at
+ * `images + r*img_pitch`, 3*n_atoms bytes, as written by mdb_nojump_scan) and a box diagonal
  * `box[3*r .. 3*r+2]`; the kernels then use the unwrapped position  x - n*box  evaluated in
  * float64, which is exactly the float64 frame `pbc.nojump` returns (pbc.py:235-247).
  *
@@ -86,7 +90,7 @@ typedef struct mdb_corr_args {
     const void *coords;          /* DEVICE [n_rows][pitch] of coord_type                        */
     int64_t pitch;               /* elements per row, >= 3*n_atoms                              */
     int32_t coord_type;          /* MDB_F32 or MDB_F64                                           */
-    const int8_t *images;        /* DEVICE [n_rows][img_pitch] or NULL (raw / pre-unwrapped)     */
+    const uint8_t *images;       /* DEVICE [n_rows][img_pitch] excess-128, or NULL (raw / unwrapped) */
     int64_t img_pitch;           /* bytes per image row, >= 3*n_atoms                            */
     const double *box;           /* DEVICE [n_rows][3] box diagonals; required iff images        */
     int32_t n_atoms;             /* atoms of this shard                                          */
@@ -136,18 +140,18 @@ typedef struct mdb_nojump_args {
     float *prev;                 /* DEVICE [3*n_atoms] in/out carry: last frame seen             */
     int32_t *cum;                /* DEVICE [3*n_atoms] in/out carry: running image counts        */
     const int32_t *out_row;      /* DEVICE [n_frames] destination row per frame, <0 = drop; NULL = identity */
-    int8_t *images;              /* DEVICE out, cumulative counts per kept frame, or NULL        */
+    uint8_t *images;             /* DEVICE out, cumulative counts (excess-128) per kept frame, or NULL */
     int64_t img_pitch;           /* bytes per row of images / jumps                              */
     int8_t *jumps;               /* DEVICE out, per-step jumps J_t per kept frame, or NULL       */
     float *coords_out;           /* DEVICE out, copy of kept frames (compaction), or NULL        */
     int64_t pitch_out;           /* floats per row of coords_out                                 */
-    int32_t *overflow;           /* DEVICE int, set to 1 if a running count left int8 range      */
+    int32_t *overflow;           /* DEVICE int, set to 1 if a running count left [-128, 127]     */
 } mdb_nojump_args;
 
 int mdb_nojump_scan(const mdb_nojump_args *args, void *stream);
 
 /* nojump, consumer side (pbc.py:235-247): out = x - n*box in float64 for one frame row. */
-int mdb_nojump_apply(const float *coords_row, const int8_t *images_row, const double box[3],
+int mdb_nojump_apply(const float *coords_row, const uint8_t *images_row, const double box[3],
                      int32_t n_atoms, double *out, void *stream);
 
 #ifdef __cplusplus

@@ -5,8 +5,8 @@ Layout in HBM:
 
 * ``coords``  float32 ``(n_rows, pitch)``: one frame per row, xyz interleaved, ``pitch`` a multiple
   of 4 floats so that every row is 16-byte aligned (float4 streaming);
-* ``images``  int8 ``(n_rows, img_pitch)``: cumulative periodic image counts per component, same
-  element order as ``coords`` (only for nojump);
+* ``images``  uint8 ``(n_rows, img_pitch)``: cumulative periodic image counts per component stored
+  excess-128 (``count + IMAGE_BIAS``), same element order as ``coords`` (only for nojump);
 * ``box``     float64 ``(n_rows, 3)``: box diagonal of the frame stored in each row.
 """
 from __future__ import annotations
@@ -16,6 +16,9 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _lib
+
+
+IMAGE_BIAS = 128
 
 
 def _round_up(x, m):

@@ -208,7 +208,7 @@ class Resident:
         if store.images is None:
             if store.coords.dtype != torch.float32:
                 raise _lib.CudaPathError('nojump needs float32 wrapped positions')
-            images = torch.empty((self.n_frames, self.pitch), dtype=torch.int8, device=self.device)
+            images = torch.empty((self.n_frames, self.pitch), dtype=torch.uint8, device=self.device)
             self._scan_all(images=images)
             store.images = images
             store.box = self._box_rows(range(self.n_frames))
@@ -232,7 +232,7 @@ class Resident:
         n3 = 3 * self.n_atoms
         if nojump:
             coords = torch.empty((n_rows, self.pitch), dtype=torch.float32, device=self.device)
-            images = torch.empty((n_rows, self.pitch), dtype=torch.int8, device=self.device)
+            images = torch.empty((n_rows, self.pitch), dtype=torch.uint8, device=self.device)
             out_row = torch.from_numpy(f2r).to(self.device)
             self._scan_all(images=images, out_row=out_row, coords_out=coords)
             store = engine.DeviceStore(coords, self.n_atoms, images=images, box=self._box_rows(frame_ids),

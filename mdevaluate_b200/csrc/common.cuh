@@ -30,9 +30,12 @@ __device__ __forceinline__ double int_to_double(int n) {
     return __hiloint2double(0x43300000, n ^ 0x80000000) - 4503601774854144.0;
 }
 
-// byte j (0..3) of a 32-bit word, sign-extended
-__device__ __forceinline__ int sbyte(uint32_t w, int j) {
-    return (int)(int8_t)((w >> (8 * j)) & 0xffu);
+// Image counts are stored excess-128 (uint8 = n + 128): byte j of a packed word becomes the double n
+// with one byte-permute and one DADD on the FP64 pipe (2^52 + b, minus 2^52 + 128) -- no sign
+// extension, no int->double conversion on the (contended) conversion pipe.
+__device__ __forceinline__ double image_count(uint32_t w, int j) {
+    const uint32_t b = (w >> (8 * j)) & 0xffu;
+    return __hiloint2double(0x43300000, (int)b) - 4503599627370624.0;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

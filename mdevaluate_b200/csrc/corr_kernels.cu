@@ -29,6 +29,8 @@
 // accumulator.  Histogram bins follow utils.histogram exactly (utils.py:328-338): a float32
 // estimate decides every sample that is not within rounding distance of a bin edge, the rest
 // take the exact float64 path (np.floor_divide semantics or np.histogram edge search).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mdb {
@@ -45,7 +47,7 @@ constexpr int kBulkThreads = kThreads + 32;       // + one producer warp
 struct CorrDev {
     const void *coords;
     long long pitch;
-    const int8_t *images;
+    const uint8_t *images;
     long long img_pitch;
     const double *box;
     int n_atoms;
@@ -72,7 +74,7 @@ __device__ __forceinline__ void unwrap12(const float (&raw)[12], const uint32_t 
         const double b0 = bx[0], b1 = bx[1], b2 = bx[2];
 #pragma unroll
         for (int c = 0; c < 12; ++c) {
-            const double n = int_to_double(sbyte(w[c >> 2], c & 3));
+            const double n = image_count(w[c >> 2], c & 3);
             const double b = (c % 3 == 0) ? b0 : ((c % 3 == 1) ? b1 : b2);
             u[c] = fma(-n, b, (double)raw[c]);
         }
@@ -280,7 +282,7 @@ struct GroupLoader<float, IMG, VEC, STREAM> {
     __device__ static __forceinline__ void load(const CorrDev &p, int row, int g, int nv, const double *bx,
                                                 double (&u)[12], float (&raw)[12]) {
         const float *base = static_cast<const float *>(p.coords) + (long long)row * p.pitch + 12ll * g;
-        uint32_t w[3] = {0u, 0u, 0u};
+        uint32_t w[3] = {0x80808080u, 0x80808080u, 0x80808080u};   // n = 0 in excess-128
         if (VEC && nv == 4) {
             const float4 *b4 = reinterpret_cast<const float4 *>(base);
             float4 a, b, c;
@@ -294,7 +296,7 @@ struct GroupLoader<float, IMG, VEC, STREAM> {
             for (int c = 0; c < 12; ++c) raw[c] = (c < 3 * nv) ? __ldg(base + c) : 0.0f;
         }
         if (IMG) {
-            const int8_t *ib = p.images + (long long)row * p.img_pitch + 12ll * g;
+            const uint8_t *ib = p.images + (long long)row * p.img_pitch + 12ll * g;
             if (VEC && nv == 4) {
                 const uint32_t *iw = reinterpret_cast<const uint32_t *>(ib);
                 if (STREAM) { w[0] = ld_stream(iw); w[1] = ld_stream(iw + 1); w[2] = ld_stream(iw + 2); }
@@ -302,7 +304,8 @@ struct GroupLoader<float, IMG, VEC, STREAM> {
             } else {
 #pragma unroll
                 for (int c = 0; c < 12; ++c)
-                    if (c < 3 * nv) w[c >> 2] |= ((uint32_t)(uint8_t)ib[c]) << (8 * (c & 3));
+                    if (c < 3 * nv)
+                        w[c >> 2] = (w[c >> 2] & ~(0xffu << (8 * (c & 3)))) | ((uint32_t)ib[c] << (8 * (c & 3)));
             }
         }
         unwrap12<IMG>(raw, w, bx, u);
@@ -445,7 +448,7 @@ __device__ __forceinline__ void fetch_group(Ring &ring, uint32_t full0, uint32_t
     const unsigned char *src = stages + (size_t)ring.stage * stage_bytes;
     const float4 *c4 = reinterpret_cast<const float4 *>(src) + 3 * tid;
     const float4 a = c4[0], b = c4[1], c = c4[2];
-    uint32_t wds[3] = {0u, 0u, 0u};
+    uint32_t wds[3] = {0x80808080u, 0x80808080u, 0x80808080u};
     if (IMG) {
         const uint32_t *iw = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes) + 3 * tid;
         wds[0] = iw[0]; wds[1] = iw[1]; wds[2] = iw[2];
@@ -463,7 +466,7 @@ __device__ __forceinline__ void fetch_group(Ring &ring, uint32_t full0, uint32_t
         for (int cc = 0; cc < 12; ++cc)
             if (cc >= 3 * nv) {
                 raw[cc] = 0.0f;
-                wds[cc >> 2] &= ~(0xffu << (8 * (cc & 3)));
+                wds[cc >> 2] = (wds[cc >> 2] & ~(0xffu << (8 * (cc & 3)))) | (0x80u << (8 * (cc & 3)));
             }
     }
     unwrap12<IMG>(raw, wds, bx, u);
@@ -674,6 +677,8 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
     else if (acc_smem + hist_smem + 3 * stage_bytes <= 220 * 1024)
         plan->stages = (int)((220 * 1024 - acc_smem - hist_smem) / stage_bytes);   // one CTA per SM
     if (plan->stages > kMaxStages) plan->stages = kMaxStages;
+    if (const char *env = getenv("MDB_STAGES"))
+        if (atoi(env) >= 2 && atoi(env) <= plan->stages) plan->stages = atoi(env);              // tuning aid
     if (plan->stages < 3) plan->bulk = false;                      // huge histograms: fall back
     const size_t bulk_smem = plan->stages * stage_bytes + acc_smem + hist_smem;
     plan->smem = plan->bulk ? bulk_smem : hist_smem;
@@ -691,6 +696,7 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
     const long long max_blocks = (n_tiles + 3) / 4;                  // at least ~4 tiles per CTA
     if (want > max_blocks) want = max_blocks;
     if (want < 1) want = 1;
+    if (const char *env = getenv("MDB_ABLOCKS")) want = atoll(env) > 0 ? atoll(env) : want;   // tuning aid
     const long long tiles_per_block = (n_tiles + want - 1) / want;
     plan->groups_per_block = (int)(tiles_per_block * kThreads);
     plan->n_ablocks = (int)((n_tiles + tiles_per_block - 1) / tiles_per_block);

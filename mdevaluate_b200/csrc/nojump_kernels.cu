@@ -30,7 +30,7 @@ struct NojumpDev {
     float *prev;
     int *cum;
     const int *out_row;
-    int8_t *images;
+    uint8_t *images;   // excess-128
     long long img_pitch;
     int8_t *jumps;
     float *coords_out;
@@ -120,10 +120,13 @@ __global__ void __launch_bounds__(kThreads) nojump_scan_kernel(const NojumpDev p
                 const int orow = p.out_row ? p.out_row[t] : t;
                 if (orow >= 0) {
                     if (p.images) {
-                        int8_t *dst = p.images + (long long)orow * p.img_pitch + e0;
-                        if (full) *reinterpret_cast<uint32_t *>(dst) = pack4(cum[0], cum[1], cum[2], cum[3]);
+                        uint8_t *dst = p.images + (long long)orow * p.img_pitch + e0;
+                        if (full)
+                            *reinterpret_cast<uint32_t *>(dst) =
+                                pack4(cum[0] + MDB_IMAGE_BIAS, cum[1] + MDB_IMAGE_BIAS, cum[2] + MDB_IMAGE_BIAS,
+                                      cum[3] + MDB_IMAGE_BIAS);
                         else
-                            for (int j = 0; j < nv; ++j) dst[j] = (int8_t)cum[j];
+                            for (int j = 0; j < nv; ++j) dst[j] = (uint8_t)(cum[j] + MDB_IMAGE_BIAS);
                     }
                     if (p.jumps) {
                         int8_t *dst = p.jumps + (long long)orow * p.img_pitch + e0;
@@ -150,14 +153,14 @@ __global__ void __launch_bounds__(kThreads) nojump_scan_kernel(const NojumpDev p
     if (overflow && p.overflow) atomicExch(p.overflow, 1);
 }
 
-__global__ void nojump_apply_kernel(const float *__restrict__ x, const int8_t *__restrict__ n, double b0, double b1,
+__global__ void nojump_apply_kernel(const float *__restrict__ x, const uint8_t *__restrict__ n, double b0, double b1,
                                     double b2, int n_vals, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_vals) return;
     const int d = i % 3;
     const double b = d == 0 ? b0 : (d == 1 ? b1 : b2);
     // pbc.py:235-247: frame - counts * box, float64 (the product is exact, so fma == mul then sub)
-    out[i] = fma(-(double)n[i], b, (double)x[i]);
+    out[i] = fma(-(double)((int)n[i] - MDB_IMAGE_BIAS), b, (double)x[i]);
 }
 
 }  // namespace
@@ -217,7 +220,7 @@ extern "C" int mdb_nojump_scan(const mdb_nojump_args *a, void *stream) {
     return MDB_OK;
 }
 
-extern "C" int mdb_nojump_apply(const float *coords_row, const int8_t *images_row, const double box[3],
+extern "C" int mdb_nojump_apply(const float *coords_row, const uint8_t *images_row, const double box[3],
                                 int32_t n_atoms, double *out, void *stream) {
     if (!coords_row || !images_row || !box || !out || n_atoms <= 0)
         return fail(MDB_ERR_ARGUMENT, "mdb_nojump_apply: NULL pointer or n_atoms <= 0");

@@ -65,7 +65,7 @@ def test_image_counts_bit_exact(small, md):
     np.testing.assert_array_equal(jumps, g['jumps'])
     store = res.store_for(np.arange(len(coords)), nojump=True)
     n3 = 3 * res.n_atoms
-    images = store.images[:, :n3].cpu().numpy().reshape(len(coords), -1, 3)
+    images = store.images[:, :n3].cpu().numpy().astype(np.int64).reshape(len(coords), -1, 3) - 128
     np.testing.assert_array_equal(images, np.cumsum(g['jumps'], axis=0, dtype=np.int64))
 
 
@@ -171,7 +171,7 @@ def test_config1_golden(golden, md):
     # dense jump statistics of the whole trajectory
     res = coords._resident()
     store = res.store_for(np.arange(1000), nojump=True)
-    last = store.images[999, :3000].cpu().numpy().reshape(1000, 3).astype(np.int64)
+    last = store.images[999, :3000].cpu().numpy().reshape(1000, 3).astype(np.int64) - 128
     np.testing.assert_array_equal(last, g['count_checksum'])
 
 
