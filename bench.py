@@ -311,7 +311,8 @@ def ours_arm(a):
         n_sub = min(a.cpu_atoms, N)
         sub = block[:, :3 * n_sub].cpu().numpy().reshape(T, n_sub, 3)
         ref, scan_s, corr_s = cpu_reference_step(sub, box, times, a.segments, a.function)
-        sub_store = engine.DeviceStore(store.coords, n_sub, images=store.images, box=store.box)
+        sub_store = engine.DeviceStore(store.coords, n_sub, images=store.images, box=store.box,
+                                       box_const=store.box_const)
         starts, idx = c._schedule(frames, c.log_indices, a.segments, 0.5, None)
         rows = (starts[:, None] + idx[None, :]).astype(np.int32)
         spec = c._kernel_spec(fn)

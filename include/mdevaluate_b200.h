@@ -74,7 +74,7 @@ int mdb_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * for already unwrapped frames).  With `images` != NULL every row also has cumulative periodic
  * image counts n, one byte per component stored excess-128 (uint8 = n + MDB_IMAGE_BIAS; row r at
  * `images + r*img_pitch`, 3*n_atoms bytes, as written by mdb_nojump_scan) and a box diagonal
- * `box[3*r .. 3*r+2]`; the kernels then use the unwrapped position  x - n*box  evaluated in
+ * `box[3*r .. 3*r+2]` (or the single `box_const` when the box never changes); the kernels then use the unwrapped position  x - n*box  evaluated in
  * float64, which is exactly the float64 frame `pbc.nojump` returns (pbc.py:235-247).
  *
  * `rows[s*n_lags + l]` is the storage row of frame  start_frames[s] + idx[l]; entry l == 0 is
@@ -92,7 +92,8 @@ typedef struct mdb_corr_args {
     int32_t coord_type;          /* MDB_F32 or MDB_F64                                           */
     const uint8_t *images;       /* DEVICE [n_rows][img_pitch] excess-128, or NULL (raw / unwrapped) */
     int64_t img_pitch;           /* bytes per image row, >= 3*n_atoms                            */
-    const double *box;           /* DEVICE [n_rows][3] box diagonals; required iff images        */
+    const double *box;           /* DEVICE [n_rows][3] box diagonals per row, or NULL: box_const  */
+    double box_const[3];         /* the one box diagonal of every row when box == NULL (with images) */
     int32_t n_atoms;             /* atoms of this shard                                          */
     int32_t n_origins;           /* S                                                            */
     int32_t n_lags;              /* L                                                            */

@@ -33,11 +33,12 @@ def row_pitch(n_atoms):
 class DeviceStore:
     """Frame rows resident in HBM plus the map trajectory frame -> row."""
 
-    def __init__(self, coords, n_atoms, images=None, box=None, frame_to_row=None, n_frames=None):
+    def __init__(self, coords, n_atoms, images=None, box=None, frame_to_row=None, n_frames=None, box_const=None):
         self.coords = coords            # torch (n_rows, pitch) float32 / float64
         self.n_atoms = int(n_atoms)
         self.images = images            # torch int8 (n_rows, img_pitch) or None
         self.box = box                  # torch float64 (n_rows, 3) or None
+        self.box_const = box_const      # 3 floats when every row has the same box
         self.frame_to_row = frame_to_row  # np.int32 (T,) with -1 = absent, or None = identity
         self.n_frames = n_frames if n_frames is not None else coords.shape[0]
         self._cache = {}
@@ -143,7 +144,11 @@ def correlate_device(store, rows, spec, stream=None):
     if store.images is not None:
         a.images = store.images.data_ptr()
         a.img_pitch = store.images.stride(0)
-        a.box = store.box.data_ptr()
+        if store.box_const is not None:
+            a.box = None
+            a.box_const[0], a.box_const[1], a.box_const[2] = store.box_const
+        else:
+            a.box = store.box.data_ptr()
     a.n_atoms = store.n_atoms
     a.n_origins = S
     a.n_lags = L

@@ -33,7 +33,7 @@ class CudaPathError(RuntimeError):
 class CorrArgs(C.Structure):
     _fields_ = [
         ('coords', C.c_void_p), ('pitch', C.c_int64), ('coord_type', C.c_int32),
-        ('images', C.c_void_p), ('img_pitch', C.c_int64), ('box', C.c_void_p),
+        ('images', C.c_void_p), ('img_pitch', C.c_int64), ('box', C.c_void_p), ('box_const', C.c_double * 3),
         ('n_atoms', C.c_int32), ('n_origins', C.c_int32), ('n_lags', C.c_int32),
         ('rows', C.c_void_p), ('flags', C.c_int32), ('q', C.c_double),
         ('n_bins', C.c_int32), ('bin_mode', C.c_int32), ('dx', C.c_double), ('edges', C.c_void_p),

@@ -68,6 +68,11 @@ class Resident:
             b = np.stack([np.asarray(self._box_of(int(i)), dtype=np.float64) for i in frame_ids])
         return torch.from_numpy(np.ascontiguousarray(b)).to(self.device)
 
+    def _box_const(self):
+        if getattr(self.reader, 'box_constant', False):
+            return tuple(float(b) for b in np.asarray(self.reader.box_diag, dtype=np.float64))
+        return None
+
     # -- segment source: a device float32 (n, pitch') view of frames [t0, t1) -------------------
     def _segment_frames(self):
         per_frame = self.pitch * 4
@@ -212,6 +217,7 @@ class Resident:
             self._scan_all(images=images)
             store.images = images
             store.box = self._box_rows(range(self.n_frames))
+            store.box_const = self._box_const()
         return store
 
     def dense_jumps(self):
@@ -236,7 +242,7 @@ class Resident:
             out_row = torch.from_numpy(f2r).to(self.device)
             self._scan_all(images=images, out_row=out_row, coords_out=coords)
             store = engine.DeviceStore(coords, self.n_atoms, images=images, box=self._box_rows(frame_ids),
-                                       frame_to_row=f2r, n_frames=self.n_frames)
+                                       frame_to_row=f2r, n_frames=self.n_frames, box_const=self._box_const())
         else:
             tdt = torch.float32 if self.dtype == np.float32 else torch.float64
             coords = torch.empty((n_rows, self.pitch), dtype=tdt, device=self.device)

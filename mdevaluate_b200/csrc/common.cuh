@@ -63,6 +63,68 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
     return r;
 }
 
+// ---- packed float32 pairs: sm_100 executes add/mul/fma on two floats per instruction (FFMA2) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 bcast2(float c) { return pack2(c, c); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float y) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));   // bare MUFU.RSQ
+    return r;
+}
+
+// Two sinc evaluations at once: the same algorithm as sinc_of_square below with every float32
+// add / mul / fma issued as one packed instruction for the pair.  y is clamped at 2^-100 (a power of
+// four, so rsqrt, the Newton step and the final product are exact there): y = 0 gives exactly 1.
+__device__ __forceinline__ void sinc_of_square_x2(float y0, float y1, float &r0, float &r1) {
+    y0 = fmaxf(y0, 7.888609052210118e-31f);
+    y1 = fmaxf(y1, 7.888609052210118e-31f);
+    const f32x2 y = pack2(y0, y1);
+    f32x2 rs = pack2(rsqrt_approx(y0), rsqrt_approx(y1));
+    f32x2 t = mul2(mul2(y, bcast2(-0.5f)), rs);
+    t = fma2(t, rs, bcast2(1.5f));
+    rs = mul2(rs, t);
+    const f32x2 x = mul2(y, rs);
+    const f32x2 kb = fma2(x, bcast2(0.318309886183790672f), bcast2(12582912.0f));
+    const f32x2 kf = add2(kb, bcast2(-12582912.0f));
+    f32x2 z = fma2(kf, bcast2(-3.140625f), x);
+    z = fma2(kf, bcast2(-9.676535846665502e-4f), z);
+    const f32x2 s = mul2(z, z);
+    f32x2 p = fma2(s, bcast2(-2.4061128200969506e-08f), bcast2(2.7535631943464978e-06f));
+    p = fma2(p, s, bcast2(-1.9841075118165463e-04f));
+    p = fma2(p, s, bcast2(8.33333283662796e-03f));
+    p = fma2(p, s, bcast2(-1.666666716337204e-01f));
+    f32x2 sn = fma2(mul2(z, s), p, z);
+    float kb0, kb1, sn0, sn1;
+    unpack2(kb, kb0, kb1);
+    unpack2(sn, sn0, sn1);
+    sn0 = __int_as_float(__float_as_int(sn0) ^ (__float_as_int(kb0) << 31));
+    sn1 = __int_as_float(__float_as_int(sn1) ^ (__float_as_int(kb1) << 31));
+    unpack2(mul2(pack2(sn0, sn1), rs), r0, r1);
+}
+
 // sin(sqrt(y)) / sqrt(y) for y >= 0 in float32, |error| ~1e-7 for sqrt(y) up to a few 1e4.
 //   one MUFU.RSQ + a Newton step give 1/x and x = y/x;
 //   x is reduced by multiples of pi (2-term Cody-Waite with FMA), sin on [-pi/2, pi/2] is an odd

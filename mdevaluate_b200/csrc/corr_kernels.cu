@@ -50,6 +50,7 @@ struct CorrDev {
     const uint8_t *images;
     long long img_pitch;
     const double *box;
+    double box_const[3];  // used when box == nullptr: the same box for every row (kernel-parameter constants)
     int n_atoms;
     int n_groups;        // ceil(n_atoms / 4)
     int groups_per_block;
@@ -147,6 +148,7 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
     sum2 = 0.0;
     sum4 = 0.0;
     sums = 0.0f;
+    float yq[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const double ddx = u0[3 * a] - ut[3 * a];
@@ -155,7 +157,7 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
         const double r2 = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
         if constexpr (kR2) sum2 += r2;
         if constexpr (kR4) sum4 = fma(r2, r2, sum4);
-        if constexpr (kSinc) sums += sinc_of_square((float)(r2 * p.q2));
+        if constexpr (kSinc) yq[a] = (float)(r2 * p.q2);
         if constexpr (kHist) {
             if (!MASKED || a < nv) {
                 int bin = -1;
@@ -192,7 +194,13 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
             }
         }
     }
-    if constexpr (kSinc && MASKED) sums -= (float)(4 - nv);
+    if constexpr (kSinc) {
+        float v0, v1, v2, v3;
+        sinc_of_square_x2(yq[0], yq[1], v0, v1);
+        sinc_of_square_x2(yq[2], yq[3], v2, v3);
+        sums = (v0 + v1) + (v2 + v3);
+        if constexpr (MASKED) sums -= (float)(4 - nv);
+    }
 }
 
 // CTA prologue shared by both kernels: which (origin, chunk, atom block) am I, rows and boxes.
@@ -221,9 +229,9 @@ __device__ __forceinline__ void load_rows(const CorrDev &p, const CtaWork &w, in
         const int row = (tid == 0 || tid - 1 < w.nl) ? p.rows[(long long)w.s * p.L + l] : 0;
         s_row[tid] = row;
         if (IMG) {
-            s_box[tid][0] = p.box[3ll * row];
-            s_box[tid][1] = p.box[3ll * row + 1];
-            s_box[tid][2] = p.box[3ll * row + 2];
+            s_box[tid][0] = p.box ? p.box[3ll * row] : p.box_const[0];
+            s_box[tid][1] = p.box ? p.box[3ll * row + 1] : p.box_const[1];
+            s_box[tid][2] = p.box ? p.box[3ll * row + 2] : p.box_const[2];
         }
     }
 }
@@ -440,10 +448,10 @@ struct Ring {
 };
 
 // Take the calling thread's 4 atoms out of the current stage, release the stage, unwrap.
-template <bool IMG, bool MASKED>
-__device__ __forceinline__ void fetch_group(Ring &ring, uint32_t full0, uint32_t empty0, const unsigned char *stages,
-                                            int stage_bytes, int tid, int nv, const double *bx, double (&u)[12],
-                                            float (&raw)[12]) {
+template <bool IMG, bool MASKED, bool BOXC>
+__device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
+                                            const unsigned char *stages, int stage_bytes, int tid, int nv,
+                                            const double *bx, double (&u)[12], float (&raw)[12]) {
     mbar_wait(full0 + 8 * ring.stage, ring.phase);
     const unsigned char *src = stages + (size_t)ring.stage * stage_bytes;
     const float4 *c4 = reinterpret_cast<const float4 *>(src) + 3 * tid;
@@ -469,13 +477,14 @@ __device__ __forceinline__ void fetch_group(Ring &ring, uint32_t full0, uint32_t
                 wds[cc >> 2] = (wds[cc >> 2] & ~(0xffu << (8 * (cc & 3)))) | (0x80u << (8 * (cc & 3)));
             }
     }
-    unwrap12<IMG>(raw, wds, bx, u);
+    // a box that is the same for every row comes from the kernel parameters (constant bank operands)
+    unwrap12<IMG>(raw, wds, BOXC ? p.box_const : bx, u);
 }
 
 // One tile of 1024 atoms: origin group into registers, then the lag rows of the chunk one by one.
 // The loop over lags is NOT unrolled (the body is 4 evaluations, ~1 KiB of code, and stays in the
 // instruction cache); per-lag accumulators live in shared memory, one private column per thread.
-template <bool IMG, int FLAGS, bool MASKED>
+template <bool IMG, int FLAGS, bool MASKED, bool BOXC>
 __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
                                              const unsigned char *stages, int stage_bytes, int tid, int nv, int nl,
                                              const double (*s_box)[3], double *s_acc, unsigned int *s_hist,
@@ -488,12 +497,12 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
     constexpr int NV = (kR2 ? 1 : 0) + (kR4 ? 1 : 0) + (kSinc ? 1 : 0);
     double u0[12];
     float raw0[12];
-    fetch_group<IMG, MASKED>(ring, full0, empty0, stages, stage_bytes, tid, nv, s_box[0], u0, raw0);
+    fetch_group<IMG, MASKED, BOXC>(p, ring, full0, empty0, stages, stage_bytes, tid, nv, s_box[0], u0, raw0);
 #pragma unroll 1
     for (int k = 0; k < nl; ++k) {
         double ut[12];
         float rawt[12];
-        fetch_group<IMG, MASKED>(ring, full0, empty0, stages, stage_bytes, tid, nv, s_box[k + 1], ut, rawt);
+        fetch_group<IMG, MASKED, BOXC>(p, ring, full0, empty0, stages, stage_bytes, tid, nv, s_box[k + 1], ut, rawt);
         double s2, s4;
         float ss;
         eval_group<FLAGS, kHistF32, MASKED>(p, u0, raw0, ut, rawt, nv, s2, s4, ss, s_hist + k * p.n_bins, s_edges);
@@ -505,7 +514,7 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
     }
 }
 
-template <bool IMG, int FLAGS>
+template <bool IMG, int FLAGS, bool BOXC>
 __global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDev p, const int n_stages) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
@@ -585,12 +594,12 @@ __global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDe
     for (int t = 0; t < n_tiles; ++t) {
         const int g_last = g_begin + t * kThreads + kThreads - 1;          // last group of this tile
         if (4 * g_last + 3 < p.n_atoms) {
-            process_tile<IMG, FLAGS, false>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, 4, w.nl, s_box, s_acc,
+            process_tile<IMG, FLAGS, false, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, 4, w.nl, s_box, s_acc,
                                             s_hist, s_edges);
         } else {
             const int g = g_begin + t * kThreads + tid;
             const int nv = max(0, min(4, p.n_atoms - 4 * g));
-            process_tile<IMG, FLAGS, true>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, nv, w.nl, s_box, s_acc,
+            process_tile<IMG, FLAGS, true, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, nv, w.nl, s_box, s_acc,
                                            s_hist, s_edges);
         }
     }
@@ -733,7 +742,11 @@ int launch_kernel(Kernel kern, const CorrDev &p, const Plan &plan, int threads, 
 template <typename CT, bool IMG, int FLAGS>
 int launch_flags(const CorrDev &p, const Plan &plan, cudaStream_t st) {
     if constexpr (sizeof(CT) == 4) {
-        if (plan.bulk) return launch_kernel(corr_bulk_kernel<IMG, FLAGS>, p, plan, kBulkThreads, st, plan.stages);
+        if (plan.bulk) {
+            if (IMG && p.box == nullptr)
+                return launch_kernel(corr_bulk_kernel<IMG, FLAGS, true>, p, plan, kBulkThreads, st, plan.stages);
+            return launch_kernel(corr_bulk_kernel<IMG, FLAGS, false>, p, plan, kBulkThreads, st, plan.stages);
+        }
     }
     if (plan.vec) return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, true>, p, plan, kThreads, st);
     return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, false>, p, plan, kThreads, st);
@@ -773,7 +786,8 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     if (a->coord_type != MDB_F32 && a->coord_type != MDB_F64) return fail(MDB_ERR_ARGUMENT, "bad coord_type");
     if (a->images && a->coord_type != MDB_F32)
         return fail(MDB_ERR_ARGUMENT, "image counts go with float32 (wrapped) coordinates");
-    if (a->images && !a->box) return fail(MDB_ERR_ARGUMENT, "box is required with images");
+    if (a->images && !a->box && !(a->box_const[0] > 0.0 && a->box_const[1] > 0.0 && a->box_const[2] > 0.0))
+        return fail(MDB_ERR_ARGUMENT, "images need box (per row) or a positive box_const");
     if (a->images && a->img_pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "img_pitch < 3*n_atoms");
     const bool hist = (a->flags & MDB_HIST) != 0;
     if (hist) {
@@ -793,6 +807,7 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     p.images = a->images;
     p.img_pitch = a->img_pitch;
     p.box = a->box;
+    for (int d = 0; d < 3; ++d) p.box_const[d] = a->box_const[d];
     p.n_atoms = a->n_atoms;
     p.n_groups = plan.n_groups;
     p.groups_per_block = plan.groups_per_block;

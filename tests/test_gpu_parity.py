@@ -267,3 +267,29 @@ def test_c_abi_argument_checks(md):
     sm, major, minor = C.c_int(), C.c_int(), C.c_int()
     assert lib.mdb_device_info(C.byref(sm), C.byref(major), C.byref(minor)) == 0
     assert sm.value > 0 and major.value >= 10
+
+
+def test_per_frame_box(md):
+    """NPT-like trajectory: the box changes every frame.  Jumps are detected with frame 0's box
+    (reader.py:167), each frame is unwrapped with its own box (pbc.py:237, cache-free definition)."""
+    from mdevaluate_b200.synthetic import random_walk
+    pos, box, times = random_walk(203, 90, seed=11, sigma=0.15, box=2.5)
+    rng = np.random.default_rng(1)
+    boxes = (box[None, :] * (1 + 0.002 * rng.standard_normal((90, 3)))).astype(np.float32)
+    boxes[0] = box
+    unw = orc.UnwrappedTrajectory(pos, boxes, times)
+    coords = md.Coordinates.from_arrays(pos, boxes, times)
+    c = md.correlation
+    np.testing.assert_array_equal(np.asarray(coords.nojump[57]), np.asarray(unw[57]))
+    with np.errstate(all='ignore'):
+        for ours, theirs in ((c.msd, orc.msd), (c.non_gaussian, orc.non_gaussian)):
+            _, ref = orc.shifted_correlation(theirs, unw, segments=6, window=0.5)
+            _, r = c.shifted_correlation(ours, coords.nojump, segments=6, window=0.5)
+            close(r, ref, rtol=1e-11, atol=1e-13)
+        bins = np.linspace(0, 3.0, 61)
+        _, ref = orc.shifted_correlation(partial(orc.van_hove_self, bins=bins), unw, segments=6, window=0.5)
+        _, r = c.shifted_correlation(partial(c.van_hove_self, bins=bins), coords.nojump, segments=6, window=0.5)
+        np.testing.assert_array_equal(r, ref)
+        _, ref = orc.shifted_correlation(partial(orc.isf, q=22.7), unw, segments=6, window=0.5)
+        _, r = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=6, window=0.5)
+        close(r, ref)
