@@ -39,11 +39,28 @@ struct NojumpDev {
 };
 
 template <bool BOXF32>
-__device__ __forceinline__ int jump_of(float curr, float prev, float bf, double bd, float safe) {
-    const float diff = __fsub_rn(curr, prev);
+__device__ __forceinline__ int jump_of(float diff, float bf, double bd, float safe) {
     if (fabsf(diff) < safe) return 0;
     if (BOXF32) return (int)(int8_t)(int)rintf(__fdiv_rn(diff, bf));
     return (int)(int8_t)(int)rint(__ddiv_rn((double)diff, bd));
+}
+
+// The rare path (some component moved by ~half a box): kept out of line so that the unrolled
+// streaming loop stays small enough for the instruction cache.
+template <bool BOXF32>
+__device__ __noinline__ int4 slow_jumps(float d0, float d1, float d2, float d3, int e0, float bx, float by, float bz,
+                                        double dbx, double dby, double dbz) {
+    const float bf[3] = {bx, by, bz};
+    const double bd[3] = {dbx, dby, dbz};
+    const float d[4] = {d0, d1, d2, d3};
+    int out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int dim = (e0 + j) % 3;
+        const float safe = 0.49f * fabsf(BOXF32 ? bf[dim] : (float)bd[dim]);
+        out[j] = jump_of<BOXF32>(d[j], bf[dim], bd[dim], safe);
+    }
+    return make_int4(out[0], out[1], out[2], out[3]);
 }
 
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
@@ -51,23 +68,23 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
            (((uint32_t)d & 0xffu) << 24);
 }
 
-// VEC: rows are 16-byte aligned and n_vals is handled in whole float4s by full threads; the last
-// partial float4 (n_vals % 4 != 0) and unaligned layouts use the guarded scalar path.
-template <bool BOXF32, bool VEC>
+// VEC: every thread moves whole float4s (rows are 16-byte aligned, all pitches multiples of 4): the
+// last thread may run up to 3 components into the row padding -- they are read and written inside
+// the padded rows but never reach the carry buffers or the overflow flag.  !VEC: guarded scalars.
+// PLAIN: the dense case (every frame kept in place, counts only) with the per-frame work cut to
+// load / 4 subtract+compare / one packed store; otherwise the general case (row map, per-step
+// jumps, compaction copy), decided per frame at run time.
+template <bool BOXF32, bool VEC, bool PLAIN>
 __global__ void __launch_bounds__(kThreads) nojump_scan_kernel(const NojumpDev p) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     const int e0 = 4 * i;
     if (e0 >= p.n_vals) return;
     const int nv = min(4, p.n_vals - e0);
-    const bool full = VEC && nv == 4;
 
-    float bf[4], safe[4];
-    double bd[4];
+    float safe[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int d = (e0 + j) % 3;
-        bf[j] = p.boxf[d];
-        bd[j] = p.boxd[d];
         safe[j] = 0.49f * fabsf(BOXF32 ? p.boxf[d] : (float)p.boxd[d]);
     }
 
@@ -88,62 +105,98 @@ __global__ void __launch_bounds__(kThreads) nojump_scan_kernel(const NojumpDev p
             }
         }
     }
+    // the packed excess-128 word of the running counts only changes on the rare path
+    uint32_t packed = pack4(cum[0] + MDB_IMAGE_BIAS, cum[1] + MDB_IMAGE_BIAS, cum[2] + MDB_IMAGE_BIAS,
+                            cum[3] + MDB_IMAGE_BIAS);
 
-    // kBatch rows are loaded before any of them is processed: the running state does not feed the
-    // addresses, so a thread keeps kBatch independent 128-bit loads in flight.
-    for (int tb = 0; tb < p.n_frames; tb += kBatch) {
-        float buf[kBatch][4];
+    auto load_row = [&](int t, float (&v)[4]) {
+        const float *row = p.coords + (long long)t * p.pitch + e0;
+        if (VEC) {
+            const float4 q = ld_stream(reinterpret_cast<const float4 *>(row));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int t = min(tb + u, p.n_frames - 1);
-            const float *row = p.coords + (long long)t * p.pitch + e0;
-            if (full) {
-                const float4 v = ld_stream(reinterpret_cast<const float4 *>(row));
-                buf[u][0] = v.x; buf[u][1] = v.y; buf[u][2] = v.z; buf[u][3] = v.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) buf[u][j] = (j < nv) ? __ldg(row + j) : 0.f;
-            }
+            for (int j = 0; j < 4; ++j) v[j] = (j < nv) ? __ldg(row + j) : 0.f;
         }
+    };
+    auto step = [&](int t, const float (&cur)[4]) {
+        float diff[4];
+        bool any = false;
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int t = tb + u;
-            if (t < p.n_frames) {
-                int jmp[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    jmp[j] = (j < nv) ? jump_of<BOXF32>(buf[u][j], prev[j], bf[j], bd[j], safe[j]) : 0;
-                    cum[j] += jmp[j];
-                    prev[j] = buf[u][j];
-                    overflow |= (cum[j] > 127 || cum[j] < -128);
-                }
-                const int orow = p.out_row ? p.out_row[t] : t;
-                if (orow >= 0) {
-                    if (p.images) {
-                        uint8_t *dst = p.images + (long long)orow * p.img_pitch + e0;
-                        if (full)
-                            *reinterpret_cast<uint32_t *>(dst) =
-                                pack4(cum[0] + MDB_IMAGE_BIAS, cum[1] + MDB_IMAGE_BIAS, cum[2] + MDB_IMAGE_BIAS,
-                                      cum[3] + MDB_IMAGE_BIAS);
-                        else
-                            for (int j = 0; j < nv; ++j) dst[j] = (uint8_t)(cum[j] + MDB_IMAGE_BIAS);
-                    }
-                    if (p.jumps) {
-                        int8_t *dst = p.jumps + (long long)orow * p.img_pitch + e0;
-                        if (full) *reinterpret_cast<uint32_t *>(dst) = pack4(jmp[0], jmp[1], jmp[2], jmp[3]);
-                        else
-                            for (int j = 0; j < nv; ++j) dst[j] = (int8_t)jmp[j];
-                    }
-                    if (p.coords_out) {
-                        float *dst = p.coords_out + (long long)orow * p.pitch_out + e0;
-                        if (full && (p.pitch_out % 4 == 0))
-                            *reinterpret_cast<float4 *>(dst) = make_float4(buf[u][0], buf[u][1], buf[u][2], buf[u][3]);
-                        else
-                            for (int j = 0; j < nv; ++j) dst[j] = buf[u][j];
-                    }
-                }
-            }
+        for (int j = 0; j < 4; ++j) {
+            diff[j] = __fsub_rn(cur[j], prev[j]);
+            any |= !(fabsf(diff[j]) < safe[j]);
+            prev[j] = cur[j];
         }
+        int jmp[4] = {0, 0, 0, 0};
+        if (any) {   // rare: some component of this float4 moved by about half a box or more
+            const int4 jv = slow_jumps<BOXF32>(diff[0], diff[1], diff[2], diff[3], e0, p.boxf[0], p.boxf[1], p.boxf[2],
+                                               p.boxd[0], p.boxd[1], p.boxd[2]);
+            jmp[0] = jv.x; jmp[1] = jv.y; jmp[2] = jv.z; jmp[3] = jv.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nv) jmp[j] = 0;
+                cum[j] += jmp[j];
+                overflow |= (cum[j] > 127 || cum[j] < -128);
+            }
+            packed = pack4(cum[0] + MDB_IMAGE_BIAS, cum[1] + MDB_IMAGE_BIAS, cum[2] + MDB_IMAGE_BIAS,
+                           cum[3] + MDB_IMAGE_BIAS);
+        }
+        if (PLAIN) {
+            uint8_t *dst = p.images + (long long)t * p.img_pitch + e0;
+            if (VEC) *reinterpret_cast<uint32_t *>(dst) = packed;
+            else
+                for (int j = 0; j < nv; ++j) dst[j] = (uint8_t)(cum[j] + MDB_IMAGE_BIAS);
+            return;
+        }
+        const int orow = p.out_row ? p.out_row[t] : t;
+        if (orow < 0) return;
+        if (p.images) {
+            uint8_t *dst = p.images + (long long)orow * p.img_pitch + e0;
+            if (VEC) *reinterpret_cast<uint32_t *>(dst) = packed;
+            else
+                for (int j = 0; j < nv; ++j) dst[j] = (uint8_t)(cum[j] + MDB_IMAGE_BIAS);
+        }
+        if (p.jumps) {
+            int8_t *dst = p.jumps + (long long)orow * p.img_pitch + e0;
+            if (VEC) *reinterpret_cast<uint32_t *>(dst) = pack4(jmp[0], jmp[1], jmp[2], jmp[3]);
+            else
+                for (int j = 0; j < nv; ++j) dst[j] = (int8_t)jmp[j];
+        }
+        if (p.coords_out) {
+            float *dst = p.coords_out + (long long)orow * p.pitch_out + e0;
+            if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(cur[0], cur[1], cur[2], cur[3]);
+            else
+                for (int j = 0; j < nv; ++j) dst[j] = cur[j];
+        }
+    };
+
+    // Software pipeline over whole double-batches: while batch A (kBatch rows, in registers) is
+    // processed the loads of batch B are in flight and vice versa; the running state does not feed
+    // the addresses, so a thread keeps up to 2*kBatch independent 128-bit loads outstanding.
+    float buf_a[kBatch][4], buf_b[kBatch][4];
+    const int n_main = p.n_frames / (2 * kBatch) * (2 * kBatch);
+    int tb = 0;
+    if (n_main > 0) {
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) load_row(u, buf_a[u]);
+        for (; tb < n_main; tb += 2 * kBatch) {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) load_row(tb + kBatch + u, buf_b[u]);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) step(tb + u, buf_a[u]);
+            if (tb + 2 * kBatch < n_main) {
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) load_row(tb + 2 * kBatch + u, buf_a[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) step(tb + kBatch + u, buf_b[u]);
+        }
+    }
+    for (int t = n_main; t < p.n_frames; ++t) {   // fewer than 2*kBatch frames left
+        float cur[4];
+        load_row(t, cur);
+        step(t, cur);
     }
 
     for (int j = 0; j < nv; ++j) {
@@ -205,16 +258,19 @@ extern "C" int mdb_nojump_scan(const mdb_nojump_args *a, void *stream) {
     bool vec = (reinterpret_cast<uintptr_t>(a->coords) % 16 == 0) && (a->pitch % 4 == 0);
     if (a->images) vec = vec && (reinterpret_cast<uintptr_t>(a->images) % 4 == 0) && (a->img_pitch % 4 == 0);
     if (a->jumps) vec = vec && (reinterpret_cast<uintptr_t>(a->jumps) % 4 == 0) && (a->img_pitch % 4 == 0);
-    if (a->coords_out) vec = vec && (reinterpret_cast<uintptr_t>(a->coords_out) % 16 == 0);
+    if (a->coords_out) vec = vec && (reinterpret_cast<uintptr_t>(a->coords_out) % 16 == 0) && (a->pitch_out % 4 == 0);
 
     const int n_threads = (p.n_vals + 3) / 4;
     const unsigned blocks = (unsigned)((n_threads + kThreads - 1) / kThreads);
+    const bool plain = vec && a->images && !a->out_row && !a->jumps && !a->coords_out;
     if (a->box_is_f32) {
-        if (vec) nojump_scan_kernel<true, true><<<blocks, kThreads, 0, st>>>(p);
-        else nojump_scan_kernel<true, false><<<blocks, kThreads, 0, st>>>(p);
+        if (plain) nojump_scan_kernel<true, true, true><<<blocks, kThreads, 0, st>>>(p);
+        else if (vec) nojump_scan_kernel<true, true, false><<<blocks, kThreads, 0, st>>>(p);
+        else nojump_scan_kernel<true, false, false><<<blocks, kThreads, 0, st>>>(p);
     } else {
-        if (vec) nojump_scan_kernel<false, true><<<blocks, kThreads, 0, st>>>(p);
-        else nojump_scan_kernel<false, false><<<blocks, kThreads, 0, st>>>(p);
+        if (plain) nojump_scan_kernel<false, true, true><<<blocks, kThreads, 0, st>>>(p);
+        else if (vec) nojump_scan_kernel<false, true, false><<<blocks, kThreads, 0, st>>>(p);
+        else nojump_scan_kernel<false, false, false><<<blocks, kThreads, 0, st>>>(p);
     }
     MDB_CUDA_CHECK(cudaGetLastError());
     return MDB_OK;
