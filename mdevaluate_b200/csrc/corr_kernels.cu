@@ -131,6 +131,18 @@ struct Accum {
     }
 };
 
+// Exact bin of one displacement (the rare / general path, kept out of line so that the streaming
+// loop stays small): float64 sqrt of the unfused r^2, then utils.histogram's rule.
+__device__ __noinline__ int exact_bin(double ddx, double ddy, double ddz, int bin_mode, double dx, double inv_dx,
+                                      int n_bins, const double *s_edges) {
+    const double r = sqrt(r2_unfused(ddx, ddy, ddz));
+    if (bin_mode == MDB_BINS_UNIFORM) {
+        const long long kk = exact_floor_div(r, dx, inv_dx);
+        return (kk < n_bins) ? (int)kk : -1;
+    }
+    return edge_bin(r, s_edges, n_bins);
+}
+
 // One group of 4 atoms against one lag frame: partial sums of r^2, r^4 (float64) and sinc (float32)
 // over the group, histogram counts straight into shared memory.  MASKED is only instantiated for
 // the last group(s) of a shard: atoms beyond `nv` carry zeroed inputs on both sides, so they add
@@ -149,6 +161,8 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
     sum4 = 0.0;
     sums = 0.0f;
     float yq[4];
+    double dd[4][3];
+    double r2v[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const double ddx = u0[3 * a] - ut[3 * a];
@@ -159,39 +173,8 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
         if constexpr (kR4) sum4 = fma(r2, r2, sum4);
         if constexpr (kSinc) yq[a] = (float)(r2 * p.q2);
         if constexpr (kHist) {
-            if (!MASKED || a < nv) {
-                int bin = -1;
-                if (HIST_F32) {
-                    // raw float32 frames: the reference computes r in float32 (correlation.py:246-247
-                    // on float32 arrays); replay vec = start - end; (vec**2).sum(-1) ** .5 in float32
-                    const float vx = __fsub_rn(raw0[3 * a], rawt[3 * a]);
-                    const float vy = __fsub_rn(raw0[3 * a + 1], rawt[3 * a + 1]);
-                    const float vz = __fsub_rn(raw0[3 * a + 2], rawt[3 * a + 2]);
-                    const float q = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
-                    const double r = (double)__fsqrt_rn(q);
-                    if (p.bin_mode == MDB_BINS_UNIFORM) {
-                        const long long kk = exact_floor_div(r, p.dx, p.inv_dx);
-                        bin = (kk < p.n_bins) ? (int)kk : -1;
-                    } else {
-                        bin = edge_bin(r, s_edges, p.n_bins);
-                    }
-                } else if (p.bin_mode == MDB_BINS_UNIFORM) {
-                    // float32 estimate; exact path only near a bin edge
-                    const float t = __fsqrt_rn((float)r2) * p.inv_dx_f;
-                    const float fl = floorf(t);
-                    const float fr = t - fl;
-                    const float margin = fmaf(t, 6.0e-7f, 1.0e-6f);
-                    if (fr > margin && fr < 1.0f - margin) {
-                        bin = (t < (float)p.n_bins) ? (int)fl : -1;
-                    } else {
-                        const long long kk = exact_floor_div(sqrt(r2_unfused(ddx, ddy, ddz)), p.dx, p.inv_dx);
-                        bin = (kk < p.n_bins) ? (int)kk : -1;
-                    }
-                } else {
-                    bin = edge_bin(sqrt(r2_unfused(ddx, ddy, ddz)), s_edges, p.n_bins);
-                }
-                if (bin >= 0) atomicAdd(&s_hist_k[bin], 1u);
-            }
+            dd[a][0] = ddx; dd[a][1] = ddy; dd[a][2] = ddz;
+            r2v[a] = r2;
         }
     }
     if constexpr (kSinc) {
@@ -200,6 +183,66 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
         sinc_of_square_x2(yq[2], yq[3], v2, v3);
         sums = (v0 + v1) + (v2 + v3);
         if constexpr (MASKED) sums -= (float)(4 - nv);
+    }
+    if constexpr (kHist) {
+        if (HIST_F32) {
+            // raw float32 frames: the reference computes r in float32 (correlation.py:246-247 on float32
+            // arrays); replay vec = start - end; (vec**2).sum(-1) ** .5 in float32, then the exact rule
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (!MASKED || a < nv) {
+                    const float vx = __fsub_rn(raw0[3 * a], rawt[3 * a]);
+                    const float vy = __fsub_rn(raw0[3 * a + 1], rawt[3 * a + 1]);
+                    const float vz = __fsub_rn(raw0[3 * a + 2], rawt[3 * a + 2]);
+                    const float q = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+                    const double r = (double)__fsqrt_rn(q);
+                    int bin;
+                    if (p.bin_mode == MDB_BINS_UNIFORM) {
+                        const long long kk = exact_floor_div(r, p.dx, p.inv_dx);
+                        bin = (kk < p.n_bins) ? (int)kk : -1;
+                    } else {
+                        bin = edge_bin(r, s_edges, p.n_bins);
+                    }
+                    if (bin >= 0) atomicAdd(&s_hist_k[bin], 1u);
+                }
+            }
+        } else {
+            // Uniform bins: a branch-free float32 estimate t = r/dx (MUFU.RSQ, no conversions: the
+            // nearest integer and the distance to it come from the 1.5*2^23 trick).  A sample is
+            // decided here when it lies farther from every bin edge than the float32 error bound;
+            // everything else (and non-uniform bins) goes through exact_bin().
+            bool slow[4];
+            bool any_slow = false;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const bool live = !MASKED || a < nv;
+                bool fast = false;
+                int bin = 0;
+                if (p.bin_mode == MDB_BINS_UNIFORM) {
+                    const float r2f = (float)r2v[a];
+                    const float t = (r2f * rsqrt_approx(r2f)) * p.inv_dx_f;       // NaN for r2f == 0 -> slow
+                    const float tb = t + 12582912.0f;
+                    const float tr = tb - 12582912.0f;                            // rint(t) for t < 2^22
+                    const float dist = t - tr;
+                    const float margin = fmaf(t, 8.0e-7f, 1.0e-6f);   // 2x the float32 error bound (3.9e-7 t)
+                    bin = (__float_as_int(tb) - 0x4B400000) - (dist < 0.0f ? 1 : 0);
+                    fast = (fabsf(dist) > margin) && (t < 4.0e6f);
+                }
+                slow[a] = live && !fast;
+                any_slow |= slow[a];
+                if (live && fast && bin < p.n_bins) atomicAdd(&s_hist_k[bin], 1u);
+            }
+            if (any_slow) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    if (slow[a]) {
+                        const int bin = exact_bin(dd[a][0], dd[a][1], dd[a][2], p.bin_mode, p.dx, p.inv_dx, p.n_bins,
+                                                  s_edges);
+                        if (bin >= 0) atomicAdd(&s_hist_k[bin], 1u);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -640,11 +683,11 @@ struct Plan {
 
 constexpr size_t kSmemBudgetPerCta = 110 * 1024;   // two CTAs per SM
 
-// The kernel instantiation that serves a request: the four single-purpose kernels, or the
-// all-sums kernel (optionally with the histogram) for any other mix.
+// The kernel instantiation that serves a request: the four single-purpose kernels, van Hove +
+// non-Gaussian in one pass (BASELINE config 3), or the all-sums kernel (optionally with the histogram) for any other mix.
 int kernel_flags(int flags) {
     constexpr int R2 = MDB_SUM_R2, R4 = MDB_SUM_R4, SC = MDB_SUM_SINC, H = MDB_HIST;
-    if (flags == R2 || flags == SC || flags == (R2 | R4) || flags == H) return flags;
+    if (flags == R2 || flags == SC || flags == (R2 | R4) || flags == H || flags == (R2 | R4 | H)) return flags;
     return (flags & H) ? (R2 | R4 | SC | H) : (R2 | R4 | SC);
 }
 
@@ -760,6 +803,7 @@ int launch_typed(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st)
         case SC: return launch_flags<CT, IMG, SC>(p, plan, st);
         case R2 | R4: return launch_flags<CT, IMG, R2 | R4>(p, plan, st);
         case H: return launch_flags<CT, IMG, H>(p, plan, st);
+        case R2 | R4 | H: return launch_flags<CT, IMG, R2 | R4 | H>(p, plan, st);
         case R2 | R4 | SC | H: return launch_flags<CT, IMG, R2 | R4 | SC | H>(p, plan, st);
         default: return launch_flags<CT, IMG, R2 | R4 | SC>(p, plan, st);
     }
