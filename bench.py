@@ -296,13 +296,45 @@ def ours_arm(a):
     k_ms = float(np.mean(kernel_ms))
     alg_bytes = 12.0 * N * S * (L + 1)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            entry = json.load(fh).get('%s:%d:%d:%d' % (a.function, N, T, a.segments))
+        traffic = entry['bytes'] if entry else None
+    except Exception:
+        traffic = None
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'kernel': 'corr_kernel<float, images, SINC>' if a.function == 'isf'
+                'traffic': traffic, 'kernel': 'corr_kernel<float, images, SINC>' if a.function == 'isf'
                 else 'corr_kernel<float, images, R2>', 'kernel_ms': k_ms, 'kernel_ms_min': float(np.min(kernel_ms)),
                 'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
                 'moved_bytes_per_launch': 15.0 * N * S * (L + 1),
                 'note': 'algorithmic bytes = 12 B (float32 xyz) per atom*origin*(lag+1); the kernel also reads 3 B of '
                         'int8 image counts per coordinate triple (nojump), so moved bytes are 1.25x algorithmic'}
+
+    # ---- the other kernels of the path on the same rows (kernel time only; informational) ------------
+    other = {}
+    if rank == 0:
+        engine.profile_kernels(True)
+        vh_bins = np.linspace(0, 3.0, 501)
+        extra = {'msd': c.msd, 'non_gaussian': c.non_gaussian, 'van_hove_self_500bins': partial(c.van_hove_self, bins=vh_bins)}
+        if a.function != 'isf':
+            extra['isf'] = partial(c.isf, q=Q)
+        for name, f in extra.items():
+            ms = []
+            for _ in range(3):
+                c.shifted_correlation(f, frames, segments=a.segments, window=0.5)
+                ms.append(engine.last_kernel_ms())
+            other[name] = {'kernel_ms': float(min(ms)), 'evals_per_s': N * S * L / (min(ms) * 1e-3),
+                           'frac': alg_bytes / (min(ms) * 1e-3) / 1e9 / peak}
+        ms = []
+        for _ in range(3):
+            c.shifted_correlation_multi({'vh': extra['van_hove_self_500bins'], 'a2': c.non_gaussian}, frames,
+                                        segments=a.segments, window=0.5)
+            ms.append(engine.last_kernel_ms())
+        other['van_hove_self+non_gaussian (one pass)'] = {'kernel_ms': float(min(ms)),
+                                                          'evals_per_s': N * S * L / (min(ms) * 1e-3),
+                                                          'frac': alg_bytes / (min(ms) * 1e-3) / 1e9 / peak}
+        engine.profile_kernels(False)
 
     # ---- parity + CPU baseline on an atom sub-block (rank 0, N=1 only) ------------------------------
     cpu_baseline = None
@@ -369,7 +401,7 @@ def ours_arm(a):
                        'lags': int(L), 'evals_per_step': int(evals_step), 'parallelism': 'atom-shard x%d' % world,
                        'l2': 'inputs larger than L2: each step streams %.1f GB of frame rows' % (alg_bytes / 1e9)},
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': int(launches),
-            'clocks': clocks, 'parity': parity, 'nojump_pass': nojump_pass,
+            'clocks': clocks, 'parity': parity, 'nojump_pass': nojump_pass, 'other_kernels': other,
         }
         print(json.dumps(line))
     if world > 1:

@@ -741,15 +741,28 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
     int sms = 148;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // atom blocks: enough CTAs for ~8 per SM, each a whole number of 1024-atom tiles
+    // Atom blocks: every CTA gets a whole number of 1024-atom tiles.  All CTAs cost about the same, so
+    // the launch runs in ceil(CTAs / resident slots) waves of (tiles per CTA + fixed overhead): pick
+    // the split with the smallest estimate (wave quantisation is the main loss for small launches).
     const long long base = (long long)a->n_origins * plan->n_chunks;
-    long long want = (8ll * sms + base - 1) / base;
     const long long n_tiles = (plan->n_groups + kThreads - 1) / kThreads;
-    const long long max_blocks = (n_tiles + 3) / 4;                  // at least ~4 tiles per CTA
-    if (want > max_blocks) want = max_blocks;
-    if (want < 1) want = 1;
-    if (const char *env = getenv("MDB_ABLOCKS")) want = atoll(env) > 0 ? atoll(env) : want;   // tuning aid
-    const long long tiles_per_block = (n_tiles + want - 1) / want;
+    const long long slots = 2ll * sms;
+    long long best_tpb = n_tiles;
+    double best_cost = 1e300;
+    for (long long blocks = 1; blocks <= n_tiles && blocks <= 4096; ++blocks) {
+        const long long tpb = (n_tiles + blocks - 1) / blocks;
+        if ((n_tiles + tpb - 1) / tpb != blocks) continue;          // same split as a smaller block count
+        const long long ctas = base * blocks;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * ((double)tpb + 1.0);     // ~1 tile of prologue/epilogue per CTA
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best_tpb = tpb;
+        }
+    }
+    if (const char *env = getenv("MDB_ABLOCKS"))                     // tuning aid
+        if (atoll(env) > 0) best_tpb = (n_tiles + atoll(env) - 1) / atoll(env);
+    const long long tiles_per_block = best_tpb;
     plan->groups_per_block = (int)(tiles_per_block * kThreads);
     plan->n_ablocks = (int)((n_tiles + tiles_per_block - 1) / tiles_per_block);
     return MDB_OK;

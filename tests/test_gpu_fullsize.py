@@ -1,0 +1,133 @@
+"""BASELINE config-2 size on the GPU (100 000 atoms x 10 000 frames, 12 GB of frames in HBM).
+
+The oracle cannot run this size in seconds, so parity is anchored three ways:
+* an atom sub-block of the SAME trajectory against the CPU oracle (atoms are independent);
+* size-independent properties: lag 0 is exact, shard additivity, histogram totals, the segmented
+  (carried) jump scan equals the one-shot scan bit for bit;
+* the physics of the synthetic input: a Gaussian random walk has MSD = 3 sigma^2 tau,
+  F(q, tau) = exp(-q^2 sigma^2 tau / 2) and alpha_2 = 0.
+"""
+from functools import partial
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import md_oracle as orc
+
+N, T, SIGMA, Q = 100000, 10000, 0.01, 22.7
+
+
+@pytest.fixture(scope='module')
+def big():
+    import torch
+    import mdevaluate_b200 as md
+    from mdevaluate_b200._cuda import engine
+    from mdevaluate_b200.synthetic import random_walk_device, box_length
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip('needs ~20 GB of free HBM')
+    block, box, times = random_walk_device(N, T, seed=20240, box=box_length(N), pitch=engine.row_pitch(N))
+    coords = md.Coordinates.from_arrays(block, box, times, n_atoms=N)
+    yield md, coords, block, box, times
+    del coords, block
+    torch.cuda.empty_cache()
+
+
+def test_sub_block_against_oracle(big):
+    md, coords, block, box, times = big
+    from mdevaluate_b200._cuda import engine
+    n_sub = 192
+    sub = block[:, :3 * n_sub].cpu().numpy().reshape(T, n_sub, 3)
+    unw = orc.UnwrappedTrajectory(sub, box, times)
+    store = coords._resident().store_for(np.arange(T), nojump=True)
+    # image counts of the sub-block: bit-exact for all 10 000 frames
+    images = store.images[:, :3 * n_sub].cpu().numpy().astype(np.int64).reshape(T, n_sub, 3) - 128
+    np.testing.assert_array_equal(images, unw.counts)
+    assert np.abs(images).max() >= 1                     # atoms do cross the box
+    c = md.correlation
+    sub_store = engine.DeviceStore(store.coords, n_sub, images=store.images, box=store.box, box_const=store.box_const)
+    starts, idx = c._schedule(coords, c.log_indices, 10, 0.5, None)
+    rows = (starts[:, None] + idx[None, :]).astype(np.int32)
+    bins = np.linspace(0, 3.0, 501)
+    cases = (('msd', c.msd, orc.msd), ('isf', partial(c.isf, q=Q), partial(orc.isf, q=Q)),
+             ('ng', c.non_gaussian, orc.non_gaussian),
+             ('vh', partial(c.van_hove_self, bins=bins), partial(orc.van_hove_self, bins=bins)))
+    with np.errstate(all='ignore'):
+        for name, ours, theirs in cases:
+            spec = c._kernel_spec(ours)
+            sums, hist = engine.correlate_device(sub_store, rows, spec.corr)
+            got = spec.finalize(sums.cpu().numpy(), None if hist is None else hist.cpu().numpy(), n_sub, False)
+            _, ref = orc.shifted_correlation(theirs, unw, segments=10, window=0.5)
+            if name == 'vh':
+                np.testing.assert_array_equal(got, ref)
+            else:
+                nan = np.isnan(ref)
+                assert np.array_equal(np.isnan(got), nan)
+                tol = 1e-5 * np.abs(ref) + 1e-7 * (1.0 if name != 'msd' else float(np.nanmax(ref)))
+                assert (np.abs(got - ref)[~nan] <= tol[~nan]).all(), name
+                if name in ('msd', 'ng'):
+                    np.testing.assert_allclose(got[~nan], ref[~nan], rtol=1e-10, atol=1e-13)
+
+
+def test_exact_lag0_and_physics(big):
+    md, coords, block, box, times = big
+    c = md.correlation
+    t, msd = c.shifted_correlation(c.msd, coords.nojump, segments=100, average=True)
+    t, isf = c.shifted_correlation(partial(c.isf, q=Q), coords.nojump, segments=100, average=True)
+    with np.errstate(all='ignore'):
+        t, ng = c.shifted_correlation(c.non_gaussian, coords.nojump, segments=100, average=True)
+    assert msd[0] == 0.0 and isf[0] == 1.0 and np.isnan(ng[0])
+    tau = t[1:]
+    np.testing.assert_allclose(msd[1:], 3 * SIGMA ** 2 * tau, rtol=0.01)        # 1e7 atom*origins per lag
+    np.testing.assert_allclose(isf[1:], np.exp(-Q ** 2 * SIGMA ** 2 * tau / 2), atol=2e-3)
+    assert np.abs(ng[1:]).max() < 5e-3
+    # without unwrapping the MSD is wrong once atoms have crossed the box (the test is not vacuous)
+    t, raw = c.shifted_correlation(c.msd, coords, segments=10, average=True)
+    assert raw[-1] > 2 * msd[-1]
+
+
+def test_shard_additivity_and_histogram_total(big):
+    md, coords, block, box, times = big
+    from mdevaluate_b200._cuda import engine
+    import torch
+    c = md.correlation
+    store = coords._resident().store_for(np.arange(T), nojump=True)
+    starts, idx = c._schedule(coords, c.log_indices, 10, 0.5, None)
+    rows = (starts[:, None] + idx[None, :]).astype(np.int32)
+    bins = np.linspace(0, 8.0, 501)
+    spec = engine.CorrSpec(1 | 2 | 4 | 8, q=Q, n_bins=500, bin_mode=0, dx=float(np.diff(bins).mean()))
+    full_s, full_h = engine.correlate_device(store, rows, spec)
+    assert int(full_h.sum(dim=-1).min()) == N and int(full_h.sum(dim=-1).max()) == N      # every atom binned once
+    n0 = 50000 + 4 * 123                       # a split that is not a tile boundary
+    a = engine.DeviceStore(store.coords, n0, images=store.images, box=store.box, box_const=store.box_const)
+    off = 3 * n0
+    b = engine.DeviceStore(store.coords[:, off:], N - n0, images=store.images[:, off:], box=store.box,
+                           box_const=store.box_const)
+    sa, ha = engine.correlate_device(a, rows, spec)
+    sb, hb = engine.correlate_device(b, rows, spec)
+    assert torch.equal(ha + hb, full_h)                                                    # integer counts: exact
+    torch.testing.assert_close(sa + sb, full_s, rtol=1e-12, atol=1e-9)
+    # bit-reproducible run to run
+    again_s, again_h = engine.correlate_device(store, rows, spec)
+    assert torch.equal(again_s, full_s) and torch.equal(again_h, full_h)
+
+
+def test_segmented_scan_equals_one_shot(big):
+    md, coords, block, box, times = big
+    import torch
+    res = coords._resident()
+    store = res.store_for(np.arange(T), nojump=True)
+    # the same trajectory through the streaming path: many time segments with carried (prev, cum),
+    # only 500 frames kept (compaction)
+    keep = np.unique(np.random.default_rng(0).integers(0, T, 500))
+    res2 = md.Coordinates.from_arrays(block, box, times, n_atoms=N)._resident()
+    res2.force_compact = True
+    compact = res2._build_compact(keep, nojump=True)
+    rows = compact.rows_for(keep)
+    idx = torch.from_numpy(keep).to(block.device)
+    assert torch.equal(compact.images[torch.from_numpy(rows.astype(np.int64)).to(block.device)],
+                       store.images.index_select(0, idx))
+    assert torch.equal(compact.coords[torch.from_numpy(rows.astype(np.int64)).to(block.device), :3 * N],
+                       block.index_select(0, idx)[:, :3 * N])
