@@ -98,6 +98,9 @@ typedef struct mdb_corr_args {
     int32_t n_origins;           /* S                                                            */
     int32_t n_lags;              /* L                                                            */
     const int32_t *rows;         /* DEVICE [S*L] storage row per (origin, lag)                   */
+    const uint8_t *select;       /* DEVICE [S][sel_pitch] nonzero = atom takes part for origin s, or NULL (all atoms);
+                                    the sub-ensemble of subensemble_correlation, correlation.py:27-35 */
+    int64_t sel_pitch;           /* bytes per origin, >= n_atoms, multiple of 4                  */
     int32_t flags;               /* MDB_SUM_* | MDB_HIST                                         */
     double q;                    /* scattering vector length for MDB_SUM_SINC                    */
     int32_t n_bins;              /* B, for MDB_HIST                                              */

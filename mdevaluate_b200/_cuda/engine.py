@@ -109,7 +109,7 @@ def last_kernel_ms():
     return float(ms.value)
 
 
-def correlate_device(store, rows, spec, stream=None):
+def correlate_device(store, rows, spec, stream=None, select=None):
     """Launch the correlation kernels; returns device tensors ``(sums (S,L,3) f64, hist (S,L,B) i64|None)``.
 
     ``rows`` is an int32 ``(S, L)`` array of storage rows (host NumPy, cached on the device per store).
@@ -153,6 +153,11 @@ def correlate_device(store, rows, spec, stream=None):
     a.n_origins = S
     a.n_lags = L
     a.rows = rows_dev.data_ptr()
+    if select is not None:       # uint8 (S, sel_pitch): nonzero = atom takes part for that origin
+        if select.shape[0] != S or select.stride(0) % 4 or select.stride(0) < store.n_atoms:
+            raise ValueError('select must be (S, pitch) uint8 with pitch >= n_atoms and a multiple of 4')
+        a.select = select.data_ptr()
+        a.sel_pitch = select.stride(0)
     a.flags = spec.flags
     a.q = spec.q
     a.n_bins = spec.n_bins

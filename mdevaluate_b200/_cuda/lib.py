@@ -35,7 +35,7 @@ class CorrArgs(C.Structure):
         ('coords', C.c_void_p), ('pitch', C.c_int64), ('coord_type', C.c_int32),
         ('images', C.c_void_p), ('img_pitch', C.c_int64), ('box', C.c_void_p), ('box_const', C.c_double * 3),
         ('n_atoms', C.c_int32), ('n_origins', C.c_int32), ('n_lags', C.c_int32),
-        ('rows', C.c_void_p), ('flags', C.c_int32), ('q', C.c_double),
+        ('rows', C.c_void_p), ('select', C.c_void_p), ('sel_pitch', C.c_int64), ('flags', C.c_int32), ('q', C.c_double),
         ('n_bins', C.c_int32), ('bin_mode', C.c_int32), ('dx', C.c_double), ('edges', C.c_void_p),
         ('sums', C.c_void_p), ('hist', C.c_void_p),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),

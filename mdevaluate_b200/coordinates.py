@@ -21,6 +21,22 @@ class UnknownCoordinatesMode(Exception):
     pass
 
 
+def spatial_selector(frame, transform, rmin, rmax):
+    """Atoms with ``rmin <= transform(frame) <= rmax`` (coordinates.py:85-102); a selector for
+    ``correlation.subensemble_correlation``.  Runs on the host frame of each origin."""
+    from .utils import mask2indices
+    r = transform(frame)
+    selector = (rmin <= r) & (rmax >= r)
+    return mask2indices(selector)
+
+
+def spherical_radius(frame, origin=None):
+    """Distance of every atom from ``origin`` (default: box centre) (coordinates.py:49-56)."""
+    if origin is None:
+        origin = frame.box.diagonal() / 2
+    return ((frame - origin) ** 2).sum(axis=-1) ** 0.5
+
+
 class CoordinateFrame(np.ndarray):
     _known_modes = ('pbc', 'whole', 'nojump')
 

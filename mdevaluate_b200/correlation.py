@@ -27,8 +27,9 @@ from ._cuda import lib as _lib
 from ._cuda.lib import CudaPathError  # noqa: F401  (re-exported)
 from .utils import bin_rule, runningmean  # noqa: F401
 
-__all__ = ['log_indices', 'correlation', 'shifted_correlation', 'msd', 'isf', 'van_hove_self',
-           'non_gaussian', 'chi4', 'shifted_correlation_multi']
+__all__ = ['log_indices', 'correlation', 'subensemble_correlation', 'multi_subensemble_correlation',
+           'shifted_correlation', 'msd', 'isf', 'van_hove_self', 'non_gaussian', 'chi4',
+           'shifted_correlation_multi']
 
 
 # --------------------------------------------------------------------------------------------
@@ -48,6 +49,74 @@ def correlation(function, frames):
     iterator = iter(frames)
     start_frame = next(iterator)
     return map(lambda f: function(start_frame, f), chain([start_frame], iterator))
+
+
+def subensemble_correlation(selector_function, correlation_function=correlation):
+    """Correlate only the atoms ``selector_function(origin_frame)`` picks (correlation.py:27-35).
+
+    Passed as ``correlation=`` to :func:`shifted_correlation` the selection becomes a per-origin
+    atom mask inside the CUDA kernel (``mdb_corr_args.select``); called directly it evaluates pair
+    by pair like the reference."""
+    def c(function, frames):
+        iterator = iter(frames)
+        start_frame = next(iterator)
+        selector = selector_function(start_frame)
+        subensemble = map(lambda f: f[selector], chain([start_frame], iterator))
+        return correlation_function(function, subensemble)
+    c._mdb_strategy = ('sub', selector_function, correlation_function)
+    return c
+
+
+def multi_subensemble_correlation(selector_function):
+    """Several sub-ensembles per origin and their sizes (correlation.py:38-81).  ``selector_function``
+    returns an array whose entries are selectors (index lists, slices, masks); with
+    :func:`shifted_correlation` every sub-ensemble is one masked pass of the CUDA kernel and the
+    result is ``(times, result, count)`` as in the reference (correlation.py:153-189)."""
+    def cmulti(function, frames):
+        iterator = iter(frames)
+        start_frame = next(iterator)
+        selectors, sel_shape = _selector_array(selector_function(start_frame))
+        f_values = np.zeros(sel_shape + np.shape(function(start_frame, start_frame)),)
+        count = np.zeros(sel_shape, dtype=int)
+        first = [True]
+
+        def cc(act_frame):
+            for index in np.ndindex(sel_shape):
+                sel = selectors[index]
+                sf_sel = start_frame[sel]
+                if first[0]:
+                    count[index] = len(sf_sel)
+                f_values[index] = function(sf_sel, act_frame[sel]) if count[index] != 0 else 0
+            first[0] = False
+            return np.asarray(f_values.copy())
+        return map(cc, chain([start_frame], iterator)), count
+    cmulti.has_counter = True
+    cmulti._mdb_strategy = ('multi', selector_function)
+    return cmulti
+
+
+def _selector_array(selectors):
+    """The reference's reading of a multi-selector result (correlation.py:63-66)."""
+    selectors = np.asarray(selectors)
+    sel_shape = selectors.shape
+    if sel_shape[-1] == 0:
+        selectors = np.asarray(selectors, int)
+    if selectors.dtype != object:
+        sel_shape = sel_shape[:-1]
+    return selectors, sel_shape
+
+
+def _selector_mask(selector, n_atoms):
+    """Any NumPy row selector (index array, tuple from np.where, slice, boolean mask) as a 0/1 byte
+    mask over the atoms; the picked atoms keep their multiplicity 1 (duplicates are refused)."""
+    mask = np.zeros(n_atoms, dtype=np.uint8)
+    probe = np.arange(n_atoms)[selector]
+    if probe.ndim != 1:
+        raise NotImplementedError('selectors must pick rows (atoms) of the frame')
+    mask[probe] = 1
+    if int(mask.sum()) != probe.size:
+        raise NotImplementedError('selectors that pick an atom more than once are not supported on the B200 path')
+    return mask, probe.size
 
 
 # --------------------------------------------------------------------------------------------
@@ -103,7 +172,15 @@ class _Spec:
             raise NotImplementedError(name)
 
     def finalize(self, sums, hist, n_atoms, float32):
-        """Per-(origin, lag) function values from the shard-summed kernel output."""
+        """Per-(origin, lag) function values from the shard-summed kernel output.  ``n_atoms`` is the
+        number of correlated atoms: a scalar, or one count per origin (sub-ensembles, shape (S,))."""
+        if np.ndim(n_atoms):
+            n_atoms = np.asarray(n_atoms)
+            if self.name == 'van_hove_self':
+                if (n_atoms == 0).any():
+                    raise ZeroDivisionError('division by zero')      # the reference's ``1 / len(start)``
+                return (1 / n_atoms)[:, None, None] * hist
+            n_atoms = n_atoms[:, None]
         with np.errstate(divide='ignore', invalid='ignore'):
             if self.name == 'msd':
                 out = sums[..., 0] / n_atoms
@@ -220,8 +297,9 @@ def _schedule(frames, index_distribution, segments, window, skip):
     return start_frames, idx
 
 
-def _run(frames, frame_ids, specs):
-    """Kernel launch + shard reduction; returns host ``(sums, hist, n_atoms_global, float32)``."""
+def _run(frames, frame_ids, specs, select=None):
+    """Kernel launch + shard reduction; returns host ``(sums, hist, n_atoms_global, float32)``.
+    ``select`` is an optional host uint8 ``(S, N)`` per-origin atom mask."""
     flags = 0
     hist_spec = None
     q = 0.0
@@ -238,7 +316,15 @@ def _run(frames, frame_ids, specs):
         corr.n_bins, corr.bin_mode, corr.dx, corr.edges = (hist_spec.n_bins, hist_spec.bin_mode, hist_spec.dx,
                                                            hist_spec.edges)
     store, rows, n_atoms, float32, comm = _provider(frames, frame_ids)
-    sums, hist = engine.correlate_device(store, rows, corr)
+    select_dev = None
+    if select is not None:
+        if comm is not None:
+            raise NotImplementedError('sub-ensemble correlation of an atom-sharded trajectory is not implemented yet')
+        torch = _lib.require_cuda()
+        padded = np.zeros((select.shape[0], (select.shape[1] + 3) // 4 * 4), dtype=np.uint8)
+        padded[:, :select.shape[1]] = select
+        select_dev = torch.from_numpy(padded).to(store.device)
+    sums, hist = engine.correlate_device(store, rows, corr, select=select_dev)
     if comm is not None:
         from . import parallel
         sums, hist, n_atoms = parallel.allreduce_partials(sums, hist, n_atoms, comm)
@@ -267,9 +353,12 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
     Returns ``(times, result)`` with ``result`` of shape ``(segments, lags[, bins])`` or, with
     ``average=True``, ``(lags[, bins])``.
     """
-    if correlation is not globals()['correlation']:
-        raise NotImplementedError('custom correlation strategies (subensemble / has_counter) are not on the '
-                                  'B200 path yet; there is no CPU fallback')
+    strategy = getattr(correlation, '_mdb_strategy', None)
+    plain = correlation is globals()['correlation']
+    if not plain and not (strategy and (strategy[0] == 'multi' or strategy[2] is globals()['correlation'])):
+        raise NotImplementedError('only the default strategy, subensemble_correlation(selector) and '
+                                  'multi_subensemble_correlation(selector) are on the B200 path; '
+                                  'there is no CPU fallback')
     spec = _kernel_spec(function)
     start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
     frame_ids = start_frames[:, None] + idx[None, :]
@@ -277,9 +366,64 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
         raise IndexError('shifted_correlation: frame %d beyond the trajectory (%d frames)'
                          % (frame_ids.max(), len(frames)))
     times = _times(frames, idx)
-    sums, hist, n_atoms, float32 = _run(frames, frame_ids, [spec])
-    values = spec.finalize(sums, hist, n_atoms, float32)
-    return times, _average(values, len(start_frames), average)
+    if plain:
+        sums, hist, n_atoms, float32 = _run(frames, frame_ids, [spec])
+        values = spec.finalize(sums, hist, n_atoms, float32)
+        return times, _average(values, len(start_frames), average)
+
+    # ---- sub-ensembles: the selector sees every origin frame on the host, the kernel gets masks ----
+    origins = [frames[int(i)] for i in frame_ids[:, 0]]
+    n_all = len(origins[0])
+    if strategy[0] == 'sub':
+        picked = [_selector_mask(strategy[1](o), n_all) for o in origins]
+        masks = np.stack([m for m, _ in picked])
+        counts = np.array([c for _, c in picked])
+        sums, hist, _, float32 = _run(frames, frame_ids, [spec], select=masks)
+        values = spec.finalize(sums, hist, counts, float32)
+        return times, _average(values, len(start_frames), average)
+
+    sel_shape = None
+    per_origin = []
+    for o in origins:
+        selectors, shape = _selector_array(strategy[1](o))
+        if sel_shape is None:
+            sel_shape = shape
+        elif shape != sel_shape:
+            raise ValueError('the selector function must return the same number of sub-ensembles for every origin')
+        per_origin.append([_selector_mask(selectors[index], n_all) for index in np.ndindex(sel_shape)])
+    n_sub = len(per_origin[0])
+    counts = np.array([[c for _, c in row] for row in per_origin]).reshape((len(origins),) + sel_shape)
+    values = None
+    for k, index in enumerate(np.ndindex(sel_shape)):
+        masks = np.stack([row[k][0] for row in per_origin])
+        cnt = counts[(slice(None),) + index]
+        sums, hist, _, float32 = _run(frames, frame_ids, [spec], select=masks)
+        safe = np.where(cnt == 0, 1, cnt)
+        vals = spec.finalize(sums, hist, safe, float32)                  # (S, L[, B])
+        vals = np.where((cnt == 0).reshape((-1,) + (1,) * (vals.ndim - 1)), 0, vals)   # ``... else 0``
+        if values is None:
+            values = np.zeros((len(origins),) + sel_shape + vals.shape[1:], dtype=np.float64)
+        values[(slice(None),) + index] = vals
+    assert n_sub == k + 1
+    # values: (S, *sel_shape, L, ...); the reference's per-origin array is (L, *sel_shape, ...)
+    cdim = len(sel_shape)
+    if not average:
+        return times, values, counts                                     # correlation.py:178-189
+    for i in range(len(origins)):                                        # correlation.py:155-176
+        act_result = np.moveaxis(values[i], cdim, 0)
+        act_count = counts[i]
+        if i == 0:
+            count = act_count.copy()
+            bt = (np.newaxis,)
+            for j in range(act_result.ndim - 1):
+                bt += (np.newaxis,) if j >= cdim else (slice(None),)
+            result = act_result * act_count[bt]
+        else:
+            result += act_result * act_count[bt]
+            count += act_count
+    np.divide(result, count[bt], out=result, where=count[bt] != 0)
+    result = np.moveaxis(result, 0, cdim)
+    return times, result, count / len(origins)
 
 
 def shifted_correlation_multi(functions, frames, index_distribution=log_indices, segments=10, window=0.5,

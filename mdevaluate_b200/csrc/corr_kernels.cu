@@ -56,6 +56,8 @@ struct CorrDev {
     int groups_per_block;
     int S, L;
     const int *rows;
+    const uint8_t *select;   // [S][sel_pitch] 1 = atom takes part for origin s (sub-ensembles), or nullptr
+    long long sel_pitch;
     int n_chunks, n_ablocks;
     double q2;
     int n_bins;
@@ -144,13 +146,13 @@ __device__ __noinline__ int exact_bin(double ddx, double ddy, double ddz, int bi
 }
 
 // One group of 4 atoms against one lag frame: partial sums of r^2, r^4 (float64) and sinc (float32)
-// over the group, histogram counts straight into shared memory.  MASKED is only instantiated for
-// the last group(s) of a shard: atoms beyond `nv` carry zeroed inputs on both sides, so they add
-// exactly 0 to the r^2 / r^4 sums and exactly 1.0f each to the sinc sum, which is taken off again;
-// the histogram skips them.
+// over the group, histogram counts straight into shared memory.  MASKED is instantiated for the
+// last tile of a shard and for sub-ensemble launches: bit a of `vmask` says whether atom a of the
+// group takes part (it exists, and the origin's selector picked it); the others are computed and
+// discarded with selects (their inputs may be row padding).
 template <int FLAGS, bool HIST_F32, bool MASKED>
 __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[12], const float (&raw0)[12],
-                                           const double (&ut)[12], const float (&rawt)[12], int nv,
+                                           const double (&ut)[12], const float (&rawt)[12], uint32_t vmask,
                                            double &sum2, double &sum4, float &sums, unsigned int *s_hist_k,
                                            const double *s_edges) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
@@ -169,8 +171,9 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
         const double ddy = u0[3 * a + 1] - ut[3 * a + 1];
         const double ddz = u0[3 * a + 2] - ut[3 * a + 2];
         const double r2 = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
-        if constexpr (kR2) sum2 += r2;
-        if constexpr (kR4) sum4 = fma(r2, r2, sum4);
+        const bool on = !MASKED || ((vmask >> a) & 1u);
+        if constexpr (kR2) sum2 += on ? r2 : 0.0;
+        if constexpr (kR4) sum4 = MASKED ? sum4 + (on ? r2 * r2 : 0.0) : fma(r2, r2, sum4);
         if constexpr (kSinc) yq[a] = (float)(r2 * p.q2);
         if constexpr (kHist) {
             dd[a][0] = ddx; dd[a][1] = ddy; dd[a][2] = ddz;
@@ -181,8 +184,13 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
         float v0, v1, v2, v3;
         sinc_of_square_x2(yq[0], yq[1], v0, v1);
         sinc_of_square_x2(yq[2], yq[3], v2, v3);
+        if constexpr (MASKED) {
+            v0 = (vmask & 1u) ? v0 : 0.0f;
+            v1 = (vmask & 2u) ? v1 : 0.0f;
+            v2 = (vmask & 4u) ? v2 : 0.0f;
+            v3 = (vmask & 8u) ? v3 : 0.0f;
+        }
         sums = (v0 + v1) + (v2 + v3);
-        if constexpr (MASKED) sums -= (float)(4 - nv);
     }
     if constexpr (kHist) {
         if (HIST_F32) {
@@ -190,7 +198,7 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
             // arrays); replay vec = start - end; (vec**2).sum(-1) ** .5 in float32, then the exact rule
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                if (!MASKED || a < nv) {
+                if (!MASKED || ((vmask >> a) & 1u)) {
                     const float vx = __fsub_rn(raw0[3 * a], rawt[3 * a]);
                     const float vy = __fsub_rn(raw0[3 * a + 1], rawt[3 * a + 1]);
                     const float vz = __fsub_rn(raw0[3 * a + 2], rawt[3 * a + 2]);
@@ -215,7 +223,7 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
             bool any_slow = false;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const bool live = !MASKED || a < nv;
+                const bool live = !MASKED || ((vmask >> a) & 1u);
                 bool fast = false;
                 int bin = 0;
                 if (p.bin_mode == MDB_BINS_UNIFORM) {
@@ -244,6 +252,19 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
             }
         }
     }
+}
+
+// Which atoms of group g take part: they exist (tail of the shard) and, for sub-ensemble launches,
+// the selector of origin s picked them (one byte per atom, four atoms = one 32-bit word).
+__device__ __forceinline__ uint32_t group_mask(const CorrDev &p, int s, int g) {
+    const int nv = max(0, min(4, p.n_atoms - 4 * g));
+    uint32_t m = (1u << nv) - 1u;
+    if (p.select && nv > 0) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p.select + (long long)s * p.sel_pitch) + g);
+        m &= ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) |
+             ((w & 0xff000000u) ? 8u : 0u);
+    }
+    return m;
 }
 
 // CTA prologue shared by both kernels: which (origin, chunk, atom block) am I, rows and boxes.
@@ -412,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) 
     const int g_end = min(p.n_groups, g_begin + p.groups_per_block);
     for (int g = g_begin + tid; g < g_end; g += kThreads) {
         const int nv = min(4, p.n_atoms - 4 * g);
+        const uint32_t vmask = group_mask(p, w.s, g);
         double u0[12];
         float raw0[12];
         GroupLoader<CT, IMG, VEC, false>::load(p, s_row[0], g, nv, s_box[0], u0, raw0);
@@ -423,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) 
                 GroupLoader<CT, IMG, VEC, true>::load(p, s_row[k + 1], g, nv, s_box[k + 1], ut, rawt);
                 double s2, s4;
                 float ss;
-                eval_group<FLAGS, kHistF32, true>(p, u0, raw0, ut, rawt, nv, s2, s4, ss, s_hist + k * p.n_bins,
+                eval_group<FLAGS, kHistF32, true>(p, u0, raw0, ut, rawt, vmask, s2, s4, ss, s_hist + k * p.n_bins,
                                                   s_edges);
                 if constexpr (Accum<FLAGS>::kR2) acc.r2[k] += s2;
                 if constexpr (Accum<FLAGS>::kR4) acc.r4[k] += s4;
@@ -491,9 +513,9 @@ struct Ring {
 };
 
 // Take the calling thread's 4 atoms out of the current stage, release the stage, unwrap.
-template <bool IMG, bool MASKED, bool BOXC>
+template <bool IMG, bool BOXC>
 __device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
-                                            const unsigned char *stages, int stage_bytes, int tid, int nv,
+                                            const unsigned char *stages, int stage_bytes, int tid,
                                             const double *bx, double (&u)[12], float (&raw)[12]) {
     mbar_wait(full0 + 8 * ring.stage, ring.phase);
     const unsigned char *src = stages + (size_t)ring.stage * stage_bytes;
@@ -511,15 +533,6 @@ __device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32
     // single converged instruction ahead of it in program order)
     mbar_arrive_if(empty0 + 8 * ring.stage, (tid & 31) == 0);
     ring.advance();
-    if (MASKED) {
-        // last tile of the shard: whatever lies beyond atom n_atoms-1 becomes (0,0,0), n = 0
-#pragma unroll
-        for (int cc = 0; cc < 12; ++cc)
-            if (cc >= 3 * nv) {
-                raw[cc] = 0.0f;
-                wds[cc >> 2] = (wds[cc >> 2] & ~(0xffu << (8 * (cc & 3)))) | (0x80u << (8 * (cc & 3)));
-            }
-    }
     // a box that is the same for every row comes from the kernel parameters (constant bank operands)
     unwrap12<IMG>(raw, wds, BOXC ? p.box_const : bx, u);
 }
@@ -529,7 +542,8 @@ __device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32
 // instruction cache); per-lag accumulators live in shared memory, one private column per thread.
 template <bool IMG, int FLAGS, bool MASKED, bool BOXC>
 __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
-                                             const unsigned char *stages, int stage_bytes, int tid, int nv, int nl,
+                                             const unsigned char *stages, int stage_bytes, int tid, uint32_t vmask,
+                                             int nl,
                                              const double (*s_box)[3], double *s_acc, unsigned int *s_hist,
                                              const double *s_edges) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
@@ -540,15 +554,15 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
     constexpr int NV = (kR2 ? 1 : 0) + (kR4 ? 1 : 0) + (kSinc ? 1 : 0);
     double u0[12];
     float raw0[12];
-    fetch_group<IMG, MASKED, BOXC>(p, ring, full0, empty0, stages, stage_bytes, tid, nv, s_box[0], u0, raw0);
+    fetch_group<IMG, BOXC>(p, ring, full0, empty0, stages, stage_bytes, tid, s_box[0], u0, raw0);
 #pragma unroll 1
     for (int k = 0; k < nl; ++k) {
         double ut[12];
         float rawt[12];
-        fetch_group<IMG, MASKED, BOXC>(p, ring, full0, empty0, stages, stage_bytes, tid, nv, s_box[k + 1], ut, rawt);
+        fetch_group<IMG, BOXC>(p, ring, full0, empty0, stages, stage_bytes, tid, s_box[k + 1], ut, rawt);
         double s2, s4;
         float ss;
-        eval_group<FLAGS, kHistF32, MASKED>(p, u0, raw0, ut, rawt, nv, s2, s4, ss, s_hist + k * p.n_bins, s_edges);
+        eval_group<FLAGS, kHistF32, MASKED>(p, u0, raw0, ut, rawt, vmask, s2, s4, ss, s_hist + k * p.n_bins, s_edges);
         double *col = s_acc + (size_t)k * NV * kThreads + tid;
         int v = 0;
         if constexpr (kR2) { col[v * kThreads] += s2; ++v; }
@@ -636,14 +650,13 @@ __global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDe
     // ===== compute warps =====
     for (int t = 0; t < n_tiles; ++t) {
         const int g_last = g_begin + t * kThreads + kThreads - 1;          // last group of this tile
-        if (4 * g_last + 3 < p.n_atoms) {
-            process_tile<IMG, FLAGS, false, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, 4, w.nl, s_box, s_acc,
-                                            s_hist, s_edges);
+        if (4 * g_last + 3 < p.n_atoms && p.select == nullptr) {
+            process_tile<IMG, FLAGS, false, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, 0xfu, w.nl, s_box,
+                                                  s_acc, s_hist, s_edges);
         } else {
-            const int g = g_begin + t * kThreads + tid;
-            const int nv = max(0, min(4, p.n_atoms - 4 * g));
-            process_tile<IMG, FLAGS, true, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, nv, w.nl, s_box, s_acc,
-                                           s_hist, s_edges);
+            const uint32_t vmask = group_mask(p, w.s, g_begin + t * kThreads + tid);
+            process_tile<IMG, FLAGS, true, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, vmask, w.nl, s_box,
+                                                 s_acc, s_hist, s_edges);
         }
     }
 
@@ -846,6 +859,9 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     if (a->images && !a->box && !(a->box_const[0] > 0.0 && a->box_const[1] > 0.0 && a->box_const[2] > 0.0))
         return fail(MDB_ERR_ARGUMENT, "images need box (per row) or a positive box_const");
     if (a->images && a->img_pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "img_pitch < 3*n_atoms");
+    if (a->select && (a->sel_pitch < a->n_atoms || a->sel_pitch % 4 != 0 ||
+                      reinterpret_cast<uintptr_t>(a->select) % 4 != 0))
+        return fail(MDB_ERR_ARGUMENT, "select needs sel_pitch >= n_atoms, a multiple of 4, and a 4-byte aligned base");
     const bool hist = (a->flags & MDB_HIST) != 0;
     if (hist) {
         if (!a->hist) return fail(MDB_ERR_ARGUMENT, "hist is required with MDB_HIST");
@@ -871,6 +887,8 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     p.S = a->n_origins;
     p.L = a->n_lags;
     p.rows = a->rows;
+    p.select = a->select;
+    p.sel_pitch = a->sel_pitch;
     p.n_chunks = plan.n_chunks;
     p.n_ablocks = plan.n_ablocks;
     p.q2 = a->q * a->q;

@@ -13,6 +13,16 @@ def runningmean(data, nav):
     return np.convolve(data, np.ones((nav,)) / nav, mode='valid')
 
 
+def mask2indices(mask):
+    """Selected indices of a mask; for a 2-D mask along the second axis (utils.py:102-118)."""
+    mask = np.array(mask)
+    if len(mask.shape) == 1:
+        indices = np.where(mask)
+    else:
+        indices = np.array([np.where(m) for m in mask])
+    return indices
+
+
 def bin_rule(bins):
     """Which rule ``utils.histogram`` (utils.py:328-338) applies to these bin edges.
 

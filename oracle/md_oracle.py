@@ -72,9 +72,55 @@ def pairwise(function, frames):
     return map(lambda f: function(origin, f), chain([origin], it))
 
 
+def subensemble_pairwise(selector_function, correlation_function=None):
+    """``subensemble_correlation``: the origin frame picks the atoms.  mdevaluate/correlation.py:27-35."""
+    inner = pairwise if correlation_function is None else correlation_function
+
+    def strategy(function, frames):
+        it = iter(frames)
+        origin = next(it)
+        selector = selector_function(origin)
+        return inner(function, map(lambda f: f[selector], chain([origin], it)))
+    return strategy
+
+
+def multi_subensemble_pairwise(selector_function):
+    """``multi_subensemble_correlation``: several sub-ensembles per origin, with their sizes.
+    mdevaluate/correlation.py:38-81 (the strategy is flagged ``has_counter``)."""
+    def strategy(function, frames):
+        it = iter(frames)
+        origin = next(it)
+        selectors = np.asarray(selector_function(origin))
+        sel_shape = selectors.shape
+        if sel_shape[-1] == 0:
+            selectors = np.asarray(selectors, int)
+        if selectors.dtype != object:
+            sel_shape = sel_shape[:-1]
+        values = np.zeros(sel_shape + function(origin, origin).shape,)
+        count = np.zeros(sel_shape, dtype=int)
+        first = [True]
+
+        def per_frame(frame):
+            for index in np.ndindex(sel_shape):
+                sel = selectors[index]
+                picked = origin[sel]
+                if first[0]:
+                    count[index] = len(picked)
+                values[index] = function(picked, frame[sel]) if count[index] != 0 else 0
+            first[0] = False
+            return np.asarray(values.copy())
+        return map(per_frame, chain([origin], it)), count
+    strategy.has_counter = True
+    return strategy
+
+
 def shifted_correlation(function, frames, index_distribution=log_indices,
-                        segments=10, window=0.5, skip=None, average=False):
-    """Driver without the ``has_counter`` branch.  mdevaluate/correlation.py:131-151,190-201."""
+                        segments=10, window=0.5, skip=None, average=False, correlation=None):
+    """Driver.  mdevaluate/correlation.py:131-201 (``has_counter`` branch: 153-189)."""
+    if correlation is not None and getattr(correlation, 'has_counter', False):
+        return _shifted_correlation_counted(function, frames, index_distribution, segments, window, skip, average,
+                                            correlation)
+    strategy = pairwise if correlation is None else correlation
     if skip is None:
         try:
             skip = frames._slice.start / len(frames)
@@ -87,7 +133,7 @@ def shifted_correlation(function, frames, index_distribution=log_indices,
 
     result = 0 if average else []
     for s in starts:
-        row = list(pairwise(function, map(frames.__getitem__, idx + s)))
+        row = list(strategy(function, map(frames.__getitem__, idx + s)))
         if average:
             result += np.array(row)
         else:
@@ -96,6 +142,52 @@ def shifted_correlation(function, frames, index_distribution=log_indices,
     if average:
         result = result / len(starts)
     return times, result
+
+
+def _shifted_correlation_counted(function, frames, index_distribution, segments, window, skip, average, strategy):
+    """The ``has_counter`` branch.  mdevaluate/correlation.py:153-189."""
+    if skip is None:
+        try:
+            skip = frames._slice.start / len(frames)
+        except (TypeError, AttributeError):
+            skip = 0
+    starts, num_frames = schedule(len(frames), segments, window, skip)
+    idx = index_distribution(0, num_frames)
+    times = np.array([frames[i].time for i in idx]) - frames[0].time
+
+    def correlate(s):
+        return strategy(function, map(frames.__getitem__, idx + s))
+
+    if average:
+        for i, s in enumerate(starts):
+            act_result, act_count = correlate(s)
+            act_result = np.array(list(act_result))
+            act_count = np.array(act_count)
+            if i == 0:
+                count = act_count
+                cdim = act_count.ndim
+                rdim = act_result.ndim
+                bt = (np.newaxis,)
+                for j in range(rdim - 1):
+                    bt += (np.newaxis,) if j >= cdim else (slice(None),)
+                result = act_result * act_count[bt]
+            else:
+                result += act_result * act_count[bt]
+                count += act_count
+        np.divide(result, count[bt], out=result, where=count[bt] != 0)
+        result = np.moveaxis(result, 0, cdim)
+        count = count / len(starts)
+        return times, result, count
+    count = []
+    result = []
+    for s in starts:
+        act_result, act_count = correlate(s)
+        result.append(list(act_result))
+        count.append(act_count)
+    count = np.asarray(count)
+    cdim = count.ndim
+    result = np.moveaxis(np.asarray(result), 1, cdim)
+    return times, result, count
 
 
 # --------------------------------------------------------------------------- #

@@ -169,6 +169,52 @@ def main():
     g1['msd_sel'] = r
     np.savez_compressed(os.path.join(HERE, 'walk_small.npz'), **g1)
 
+    # ---- G1b: sub-ensembles picked by the origin frame (correlation.py:27-81, 153-189) ----------
+    L = float(box[0])
+
+    def slab(frame, lo=0.0, hi=0.4):            # atoms whose wrapped z lies in [lo, hi) * L at the origin
+        z = np.asarray(frame)[:, 2] % L
+        return np.where((z >= lo * L) & (z < hi * L))[0]
+
+    def slabs_masks(frame):                     # (3, N) boolean masks
+        z = np.asarray(frame)[:, 2] % L
+        edges = np.array([0.0, 0.3, 0.65, 1.0]) * L
+        return np.array([(z >= edges[i]) & (z < edges[i + 1]) for i in range(3)])
+
+    def slabs_ragged(frame):                    # object array of index arrays, one of them empty
+        z = np.asarray(frame)[:, 2] % L
+        out = np.empty(3, dtype=object)
+        out[0] = np.where(z < 0.5 * L)[0]
+        out[1] = np.where(z > 2 * L)[0]
+        out[2] = np.where(z >= 0.5 * L)[0]
+        return out
+
+    gs = {'pos': pos, 'box': box, 'times': times, 'bins': bins}
+    with np.errstate(all='ignore'):
+        for name in ('msd', 'isf', 'ng', 'vh'):
+            fn = fns[name]
+            t, r = corr.shifted_correlation(fn, coords.nojump, segments=9, window=0.4,
+                                            correlation=corr.subensemble_correlation(slab))
+            gs['sub_' + name] = r
+            t, r = corr.shifted_correlation(fn, coords.nojump, segments=9, window=0.4, average=True,
+                                            correlation=corr.subensemble_correlation(partial(slab, lo=0.5, hi=0.9)))
+            gs['sub_avg_' + name] = r
+            for tag, sel in (('masks', slabs_masks), ('ragged', slabs_ragged)):
+                if name == 'vh' and tag == 'ragged':
+                    continue
+                t, r, cnt = corr.shifted_correlation(fn, coords.nojump, segments=9, window=0.4,
+                                                     correlation=corr.multi_subensemble_correlation(sel))
+                gs['multi_%s_%s' % (tag, name)] = r
+                gs['multi_%s_count' % tag] = cnt
+                t, r, cnt = corr.shifted_correlation(fn, coords.nojump, segments=9, window=0.4, average=True,
+                                                     correlation=corr.multi_subensemble_correlation(sel))
+                gs['multi_avg_%s_%s' % (tag, name)] = r
+                gs['multi_avg_%s_count' % tag] = cnt
+        gs['sub_t'] = t
+        rr = md.coordinates.spatial_selector(coords[5], lambda f: np.asarray(f)[:, 0], 0.2, 0.9)
+        gs['spatial_selector_5'] = rr
+    np.savez_compressed(os.path.join(HERE, 'subensemble.npz'), **gs)
+
     # ---- G2: BASELINE config 1 (1000 x 1000, MSD, S=100, L=70), outputs only ---------
     pos, box, times = random_walk(1000, 1000, seed=20240)
     coords, reader = reference_coordinates(md, pos, box, times)

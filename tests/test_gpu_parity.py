@@ -293,3 +293,82 @@ def test_per_frame_box(md):
         _, ref = orc.shifted_correlation(partial(orc.isf, q=22.7), unw, segments=6, window=0.5)
         _, r = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=6, window=0.5)
         close(r, ref)
+
+
+# ---- sub-ensembles: SURVEY.md section 8f-1 (correlation.py:27-81, 153-189) ---------------------------
+def _selectors(L):
+    def slab(frame, lo=0.0, hi=0.4):
+        z = np.asarray(frame)[:, 2] % L
+        return np.where((z >= lo * L) & (z < hi * L))[0]
+
+    def slabs_masks(frame):
+        z = np.asarray(frame)[:, 2] % L
+        edges = np.array([0.0, 0.3, 0.65, 1.0]) * L
+        return np.array([(z >= edges[i]) & (z < edges[i + 1]) for i in range(3)])
+
+    def slabs_ragged(frame):
+        z = np.asarray(frame)[:, 2] % L
+        out = np.empty(3, dtype=object)
+        out[0] = np.where(z < 0.5 * L)[0]
+        out[1] = np.where(z > 2 * L)[0]
+        out[2] = np.where(z >= 0.5 * L)[0]
+        return out
+    return slab, slabs_masks, slabs_ragged
+
+
+def _check(name, got, ref):
+    if name == 'vh':
+        np.testing.assert_array_equal(got, ref)
+    elif name == 'isf':
+        close(got, ref)
+    else:
+        close(got, ref, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['msd', 'isf', 'ng', 'vh'])
+def test_subensemble_correlation_golden(golden, md, name):
+    g = golden('subensemble')
+    coords = md.Coordinates.from_arrays(g['pos'], g['box'], g['times'])
+    c = md.correlation
+    slab, slabs_masks, slabs_ragged = _selectors(float(g['box'][0]))
+    fn = {'msd': c.msd, 'isf': partial(c.isf, q=22.7), 'ng': c.non_gaussian,
+          'vh': partial(c.van_hove_self, bins=g['bins'])}[name]
+    t, r = c.shifted_correlation(fn, coords.nojump, segments=9, window=0.4,
+                                 correlation=c.subensemble_correlation(slab))
+    np.testing.assert_array_equal(t, g['sub_t'])
+    _check(name, r, g['sub_' + name])
+    t, r = c.shifted_correlation(fn, coords.nojump, segments=9, window=0.4, average=True,
+                                 correlation=c.subensemble_correlation(partial(slab, lo=0.5, hi=0.9)))
+    _check(name, r, g['sub_avg_' + name])
+    for tag, sel in (('masks', slabs_masks), ('ragged', slabs_ragged)):
+        if name == 'vh' and tag == 'ragged':
+            continue
+        t, r, cnt = c.shifted_correlation(fn, coords.nojump, segments=9, window=0.4,
+                                          correlation=c.multi_subensemble_correlation(sel))
+        np.testing.assert_array_equal(cnt, g['multi_%s_count' % tag])
+        assert r.shape == g['multi_%s_%s' % (tag, name)].shape
+        _check(name, r, g['multi_%s_%s' % (tag, name)])
+        t, r, cnt = c.shifted_correlation(fn, coords.nojump, segments=9, window=0.4, average=True,
+                                          correlation=c.multi_subensemble_correlation(sel))
+        np.testing.assert_array_equal(cnt, g['multi_avg_%s_count' % tag])
+        if name == 'vh':
+            np.testing.assert_allclose(r, g['multi_avg_%s_%s' % (tag, name)], rtol=1e-13, atol=0)
+        else:
+            _check(name, r, g['multi_avg_%s_%s' % (tag, name)])
+
+
+def test_spatial_selector_and_strategy_objects(golden, md):
+    g = golden('subensemble')
+    coords = md.Coordinates.from_arrays(g['pos'], g['box'], g['times'])
+    sel = md.coordinates.spatial_selector(coords[5], lambda f: np.asarray(f)[:, 0], 0.2, 0.9)
+    np.testing.assert_array_equal(sel[0], g['spatial_selector_5'][0])
+    c = md.correlation
+    # the strategy objects also work stand-alone, pair by pair, like the reference's generators
+    slab = _selectors(float(g['box'][0]))[0]
+    idx = [3, 4, 9]
+    vals = list(c.subensemble_correlation(slab)(c.msd, (coords.nojump[i] for i in idx)))
+    unw = orc.UnwrappedTrajectory(g['pos'], g['box'], g['times'])
+    ref = list(orc.subensemble_pairwise(slab)(orc.msd, (unw[i] for i in idx)))
+    np.testing.assert_allclose(vals, ref, rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        c.shifted_correlation(c.msd, coords, correlation=c.subensemble_correlation(lambda f: [0, 0, 1]))

@@ -130,3 +130,52 @@ def test_config1_golden(golden):
     assert r.dtype == np.float32
     t, r = orc.shifted_correlation(partial(orc.van_hove_self, bins=g['vh_bins']), unw, segments=10, window=0.5)
     same(r, g['vh'])
+
+
+# ---- sub-ensembles (correlation.py:27-81, 153-189) ---------------------------------------------------
+def _selectors(L):
+    def slab(frame, lo=0.0, hi=0.4):
+        z = np.asarray(frame)[:, 2] % L
+        return np.where((z >= lo * L) & (z < hi * L))[0]
+
+    def slabs_masks(frame):
+        z = np.asarray(frame)[:, 2] % L
+        edges = np.array([0.0, 0.3, 0.65, 1.0]) * L
+        return np.array([(z >= edges[i]) & (z < edges[i + 1]) for i in range(3)])
+
+    def slabs_ragged(frame):
+        z = np.asarray(frame)[:, 2] % L
+        out = np.empty(3, dtype=object)
+        out[0] = np.where(z < 0.5 * L)[0]
+        out[1] = np.where(z > 2 * L)[0]
+        out[2] = np.where(z >= 0.5 * L)[0]
+        return out
+    return slab, slabs_masks, slabs_ragged
+
+
+def test_subensemble_golden(golden):
+    g = golden('subensemble')
+    unw = orc.UnwrappedTrajectory(g['pos'], g['box'], g['times'])
+    slab, slabs_masks, slabs_ragged = _selectors(float(g['box'][0]))
+    fns = {'msd': orc.msd, 'isf': partial(orc.isf, q=22.7), 'ng': orc.non_gaussian,
+           'vh': partial(orc.van_hove_self, bins=g['bins'])}
+    with np.errstate(all='ignore'):
+        for name, fn in fns.items():
+            t, r = orc.shifted_correlation(fn, unw, segments=9, window=0.4,
+                                           correlation=orc.subensemble_pairwise(slab))
+            same(r, g['sub_' + name])
+            t, r = orc.shifted_correlation(fn, unw, segments=9, window=0.4, average=True,
+                                           correlation=orc.subensemble_pairwise(partial(slab, lo=0.5, hi=0.9)))
+            same(r, g['sub_avg_' + name])
+            for tag, sel in (('masks', slabs_masks), ('ragged', slabs_ragged)):
+                if name == 'vh' and tag == 'ragged':
+                    continue
+                t, r, cnt = orc.shifted_correlation(fn, unw, segments=9, window=0.4,
+                                                    correlation=orc.multi_subensemble_pairwise(sel))
+                same(r, g['multi_%s_%s' % (tag, name)])
+                same(cnt, g['multi_%s_count' % tag])
+                t, r, cnt = orc.shifted_correlation(fn, unw, segments=9, window=0.4, average=True,
+                                                    correlation=orc.multi_subensemble_pairwise(sel))
+                same(r, g['multi_avg_%s_%s' % (tag, name)])
+                same(cnt, g['multi_avg_%s_count' % tag])
+    same(t, g['sub_t'])
