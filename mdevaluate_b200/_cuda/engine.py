@@ -119,7 +119,7 @@ def correlate_device(store, rows, spec, stream=None, select=None):
     rows = np.ascontiguousarray(rows, dtype=np.int32)
     S, L = rows.shape
     dev = store.device
-    key = ('rows', rows.shape, hash(rows.tobytes()))
+    key = ('rows', rows.shape, hash(rows.data.tobytes()) if rows.size < 4096 else hash(rows.tobytes()))
     rows_dev = store._cache.get(key)
     if rows_dev is None:
         rows_dev = torch.from_numpy(rows).to(dev)
@@ -166,12 +166,16 @@ def correlate_device(store, rows, spec, stream=None, select=None):
     a.edges = edges_dev.data_ptr() if edges_dev is not None else None
     a.sums = sums.data_ptr()
     a.hist = hist.data_ptr() if hist is not None else None
-    nbytes = C.c_size_t(0)
-    _lib.check(lib.mdb_corr_workspace_bytes(C.byref(a), C.byref(nbytes)), 'mdb_corr_workspace_bytes')
+    skey = ('ws_bytes', S, L, spec.flags, spec.n_bins, a.coord_type, store.images is not None)
+    need = store._cache.get(skey)
+    if need is None:
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.mdb_corr_workspace_bytes(C.byref(a), C.byref(nbytes)), 'mdb_corr_workspace_bytes')
+        need = store._cache[skey] = nbytes.value
     wkey = 'workspace'
     ws = store._cache.get(wkey)
-    if ws is None or ws.numel() < nbytes.value:
-        ws = torch.empty((max(nbytes.value, 1),), dtype=torch.uint8, device=dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
         store._cache[wkey] = ws
     a.workspace = ws.data_ptr()
     a.workspace_bytes = ws.numel()

@@ -279,14 +279,27 @@ def _times(frames, idx):
     return np.array([frames[int(i)].time for i in idx]) - frames[0].time       # correlation.py:151
 
 
+_schedule_cache = {}
+
+
 def _schedule(frames, index_distribution, segments, window, skip):
-    """Origins and lags, the reference's expressions verbatim (correlation.py:131-144)."""
+    """Origins and lags, the reference's expressions verbatim (correlation.py:131-144).
+    The default ``log_indices`` is pure, so its schedules are memoised (arrays are read-only)."""
     if skip is None:
         try:
             skip = frames._slice.start / len(frames)
         except (TypeError, AttributeError):
             skip = 0
     assert window + skip < 1
+    key = None
+    if index_distribution is log_indices:
+        try:
+            key = (len(frames), segments, float(window), float(skip))
+            hit = _schedule_cache.get(key)
+            if hit is not None:
+                return hit
+        except TypeError:
+            key = None
 
     start_frames = np.unique(np.linspace(
         len(frames) * skip, len(frames) * (1 - window),
@@ -294,6 +307,12 @@ def _schedule(frames, index_distribution, segments, window, skip):
     ))
     num_frames = int(len(frames) * (window))
     idx = np.asarray(index_distribution(0, num_frames))
+    if key is not None:
+        start_frames.setflags(write=False)
+        idx.setflags(write=False)
+        if len(_schedule_cache) > 256:
+            _schedule_cache.clear()
+        _schedule_cache[key] = (start_frames, idx)
     return start_frames, idx
 
 
