@@ -159,6 +159,9 @@ class Coordinates:
     # -- HBM residency ------------------------------------------------------------------------
     def _resident(self):
         """The HBM residency manager shared by every view of (reader, selection)."""
+        res = self.__dict__.get('_resident_obj')
+        if res is not None:
+            return res
         from ._cuda.resident import Resident
         cache = self.frames.__dict__.setdefault('_mdb_resident', {}) if hasattr(self.frames, '__dict__') else {}
         key = hash(np.asarray(self.atom_filter).tobytes()) if self.atom_filter is not None else None
@@ -166,6 +169,7 @@ class Coordinates:
         if res is None:
             res = Resident(self.frames, self.atom_filter)
             cache[key] = res
+        self._resident_obj = res      # copies of this object (slices, mode views) inherit the handle
         return res
 
     # -- frames protocol ----------------------------------------------------------------------

@@ -43,6 +43,8 @@ def build(force=False, verbose=False):
     nvcc = nvcc_path()
     common = [nvcc, '-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--ftz=false', '--prec-div=true',
               '--prec-sqrt=true', '--fmad=true'] + ARCH
+    if os.environ.get('MDB_NVCC_DEFINES'):
+        common += ['-D' + d for d in os.environ['MDB_NVCC_DEFINES'].split(',')]
     if verbose:
         common += ['-Xptxas', '-v']
     procs = []

@@ -43,6 +43,9 @@ constexpr int kTileAtoms = 4 * kThreads;          // atoms per bulk tile
 constexpr int kCoordTileBytes = kTileAtoms * 12;  // 12288
 constexpr int kImgTileBytes = kTileAtoms * 3;     // 3072
 constexpr int kBulkThreads = kThreads + 32;       // + one producer warp
+#ifndef MDB_BULK_CTAS_PER_SM
+#define MDB_BULK_CTAS_PER_SM 2
+#endif
 
 struct CorrDev {
     const void *coords;
@@ -572,7 +575,7 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
 }
 
 template <bool IMG, int FLAGS, bool BOXC>
-__global__ void __launch_bounds__(kBulkThreads, 2) corr_bulk_kernel(const CorrDev p, const int n_stages) {
+__global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_kernel(const CorrDev p, const int n_stages) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
@@ -694,7 +697,7 @@ struct Plan {
     size_t smem;
 };
 
-constexpr size_t kSmemBudgetPerCta = 110 * 1024;   // two CTAs per SM
+constexpr size_t kSmemBudgetPerCta = (MDB_BULK_CTAS_PER_SM == 3 ? 72 : 110) * 1024;   // CTAs per SM share 227 KiB
 
 // The kernel instantiation that serves a request: the four single-purpose kernels, van Hove +
 // non-Gaussian in one pass (BASELINE config 3), or the all-sums kernel (optionally with the histogram) for any other mix.
@@ -759,7 +762,7 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
     // the split with the smallest estimate (wave quantisation is the main loss for small launches).
     const long long base = (long long)a->n_origins * plan->n_chunks;
     const long long n_tiles = (plan->n_groups + kThreads - 1) / kThreads;
-    const long long slots = 2ll * sms;
+    const long long slots = (long long)MDB_BULK_CTAS_PER_SM * sms;
     long long best_tpb = n_tiles;
     double best_cost = 1e300;
     for (long long blocks = 1; blocks <= n_tiles && blocks <= 4096; ++blocks) {
