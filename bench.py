@@ -200,7 +200,9 @@ def ours_arm(a):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        # a stuck collective must fail loudly, not hang the run
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if world > 1:
@@ -312,8 +314,9 @@ def ours_arm(a):
                         'int8 image counts per coordinate triple (nojump), so moved bytes are 1.25x algorithmic'}
 
     # ---- the other kernels of the path on the same rows (kernel time only; informational) ------------
+    # (every rank takes part: with N > 1 each call ends in the all-reduce of the partial sums)
     other = {}
-    if rank == 0:
+    if True:
         engine.profile_kernels(True)
         vh_bins = np.linspace(0, 3.0, 501)
         extra = {'msd': c.msd, 'non_gaussian': c.non_gaussian, 'van_hove_self_500bins': partial(c.van_hove_self, bins=vh_bins)}
