@@ -316,28 +316,27 @@ def ours_arm(a):
     # ---- the other kernels of the path on the same rows (kernel time only; informational) ------------
     # (every rank takes part: with N > 1 each call ends in the all-reduce of the partial sums)
     other = {}
-    if True:
-        engine.profile_kernels(True)
-        vh_bins = np.linspace(0, 3.0, 501)
-        extra = {'msd': c.msd, 'non_gaussian': c.non_gaussian, 'van_hove_self_500bins': partial(c.van_hove_self, bins=vh_bins)}
-        if a.function != 'isf':
-            extra['isf'] = partial(c.isf, q=Q)
-        for name, f in extra.items():
-            ms = []
-            for _ in range(3):
-                c.shifted_correlation(f, frames, segments=a.segments, window=0.5)
-                ms.append(engine.last_kernel_ms())
-            other[name] = {'kernel_ms': float(min(ms)), 'evals_per_s': N * S * L / (min(ms) * 1e-3),
-                           'frac': alg_bytes / (min(ms) * 1e-3) / 1e9 / peak}
+    engine.profile_kernels(True)
+    vh_bins = np.linspace(0, 3.0, 501)
+    extra = {'msd': c.msd, 'non_gaussian': c.non_gaussian, 'van_hove_self_500bins': partial(c.van_hove_self, bins=vh_bins)}
+    if a.function != 'isf':
+        extra['isf'] = partial(c.isf, q=Q)
+    for name, f in extra.items():
         ms = []
         for _ in range(3):
-            c.shifted_correlation_multi({'vh': extra['van_hove_self_500bins'], 'a2': c.non_gaussian}, frames,
-                                        segments=a.segments, window=0.5)
+            c.shifted_correlation(f, frames, segments=a.segments, window=0.5)
             ms.append(engine.last_kernel_ms())
-        other['van_hove_self+non_gaussian (one pass)'] = {'kernel_ms': float(min(ms)),
-                                                          'evals_per_s': N * S * L / (min(ms) * 1e-3),
-                                                          'frac': alg_bytes / (min(ms) * 1e-3) / 1e9 / peak}
-        engine.profile_kernels(False)
+        other[name] = {'kernel_ms': float(min(ms)), 'evals_per_s': N * S * L / (min(ms) * 1e-3),
+                       'frac': alg_bytes / (min(ms) * 1e-3) / 1e9 / peak}
+    ms = []
+    for _ in range(3):
+        c.shifted_correlation_multi({'vh': extra['van_hove_self_500bins'], 'a2': c.non_gaussian}, frames,
+                                    segments=a.segments, window=0.5)
+        ms.append(engine.last_kernel_ms())
+    other['van_hove_self+non_gaussian (one pass)'] = {'kernel_ms': float(min(ms)),
+                                                      'evals_per_s': N * S * L / (min(ms) * 1e-3),
+                                                      'frac': alg_bytes / (min(ms) * 1e-3) / 1e9 / peak}
+    engine.profile_kernels(False)
 
     # ---- parity + CPU baseline on an atom sub-block (rank 0, N=1 only) ------------------------------
     cpu_baseline = None

@@ -25,11 +25,6 @@ int &last_launch_count();
 
 // ---- small device utilities ----------------------------------------------------------------
 
-// int -> double on the FP64 pipe instead of the conversion (XU) pipe: 2^52 + 2^31 + n, minus the bias.
-__device__ __forceinline__ double int_to_double(int n) {
-    return __hiloint2double(0x43300000, n ^ 0x80000000) - 4503601774854144.0;
-}
-
 // Image counts are stored excess-128 (uint8 = n + 128): byte j of a packed word becomes the double n
 // with one byte-permute and one DADD on the FP64 pipe (2^52 + b, minus 2^52 + 128) -- no sign
 // extension, no int->double conversion on the (contended) conversion pipe.
@@ -95,9 +90,12 @@ __device__ __forceinline__ float rsqrt_approx(float y) {
     return r;
 }
 
-// Two sinc evaluations at once: the same algorithm as sinc_of_square below with every float32
-// add / mul / fma issued as one packed instruction for the pair.  y is clamped at 2^-100 (a power of
-// four, so rsqrt, the Newton step and the final product are exact there): y = 0 gives exactly 1.
+// sin(sqrt(y)) / sqrt(y) for two values y >= 0 at once, float32, |error| ~1e-7 for sqrt(y) up to a
+// few 1e4:  one MUFU.RSQ + a Newton step give 1/x and x = y/x;  x is reduced by multiples of pi
+// (2-term Cody-Waite with FMA), sin on [-pi/2, pi/2] is an odd degree-11 polynomial (near-minimax,
+// 1e-10), the sign comes from the parity of the multiple.  Every float32 add / mul / fma is one
+// packed instruction for the pair.  y is clamped at 2^-100 (a power of four, so rsqrt, the Newton
+// step and the final product are exact there): y = 0 gives exactly 1.
 __device__ __forceinline__ void sinc_of_square_x2(float y0, float y1, float &r0, float &r1) {
     y0 = fmaxf(y0, 7.888609052210118e-31f);
     y1 = fmaxf(y1, 7.888609052210118e-31f);
@@ -123,32 +121,6 @@ __device__ __forceinline__ void sinc_of_square_x2(float y0, float y1, float &r0,
     sn0 = __int_as_float(__float_as_int(sn0) ^ (__float_as_int(kb0) << 31));
     sn1 = __int_as_float(__float_as_int(sn1) ^ (__float_as_int(kb1) << 31));
     unpack2(mul2(pack2(sn0, sn1), rs), r0, r1);
-}
-
-// sin(sqrt(y)) / sqrt(y) for y >= 0 in float32, |error| ~1e-7 for sqrt(y) up to a few 1e4.
-//   one MUFU.RSQ + a Newton step give 1/x and x = y/x;
-//   x is reduced by multiples of pi (2-term Cody-Waite with FMA), sin on [-pi/2, pi/2] is an odd
-//   degree-11 polynomial (near-minimax, 1e-10), the sign comes from the parity of the multiple.
-__device__ __forceinline__ float sinc_of_square(float y) {
-    float rs;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(y));   // bare MUFU.RSQ; y < 1e-30 is handled below
-    rs = rs * fmaf(-0.5f * y * rs, rs, 1.5f);
-    const float x = y * rs;
-    const float kf_biased = fmaf(x, 0.318309886183790672f, 12582912.0f);
-    const uint32_t sign = ((uint32_t)__float_as_int(kf_biased)) << 31;
-    const float kf = kf_biased - 12582912.0f;
-    float z = fmaf(-kf, 3.140625f, x);
-    z = fmaf(-kf, 9.676535846665502e-4f, z);   // pi - 3.140625 - this = 5e-12: below float32 for k < 1e4
-    const float s = z * z;
-    float p = -2.4061128200969506e-08f;
-    p = fmaf(p, s, 2.7535631943464978e-06f);
-    p = fmaf(p, s, -1.9841075118165463e-04f);
-    p = fmaf(p, s, 8.33333283662796e-03f);
-    p = fmaf(p, s, -1.666666716337204e-01f);
-    float sn = fmaf(z * s, p, z);
-    sn = __int_as_float(__float_as_int(sn) ^ sign);
-    const float v = sn * rs;
-    return (y < 1e-30f) ? 1.0f : v;
 }
 
 }  // namespace mdb
