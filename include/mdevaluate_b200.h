@@ -51,6 +51,8 @@ typedef enum mdb_status {
 #define MDB_SUM_R4   2   /* sum_i |dr_i|^4              -> non_gaussian   correlation.py:355-362 */
 #define MDB_SUM_SINC 4   /* sum_i sin(q r_i)/(q r_i)    -> isf            correlation.py:211-220 */
 #define MDB_HIST     8   /* histogram of r_i            -> van_hove_self  correlation.py:239-248 */
+#define MDB_SUM_LEGENDRE 16 /* sum_i P_l(u_i(0).u_i(t)), alone -> rotational_autocorrelation correlation.py:223-236;
+                               the rows hold vectors, the sum lands in slot 0 of `sums` */
 
 /* histogram binning rule (utils.py:328-338) */
 #define MDB_BINS_UNIFORM 0  /* bins.min()==0 and equal widths: bin = floor_divide(r, dx), r >= n_bins*dx dropped */
@@ -103,6 +105,7 @@ typedef struct mdb_corr_args {
     int64_t sel_pitch;           /* bytes per origin, >= n_atoms, multiple of 4                  */
     int32_t flags;               /* MDB_SUM_* | MDB_HIST                                         */
     double q;                    /* scattering vector length for MDB_SUM_SINC                    */
+    int32_t legendre_order;      /* l of P_l for MDB_SUM_LEGENDRE (0..32)                        */
     int32_t n_bins;              /* B, for MDB_HIST                                              */
     int32_t bin_mode;            /* MDB_BINS_UNIFORM / MDB_BINS_EDGES                            */
     double dx;                   /* uniform bin width (np.diff(bins).mean())                     */

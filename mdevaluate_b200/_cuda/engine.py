@@ -76,9 +76,10 @@ class DeviceStore:
 class CorrSpec:
     """What one correlation launch has to accumulate (built by correlation._kernel_spec)."""
 
-    def __init__(self, flags, q=0.0, n_bins=0, bin_mode=_lib.BINS_UNIFORM, dx=0.0, edges=None):
+    def __init__(self, flags, q=0.0, n_bins=0, bin_mode=_lib.BINS_UNIFORM, dx=0.0, edges=None, order=0):
         self.flags = int(flags)
         self.q = float(q)
+        self.order = int(order)
         self.n_bins = int(n_bins)
         self.bin_mode = int(bin_mode)
         self.dx = float(dx)
@@ -160,6 +161,7 @@ def correlate_device(store, rows, spec, stream=None, select=None):
         a.sel_pitch = select.stride(0)
     a.flags = spec.flags
     a.q = spec.q
+    a.legendre_order = spec.order
     a.n_bins = spec.n_bins
     a.bin_mode = spec.bin_mode
     a.dx = spec.dx

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, 'libmdevaluate_b200.so')
 
 # flags (keep in sync with include/mdevaluate_b200.h)
 F32, F64 = 0, 1
-SUM_R2, SUM_R4, SUM_SINC, HIST = 1, 2, 4, 8
+SUM_R2, SUM_R4, SUM_SINC, HIST, SUM_LEGENDRE = 1, 2, 4, 8, 16
 BINS_UNIFORM, BINS_EDGES = 0, 1
 ABI_VERSION = 1
 
@@ -36,6 +36,7 @@ class CorrArgs(C.Structure):
         ('images', C.c_void_p), ('img_pitch', C.c_int64), ('box', C.c_void_p), ('box_const', C.c_double * 3),
         ('n_atoms', C.c_int32), ('n_origins', C.c_int32), ('n_lags', C.c_int32),
         ('rows', C.c_void_p), ('select', C.c_void_p), ('sel_pitch', C.c_int64), ('flags', C.c_int32), ('q', C.c_double),
+        ('legendre_order', C.c_int32),
         ('n_bins', C.c_int32), ('bin_mode', C.c_int32), ('dx', C.c_double), ('edges', C.c_void_p),
         ('sums', C.c_void_p), ('hist', C.c_void_p),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),

@@ -28,8 +28,8 @@ from ._cuda.lib import CudaPathError  # noqa: F401  (re-exported)
 from .utils import bin_rule, runningmean  # noqa: F401
 
 __all__ = ['log_indices', 'correlation', 'subensemble_correlation', 'multi_subensemble_correlation',
-           'shifted_correlation', 'msd', 'isf', 'van_hove_self', 'non_gaussian', 'chi4',
-           'shifted_correlation_multi']
+           'shifted_correlation', 'msd', 'isf', 'van_hove_self', 'non_gaussian', 'rotational_autocorrelation',
+           'chi4', 'shifted_correlation_multi']
 
 
 # --------------------------------------------------------------------------------------------
@@ -144,15 +144,23 @@ def non_gaussian(onset, frame):
     return _pair_value(_Spec('non_gaussian'), onset, frame)
 
 
-_KNOWN = {'msd': msd, 'isf': isf, 'van_hove_self': van_hove_self, 'non_gaussian': non_gaussian}
+def rotational_autocorrelation(onset, frame, order=2):
+    """Legendre polynomial ``P_order`` of the scalar products of the vectors in ``onset`` and ``frame``,
+    averaged (correlation.py:223-236).  The frames hold vectors (e.g. unit bond vectors)."""
+    return _pair_value(_Spec('rotational_autocorrelation', order=order), onset, frame)
+
+
+_KNOWN = {'msd': msd, 'isf': isf, 'van_hove_self': van_hove_self, 'non_gaussian': non_gaussian,
+          'rotational_autocorrelation': rotational_autocorrelation}
 
 
 class _Spec:
     """A recognised correlation function with its bound parameters."""
 
-    def __init__(self, name, q=None, bins=None):
+    def __init__(self, name, q=None, bins=None, order=2):
         self.name = name
         self.q = q
+        self.order = order
         self.bins = None if bins is None else np.asarray(bins)
         if name == 'isf':
             if q is None:
@@ -162,6 +170,10 @@ class _Spec:
             self.corr = engine.CorrSpec(_lib.SUM_R2)
         elif name == 'non_gaussian':
             self.corr = engine.CorrSpec(_lib.SUM_R2 | _lib.SUM_R4)
+        elif name == 'rotational_autocorrelation':
+            if int(order) != order or not 0 <= order <= 32:
+                raise ValueError('order must be an integer in 0..32')
+            self.corr = engine.CorrSpec(_lib.SUM_LEGENDRE, order=int(order))
         elif name == 'van_hove_self':
             if bins is None:
                 raise TypeError("van_hove_self() missing required argument 'bins'")
@@ -182,7 +194,7 @@ class _Spec:
                 return (1 / n_atoms)[:, None, None] * hist
             n_atoms = n_atoms[:, None]
         with np.errstate(divide='ignore', invalid='ignore'):
-            if self.name == 'msd':
+            if self.name in ('msd', 'rotational_autocorrelation'):
                 out = sums[..., 0] / n_atoms
             elif self.name == 'isf':
                 out = sums[..., 2] / n_atoms
@@ -192,8 +204,11 @@ class _Spec:
                 out = 3 / 5 * m4 / m2 ** 2 - 1
             else:
                 return 1 / n_atoms * hist          # always float64 (correlation.py:248)
-        # the reference computes in the frames' dtype: float32 frames give float32 results
-        return out.astype(np.float32) if float32 else out
+        # the reference computes in the frames' dtype: float32 frames give float32 results (the Legendre
+        # polynomial has float64 coefficients, so rotational_autocorrelation is always float64)
+        if float32 and self.name != 'rotational_autocorrelation':
+            return out.astype(np.float32)
+        return out
 
 
 def _kernel_spec(function):
@@ -214,13 +229,16 @@ def _kernel_spec(function):
     theirs = name in _KNOWN and (module.endswith('correlation') or module.endswith('md_oracle'))
     if not (ours or theirs):
         raise NotImplementedError(
-            'shifted_correlation on the B200 path supports msd, isf, van_hove_self and non_gaussian '
+            'shifted_correlation on the B200 path supports msd, isf, van_hove_self, non_gaussian and '
+            'rotational_autocorrelation '
             '(optionally via functools.partial); got %r. There is no CPU fallback.' % (function,))
     kwargs.pop('box', None)      # isf's ``box`` argument is unused by the reference (correlation.py:211)
     if name == 'isf':
         extra = set(kwargs) - {'q'}
     elif name == 'van_hove_self':
         extra = set(kwargs) - {'bins'}
+    elif name == 'rotational_autocorrelation':
+        extra = set(kwargs) - {'order'}
     else:
         extra = set(kwargs)
     if extra:
@@ -322,6 +340,9 @@ def _run(frames, frame_ids, specs, select=None):
     flags = 0
     hist_spec = None
     q = 0.0
+    order = 0
+    if len(specs) > 1 and any(sp.name == 'rotational_autocorrelation' for sp in specs):
+        raise NotImplementedError('rotational_autocorrelation runs alone (its frames hold vectors)')
     for sp in specs:
         flags |= sp.corr.flags
         if sp.corr.flags & _lib.HIST:
@@ -330,7 +351,8 @@ def _run(frames, frame_ids, specs, select=None):
             hist_spec = sp.corr
         if sp.corr.flags & _lib.SUM_SINC:
             q = sp.corr.q
-    corr = engine.CorrSpec(flags, q=q)
+        order = max(order, sp.corr.order)
+    corr = engine.CorrSpec(flags, q=q, order=order)
     if hist_spec is not None:
         corr.n_bins, corr.bin_mode, corr.dx, corr.edges = (hist_spec.n_bins, hist_spec.bin_mode, hist_spec.dx,
                                                            hist_spec.edges)

@@ -63,6 +63,7 @@ struct CorrDev {
     long long sel_pitch;
     int n_chunks, n_ablocks;
     double q2;
+    int leg_order;
     int n_bins;
     int bin_mode;
     double dx, inv_dx;
@@ -120,7 +121,7 @@ __device__ __forceinline__ double r2_unfused(double ddx, double ddy, double ddz)
 // Accumulators of one thread for the lags of its chunk.
 template <int FLAGS>
 struct Accum {
-    static constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    static constexpr bool kR2 = (FLAGS & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) != 0;   // slot 0
     static constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     static constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     double r2[kR2 ? kLagChunk : 1];
@@ -175,6 +176,17 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
         const double ddz = u0[3 * a + 2] - ut[3 * a + 2];
         const double r2 = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
         const bool on = !MASKED || ((vmask >> a) & 1u);
+        if constexpr ((FLAGS & MDB_SUM_LEGENDRE) != 0) {
+            // rows are vectors: P_l of the scalar product (Bonnet recurrence), summed into slot 0
+            const double x = fma(u0[3 * a + 2], ut[3 * a + 2], fma(u0[3 * a + 1], ut[3 * a + 1], u0[3 * a] * ut[3 * a]));
+            double pm = 1.0, pl = (p.leg_order == 0) ? 1.0 : x;
+            for (int k = 1; k < p.leg_order; ++k) {
+                const double pn = (fma((double)(2 * k + 1) * x, pl, -(double)k * pm)) / (double)(k + 1);
+                pm = pl;
+                pl = pn;
+            }
+            sum2 += on ? pl : 0.0;
+        }
         if constexpr (kR2) sum2 += on ? r2 : 0.0;
         if constexpr (kR4) sum4 = MASKED ? sum4 + (on ? r2 * r2 : 0.0) : fma(r2, r2, sum4);
         if constexpr (kSinc) yq[a] = (float)(r2 * p.q2);
@@ -308,7 +320,7 @@ __device__ __forceinline__ void load_rows(const CorrDev &p, const CtaWork &w, in
 template <int FLAGS, typename Sync>
 __device__ __forceinline__ void cta_epilogue(const CorrDev &p, const CtaWork &w, int tid, Accum<FLAGS> &acc,
                                              double (*s_red)[kLagChunk * 3], const unsigned int *s_hist, Sync sync) {
-    constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    constexpr bool kR2 = (FLAGS & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
@@ -549,7 +561,7 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
                                              int nl,
                                              const double (*s_box)[3], double *s_acc, unsigned int *s_hist,
                                              const double *s_edges) {
-    constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    constexpr bool kR2 = (FLAGS & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
@@ -576,7 +588,7 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
 
 template <bool IMG, int FLAGS, bool BOXC>
 __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_kernel(const CorrDev p, const int n_stages) {
-    constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    constexpr bool kR2 = (FLAGS & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
@@ -703,7 +715,9 @@ constexpr size_t kSmemBudgetPerCta = (MDB_BULK_CTAS_PER_SM == 3 ? 72 : 110) * 10
 // non-Gaussian in one pass (BASELINE config 3), or the all-sums kernel (optionally with the histogram) for any other mix.
 int kernel_flags(int flags) {
     constexpr int R2 = MDB_SUM_R2, R4 = MDB_SUM_R4, SC = MDB_SUM_SINC, H = MDB_HIST;
-    if (flags == R2 || flags == SC || flags == (R2 | R4) || flags == H || flags == (R2 | R4 | H)) return flags;
+    if (flags == R2 || flags == SC || flags == (R2 | R4) || flags == H || flags == (R2 | R4 | H) ||
+        flags == MDB_SUM_LEGENDRE)
+        return flags;
     return (flags & H) ? (R2 | R4 | SC | H) : (R2 | R4 | SC);
 }
 
@@ -711,8 +725,11 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
     if (!a) return fail(MDB_ERR_ARGUMENT, "args is NULL");
     if (a->n_atoms <= 0 || a->n_origins <= 0 || a->n_lags <= 0)
         return fail(MDB_ERR_ARGUMENT, "n_atoms, n_origins and n_lags must be positive");
-    if (!(a->flags & (MDB_SUM_R2 | MDB_SUM_R4 | MDB_SUM_SINC | MDB_HIST)))
+    if (!(a->flags & (MDB_SUM_R2 | MDB_SUM_R4 | MDB_SUM_SINC | MDB_HIST | MDB_SUM_LEGENDRE)))
         return fail(MDB_ERR_ARGUMENT, "flags selects nothing to compute");
+    if ((a->flags & MDB_SUM_LEGENDRE) && (a->flags != MDB_SUM_LEGENDRE || a->images || a->legendre_order < 0 ||
+                                          a->legendre_order > 32))
+        return fail(MDB_ERR_ARGUMENT, "MDB_SUM_LEGENDRE stands alone, on raw vector rows, with 0 <= order <= 32");
     if (a->pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "pitch < 3*n_atoms");
     plan->n_groups = (a->n_atoms + 3) / 4;
     plan->n_chunks = (a->n_lags + kLagChunk - 1) / kLagChunk;
@@ -736,7 +753,8 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
     }
     const size_t stage_bytes = kCoordTileBytes + (a->images ? kImgTileBytes : 0);
     const int kf = kernel_flags(a->flags);
-    const int nv_kernel = ((kf & MDB_SUM_R2) ? 1 : 0) + ((kf & MDB_SUM_R4) ? 1 : 0) + ((kf & MDB_SUM_SINC) ? 1 : 0);
+    const int nv_kernel = ((kf & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) ? 1 : 0) + ((kf & MDB_SUM_R4) ? 1 : 0) +
+                          ((kf & MDB_SUM_SINC) ? 1 : 0);
     const size_t acc_smem = (size_t)nv_kernel * kLagChunk * kThreads * sizeof(double);
     // ring depth: what fits next to the accumulators / histogram with two CTAs per SM, 3..8 stages
     plan->stages = 0;
@@ -833,6 +851,9 @@ int launch_typed(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st)
         case R2 | R4: return launch_flags<CT, IMG, R2 | R4>(p, plan, st);
         case H: return launch_flags<CT, IMG, H>(p, plan, st);
         case R2 | R4 | H: return launch_flags<CT, IMG, R2 | R4 | H>(p, plan, st);
+        case MDB_SUM_LEGENDRE:
+            if constexpr (!IMG) return launch_flags<CT, false, MDB_SUM_LEGENDRE>(p, plan, st);
+            return fail(MDB_ERR_ARGUMENT, "MDB_SUM_LEGENDRE needs raw rows");
         case R2 | R4 | SC | H: return launch_flags<CT, IMG, R2 | R4 | SC | H>(p, plan, st);
         default: return launch_flags<CT, IMG, R2 | R4 | SC>(p, plan, st);
     }
@@ -895,6 +916,7 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     p.n_chunks = plan.n_chunks;
     p.n_ablocks = plan.n_ablocks;
     p.q2 = a->q * a->q;
+    p.leg_order = a->legendre_order;
     p.n_bins = hist ? a->n_bins : 0;
     p.bin_mode = a->bin_mode;
     p.dx = a->dx;

@@ -206,6 +206,14 @@ def isf(start, frame, q, box=None):
     return np.sinc(distance * q / np.pi).mean()
 
 
+def rotational_autocorrelation(onset, frame, order=2):
+    """mdevaluate/correlation.py:223-236."""
+    from scipy.special import legendre
+    scalar_prod = (onset * frame).sum(axis=-1)
+    poly = legendre(order)
+    return poly(scalar_prod).mean()
+
+
 def runningmean(data, nav):
     """mdevaluate/utils.py:150-161."""
     return np.convolve(data, np.ones((nav,)) / nav, mode='valid')

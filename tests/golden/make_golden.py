@@ -215,6 +215,25 @@ def main():
         gs['spatial_selector_5'] = rr
     np.savez_compressed(os.path.join(HERE, 'subensemble.npz'), **gs)
 
+    # ---- G1c: rotational autocorrelation of unit vectors (correlation.py:223-236) ---------------
+    rng = np.random.default_rng(21)
+    v = rng.standard_normal((150, 77, 3))
+    for t in range(1, 150):
+        v[t] = v[t - 1] + 0.15 * rng.standard_normal((77, 3))
+        v[t] /= np.linalg.norm(v[t], axis=1, keepdims=True)
+    v[0] /= np.linalg.norm(v[0], axis=1, keepdims=True)
+    gr = {}
+    for dt, tag in ((np.float64, 'f64'), (np.float32, 'f32')):
+        vv = v.astype(dt)
+        vc, _ = reference_coordinates(md, vv, np.ones(3, dtype=dt) * 100, np.arange(150) * 2.0)
+        gr['vec_' + tag] = vv
+        for order in (1, 2, 4):
+            t, r = corr.shifted_correlation(partial(corr.rotational_autocorrelation, order=order), vc, segments=8,
+                                            window=0.5)
+            gr['rot%d_%s' % (order, tag)] = r
+        gr['rot_t'] = t
+    np.savez_compressed(os.path.join(HERE, 'rotational.npz'), **gr)
+
     # ---- G2: BASELINE config 1 (1000 x 1000, MSD, S=100, L=70), outputs only ---------
     pos, box, times = random_walk(1000, 1000, seed=20240)
     coords, reader = reference_coordinates(md, pos, box, times)

@@ -372,3 +372,22 @@ def test_spatial_selector_and_strategy_objects(golden, md):
     np.testing.assert_allclose(vals, ref, rtol=1e-12)
     with pytest.raises(NotImplementedError):
         c.shifted_correlation(c.msd, coords, correlation=c.subensemble_correlation(lambda f: [0, 0, 1]))
+
+
+def test_rotational_autocorrelation_golden(golden, md):
+    """P_l of unit-vector scalar products (correlation.py:223-236)."""
+    g = golden('rotational')
+    c = md.correlation
+    for tag, tol in (('f64', 1e-12), ('f32', 2e-6)):
+        coords = md.Coordinates.from_arrays(g['vec_' + tag], np.ones(3) * 100, np.arange(150) * 2.0)
+        for order in (1, 2, 4):
+            t, r = c.shifted_correlation(partial(c.rotational_autocorrelation, order=order), coords, segments=8,
+                                         window=0.5)
+            ref = g['rot%d_%s' % (order, tag)]
+            assert r.dtype == ref.dtype
+            np.testing.assert_array_equal(t, g['rot_t'])
+            np.testing.assert_allclose(r, ref, rtol=tol, atol=tol)
+    a, b = g['vec_f64'][3], g['vec_f64'][40]
+    np.testing.assert_allclose(c.rotational_autocorrelation(a, b, order=2), orc.rotational_autocorrelation(a, b, 2),
+                               rtol=1e-12)
+    np.testing.assert_allclose(c.rotational_autocorrelation(a, a, order=3), 1.0, rtol=1e-12)

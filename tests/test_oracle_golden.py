@@ -179,3 +179,14 @@ def test_subensemble_golden(golden):
                 same(r, g['multi_avg_%s_%s' % (tag, name)])
                 same(cnt, g['multi_avg_%s_count' % tag])
     same(t, g['sub_t'])
+
+
+def test_rotational_autocorrelation_golden(golden):
+    g = golden('rotational')
+    for tag in ('f64', 'f32'):
+        frames = orc.ArrayTrajectory(g['vec_' + tag], np.ones(3) * 100, np.arange(150) * 2.0)
+        for order in (1, 2, 4):
+            t, r = orc.shifted_correlation(partial(orc.rotational_autocorrelation, order=order), frames, segments=8,
+                                           window=0.5)
+            same(r, g['rot%d_%s' % (order, tag)])
+        same(t, g['rot_t'])
