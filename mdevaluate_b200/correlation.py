@@ -334,6 +334,18 @@ def _schedule(frames, index_distribution, segments, window, skip):
     return start_frames, idx
 
 
+def _frame_ids(start_frames, idx, n_frames):
+    """(S, L) trajectory frame of every (origin, lag); Python index rules as in ``frames[i]``."""
+    frame_ids = start_frames[:, None] + idx[None, :]
+    if frame_ids.size:
+        if frame_ids.max() >= n_frames or frame_ids.min() < -n_frames:
+            raise IndexError('shifted_correlation: frame %d outside the trajectory (%d frames)'
+                             % (frame_ids.max() if frame_ids.max() >= n_frames else frame_ids.min(), n_frames))
+        if frame_ids.min() < 0:
+            frame_ids = np.where(frame_ids < 0, frame_ids + n_frames, frame_ids)
+    return frame_ids
+
+
 def _run(frames, frame_ids, specs, select=None):
     """Kernel launch + shard reduction; returns host ``(sums, hist, n_atoms_global, float32)``.
     ``select`` is an optional host uint8 ``(S, N)`` per-origin atom mask."""
@@ -402,10 +414,7 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
                                   'there is no CPU fallback')
     spec = _kernel_spec(function)
     start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
-    frame_ids = start_frames[:, None] + idx[None, :]
-    if frame_ids.size and frame_ids.max() >= len(frames):
-        raise IndexError('shifted_correlation: frame %d beyond the trajectory (%d frames)'
-                         % (frame_ids.max(), len(frames)))
+    frame_ids = _frame_ids(start_frames, idx, len(frames))
     times = _times(frames, idx)
     if plain:
         sums, hist, n_atoms, float32 = _run(frames, frame_ids, [spec])
@@ -477,9 +486,7 @@ def shifted_correlation_multi(functions, frames, index_distribution=log_indices,
     """
     specs = {k: _kernel_spec(f) for k, f in functions.items()}
     start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
-    frame_ids = start_frames[:, None] + idx[None, :]
-    if frame_ids.size and frame_ids.max() >= len(frames):
-        raise IndexError('shifted_correlation: frame beyond the trajectory')
+    frame_ids = _frame_ids(start_frames, idx, len(frames))
     qs = {sp.q for sp in specs.values() if sp.name == 'isf'}
     if len(qs) > 1:
         raise NotImplementedError('one q per launch')

@@ -641,9 +641,11 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
             const uint32_t stages0 = smem_u32(smem_raw);
             for (int t = 0; t < n_tiles; ++t) {
                 const long long first_float = 12ll * (g_begin + (long long)t * kThreads);
-                // the padded row end bounds the copy; both sizes stay multiples of 16 bytes
-                const uint32_t cbytes = (uint32_t)min((long long)kCoordTileBytes, (row_floats - first_float) * 4);
-                const uint32_t ibytes = IMG ? (uint32_t)min((long long)kImgTileBytes, p.img_pitch - first_float) : 0u;
+                // copy what the shard's atoms need, rounded up to the 16-byte granule of the bulk copy (rows
+                // are readable that far: pitch % 4 == 0 floats, image pitch % 16 == 0 bytes)
+                const long long left = 3ll * p.n_atoms - first_float;          // components still to come
+                const uint32_t cbytes = (uint32_t)min((long long)kCoordTileBytes, ((left + 3) / 4) * 16);
+                const uint32_t ibytes = IMG ? (uint32_t)min((long long)kImgTileBytes, ((left + 15) / 16) * 16) : 0u;
                 for (int u = 0; u < n_units; ++u) {
                     const int row = s_row[u];
                     mbar_wait(empty0 + 8 * ring.stage, ring.phase ^ 1);
