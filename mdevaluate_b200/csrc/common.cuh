@@ -123,4 +123,44 @@ __device__ __forceinline__ void sinc_of_square_x2(float y0, float y1, float &r0,
     unpack2(mul2(pack2(sn0, sn1), rs), r0, r1);
 }
 
+// ---- mbarrier + bulk-copy (TMA engine) primitives shared by the streaming kernels ------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) {
+    return (uint32_t)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive executed by the lanes with pred != 0 (predicated, no divergent branch)
+__device__ __forceinline__ void mbar_arrive_if(uint32_t bar, uint32_t pred) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.u32 P1, %1, 0;\n"
+        "@P1 mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}" ::"r"(bar),
+        "r"(pred)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy executed by the TMA engine; completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 }  // namespace mdb

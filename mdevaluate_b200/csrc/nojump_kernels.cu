@@ -10,6 +10,8 @@
 // in the dtype NumPy uses: float32 subtract, IEEE float32 divide (float64 divide when the box is
 // float64), round-half-even.  A division-free test decides the common case: |curr - prev| <
 // 0.49 * box implies |quotient| < 0.5 after rounding, i.e. a jump of 0.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mdb {
@@ -206,6 +208,128 @@ __global__ void __launch_bounds__(kThreads) nojump_scan_kernel(const NojumpDev p
     if (overflow && p.overflow) atomicExch(p.overflow, 1);
 }
 
+// The dense case again, fed by the TMA engine: a producer warp streams the CTA's column slab
+// (kThreads float4 = 4 KiB per frame row) into a ring of shared-memory stages of kRowsPerStage rows
+// with cp.async.bulk + mbarriers; the compute threads take their float4 per row from shared memory.
+// Only 3N/4 threads exist (75 k for 10^5 atoms), too few to cover HBM latency with register loads;
+// here the ring keeps kStages*kRowsPerStage*4 KiB per CTA in flight.
+constexpr int kRowsPerStage = 4;
+constexpr int kScanStages = 6;
+constexpr int kSlabBytes = kThreads * 16;
+constexpr int kScanBulkThreads = kThreads + 32;
+
+template <bool BOXF32>
+__global__ void __launch_bounds__(kScanBulkThreads, 2) nojump_scan_bulk_kernel(const NojumpDev p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];   // [kScanStages][kRowsPerStage][kSlabBytes]
+    __shared__ __align__(8) uint64_t s_full[kScanStages];
+    __shared__ __align__(8) uint64_t s_empty[kScanStages];
+    const int tid = threadIdx.x;
+    if (tid == kThreads) {
+        for (int i = 0; i < kScanStages; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], kThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
+    const long long col0 = (long long)blockIdx.x * (kThreads * 4);          // first component of the slab
+    const int n_stage_rows = (p.n_frames + kRowsPerStage - 1) / kRowsPerStage;
+
+    if (tid >= kThreads) {
+        if (tid == kThreads) {
+            const long long left = p.n_vals - col0;
+            const uint32_t bytes = (uint32_t)min((long long)kSlabBytes, ((left + 3) / 4) * 16);
+            const uint32_t stages0 = smem_u32(smem_raw);
+            uint32_t stage = 0, phase = 0;
+            for (int sr = 0; sr < n_stage_rows; ++sr) {
+                const int t0 = sr * kRowsPerStage;
+                const int nr = min(kRowsPerStage, p.n_frames - t0);
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t bar = full0 + 8 * stage;
+                mbar_expect_tx(bar, bytes * nr);
+                for (int r = 0; r < nr; ++r)
+                    bulk_g2s(stages0 + (stage * kRowsPerStage + r) * kSlabBytes,
+                             p.coords + (long long)(t0 + r) * p.pitch + col0, bytes, bar);
+                if (++stage == kScanStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    const int e0 = (int)col0 + 4 * tid;
+    const bool live = e0 < p.n_vals;
+    const int nv = live ? min(4, p.n_vals - e0) : 0;
+    float safe[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int d = (e0 + j) % 3;
+        safe[j] = 0.49f * fabsf(BOXF32 ? p.boxf[d] : (float)p.boxd[d]);
+    }
+    float prev[4];
+    int cum[4];
+    bool overflow = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        prev[j] = 0.f;
+        cum[j] = 0;
+        if (j < nv) {
+            if (p.first_segment) {
+                prev[j] = p.whole0 ? p.whole0[e0 + j] : p.coords[e0 + j];
+            } else {
+                prev[j] = p.prev[e0 + j];
+                cum[j] = p.cum[e0 + j];
+            }
+        }
+    }
+    uint32_t packed = pack4(cum[0] + MDB_IMAGE_BIAS, cum[1] + MDB_IMAGE_BIAS, cum[2] + MDB_IMAGE_BIAS,
+                            cum[3] + MDB_IMAGE_BIAS);
+    uint8_t *dst = p.images + e0;
+    uint32_t stage = 0, phase = 0;
+    for (int sr = 0; sr < n_stage_rows; ++sr) {
+        const int t0 = sr * kRowsPerStage;
+        mbar_wait(full0 + 8 * stage, phase);
+        float4 rows[kRowsPerStage];
+#pragma unroll
+        for (int r = 0; r < kRowsPerStage; ++r)
+            rows[r] = reinterpret_cast<const float4 *>(smem_raw + (size_t)(stage * kRowsPerStage + r) * kSlabBytes)[tid];
+        mbar_arrive_if(empty0 + 8 * stage, (tid & 31) == 0);
+        if (++stage == kScanStages) { stage = 0; phase ^= 1; }
+#pragma unroll
+        for (int r = 0; r < kRowsPerStage; ++r) {
+            if (t0 + r < p.n_frames && live) {
+                const float cur[4] = {rows[r].x, rows[r].y, rows[r].z, rows[r].w};
+                float diff[4];
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    diff[j] = __fsub_rn(cur[j], prev[j]);
+                    any |= !(fabsf(diff[j]) < safe[j]);
+                    prev[j] = cur[j];
+                }
+                if (any) {
+                    const int4 jv = slow_jumps<BOXF32>(diff[0], diff[1], diff[2], diff[3], e0, p.boxf[0], p.boxf[1],
+                                                       p.boxf[2], p.boxd[0], p.boxd[1], p.boxd[2]);
+                    const int jmp[4] = {jv.x, jv.y, jv.z, jv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < nv) cum[j] += jmp[j];
+                        overflow |= (cum[j] > 127 || cum[j] < -128);
+                    }
+                    packed = pack4(cum[0] + MDB_IMAGE_BIAS, cum[1] + MDB_IMAGE_BIAS, cum[2] + MDB_IMAGE_BIAS,
+                                   cum[3] + MDB_IMAGE_BIAS);
+                }
+                *reinterpret_cast<uint32_t *>(dst + (long long)(t0 + r) * p.img_pitch) = packed;
+            }
+        }
+    }
+    for (int j = 0; j < nv; ++j) {
+        p.prev[e0 + j] = prev[j];
+        p.cum[e0 + j] = cum[j];
+    }
+    if (overflow && p.overflow) atomicExch(p.overflow, 1);
+}
+
 __global__ void nojump_apply_kernel(const float *__restrict__ x, const uint8_t *__restrict__ n, double b0, double b1,
                                     double b2, int n_vals, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,6 +387,23 @@ extern "C" int mdb_nojump_scan(const mdb_nojump_args *a, void *stream) {
     const int n_threads = (p.n_vals + 3) / 4;
     const unsigned blocks = (unsigned)((n_threads + kThreads - 1) / kThreads);
     const bool plain = vec && a->images && !a->out_row && !a->jumps && !a->coords_out;
+    // the bulk-copy variant needs enough frames to fill its ring and is the default for the dense case
+    const bool bulk = plain && a->n_frames >= 64 && getenv("MDB_SCAN_LDG") == nullptr;
+    if (bulk) {
+        const unsigned bblocks = (unsigned)((p.n_vals + kThreads * 4 - 1) / (kThreads * 4));
+        const size_t smem = (size_t)kScanStages * kRowsPerStage * kSlabBytes;
+        if (a->box_is_f32) {
+            MDB_CUDA_CHECK(cudaFuncSetAttribute(nojump_scan_bulk_kernel<true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nojump_scan_bulk_kernel<true><<<bblocks, kScanBulkThreads, smem, st>>>(p);
+        } else {
+            MDB_CUDA_CHECK(cudaFuncSetAttribute(nojump_scan_bulk_kernel<false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nojump_scan_bulk_kernel<false><<<bblocks, kScanBulkThreads, smem, st>>>(p);
+        }
+        MDB_CUDA_CHECK(cudaGetLastError());
+        return MDB_OK;
+    }
     if (a->box_is_f32) {
         if (plain) nojump_scan_kernel<true, true, true><<<blocks, kThreads, 0, st>>>(p);
         else if (vec) nojump_scan_kernel<true, true, false><<<blocks, kThreads, 0, st>>>(p);
