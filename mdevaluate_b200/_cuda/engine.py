@@ -120,7 +120,7 @@ def correlate_device(store, rows, spec, stream=None, select=None):
     rows = np.ascontiguousarray(rows, dtype=np.int32)
     S, L = rows.shape
     dev = store.device
-    key = ('rows', rows.shape, hash(rows.data.tobytes()) if rows.size < 4096 else hash(rows.tobytes()))
+    key = ('rows', rows.shape, rows.tobytes())       # the bytes themselves: no hash-collision risk
     rows_dev = store._cache.get(key)
     if rows_dev is None:
         rows_dev = torch.from_numpy(rows).to(dev)
@@ -132,7 +132,7 @@ def correlate_device(store, rows, spec, stream=None, select=None):
     hist = torch.empty((S, L, spec.n_bins), dtype=torch.int64, device=dev) if want_hist else None
     edges_dev = None
     if want_hist and spec.bin_mode == _lib.BINS_EDGES:
-        ekey = ('edges', hash(spec.edges.tobytes()))
+        ekey = ('edges', spec.edges.tobytes())
         edges_dev = store._cache.get(ekey)
         if edges_dev is None:
             edges_dev = torch.from_numpy(spec.edges).to(dev)

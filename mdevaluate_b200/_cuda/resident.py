@@ -284,7 +284,7 @@ class Resident:
                 extra += self.pitch * self.n_frames
             if extra <= _mem_budget(torch, self.device):
                 return self._ensure_dense_images() if nojump else self._ensure_dense()
-        key = ('nojump' if nojump else 'raw', hash(frame_ids.tobytes()))
+        key = ('nojump' if nojump else 'raw', frame_ids.tobytes())
         store = self._compact.get(key)
         if store is None:
             logger.debug('building compact store of %d frames (nojump=%s)', len(frame_ids), nojump)

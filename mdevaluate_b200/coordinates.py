@@ -164,7 +164,7 @@ class Coordinates:
             return res
         from ._cuda.resident import Resident
         cache = self.frames.__dict__.setdefault('_mdb_resident', {}) if hasattr(self.frames, '__dict__') else {}
-        key = hash(np.asarray(self.atom_filter).tobytes()) if self.atom_filter is not None else None
+        key = np.asarray(self.atom_filter).tobytes() if self.atom_filter is not None else None
         res = cache.get(key)
         if res is None:
             res = Resident(self.frames, self.atom_filter)
