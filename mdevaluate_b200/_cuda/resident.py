@@ -188,6 +188,13 @@ class Resident:
         overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
         box0 = self._box_of(0)
         box_is_f32 = box0.dtype == np.float32
+        whole0 = None
+        ref0 = getattr(self.reader, 'whole0', None)
+        if ref0 is not None:      # frame0.whole of the selected atoms (reader.py:166)
+            ref0 = ref0 if self.atom_filter is None else ref0[self.atom_filter]
+            if ref0.shape != (self.n_atoms, 3):
+                raise ValueError('whole0 must have shape (M, 3)')
+            whole0 = torch.from_numpy(np.ascontiguousarray(ref0.reshape(-1))).to(self.device)
         dense = self._dense
         if dense is not None and dense.coords.dtype == torch.float32:
             source = ((0, self.n_frames, dense.coords),)
@@ -203,7 +210,7 @@ class Resident:
                 jmp_seg = jumps[t0:t1] if jumps is not None else None
             engine.nojump_scan(seg, self.n_atoms, box0, box_is_f32, prev, cum, first_segment=(t0 == 0),
                                images=img_seg, jumps=jmp_seg, out_row=rows, coords_out=coords_out,
-                               overflow=overflow)
+                               overflow=overflow, whole0=whole0)
         if int(overflow.item()):
             raise _lib.CudaPathError('an atom crossed more than 127 periodic images; int8 image counts overflow')
 

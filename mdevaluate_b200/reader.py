@@ -58,11 +58,15 @@ class MemoryReader:
             float32 holding ``3*M`` interleaved xyz values per row (then pass ``n_atoms``).
         box: box diagonal ``(3,)``, matrix ``(3,3)``, or per frame ``(T,3)`` / ``(T,3,3)``.
         times: ``(T,)`` frame times; default ``arange(T)``.
+        whole0: optional ``(M, 3)`` positions of frame 0 with molecules made whole (the reference's
+            ``trajectory[0].whole``, reader.py:166): the jumps of frame 0 are taken against it.  Default:
+            frame 0 itself, which is what ``whole`` returns for single-atom residues.
     """
 
-    def __init__(self, positions, box, times=None, n_atoms=None, filename='<memory>'):
+    def __init__(self, positions, box, times=None, n_atoms=None, filename='<memory>', whole0=None):
         self.filename = filename
         self._nojump_matrixes = None
+        self.whole0 = None if whole0 is None else np.ascontiguousarray(whole0, dtype=np.float32)
         self.device_block = None
         self.host_block = None
         if isinstance(positions, np.ndarray):

@@ -391,3 +391,24 @@ def test_rotational_autocorrelation_golden(golden, md):
     np.testing.assert_allclose(c.rotational_autocorrelation(a, b, order=2), orc.rotational_autocorrelation(a, b, 2),
                                rtol=1e-12)
     np.testing.assert_allclose(c.rotational_autocorrelation(a, a, order=3), 1.0, rtol=1e-12)
+
+
+def test_whole0_reference_frame(md):
+    """Row 0 of the jump table is taken against frame0.whole (reader.py:166): molecules that were
+    wrapped apart in frame 0 start with a non-zero image count."""
+    from mdevaluate_b200.synthetic import random_walk
+    pos, box, times = random_walk(57, 80, seed=2, sigma=0.1, box=2.0)
+    whole0 = pos[0].copy()
+    whole0[::5, 0] += box[0]            # these atoms sit one box further in the whole molecule
+    whole0[3::7, 2] -= box[2]
+    unw = orc.UnwrappedTrajectory(pos, box, times, whole0=whole0)
+    coords = md.Coordinates(md.MemoryReader(pos, box, times, whole0=whole0))
+    store = coords._resident().store_for(np.arange(80), nojump=True)
+    images = store.images[:, :3 * 57].cpu().numpy().astype(np.int64).reshape(80, 57, 3) - 128
+    np.testing.assert_array_equal(images, unw.counts)
+    assert np.count_nonzero(images[0]) > 0
+    np.testing.assert_array_equal(np.asarray(coords.nojump[33]), np.asarray(unw[33]))
+    c = md.correlation
+    _, ref = orc.shifted_correlation(orc.msd, unw, segments=4)
+    _, r = c.shifted_correlation(c.msd, coords.nojump, segments=4)
+    close(r, ref, rtol=1e-11, atol=1e-13)
