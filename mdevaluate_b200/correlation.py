@@ -334,6 +334,17 @@ def _schedule(frames, index_distribution, segments, window, skip):
     return start_frames, idx
 
 
+def _global_counts(frames, counts):
+    """Sub-ensemble sizes: summed over the shards of an atom-sharded trajectory (every rank runs the
+    selector on its own atoms)."""
+    comm = getattr(frames, 'comm', None)
+    if comm is None:
+        return counts
+    from . import parallel
+    torch = _lib.require_cuda()
+    return parallel.allreduce_counts(counts, comm, torch.device('cuda', torch.cuda.current_device()))
+
+
 def _frame_ids(start_frames, idx, n_frames):
     """(S, L) trajectory frame of every (origin, lag); Python index rules as in ``frames[i]``."""
     frame_ids = start_frames[:, None] + idx[None, :]
@@ -371,8 +382,6 @@ def _run(frames, frame_ids, specs, select=None):
     store, rows, n_atoms, float32, comm = _provider(frames, frame_ids)
     select_dev = None
     if select is not None:
-        if comm is not None:
-            raise NotImplementedError('sub-ensemble correlation of an atom-sharded trajectory is not implemented yet')
         torch = _lib.require_cuda()
         padded = np.zeros((select.shape[0], (select.shape[1] + 3) // 4 * 4), dtype=np.uint8)
         padded[:, :select.shape[1]] = select
@@ -427,7 +436,7 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
     if strategy[0] == 'sub':
         picked = [_selector_mask(strategy[1](o), n_all) for o in origins]
         masks = np.stack([m for m, _ in picked])
-        counts = np.array([c for _, c in picked])
+        counts = _global_counts(frames, np.array([c for _, c in picked]))
         sums, hist, _, float32 = _run(frames, frame_ids, [spec], select=masks)
         values = spec.finalize(sums, hist, counts, float32)
         return times, _average(values, len(start_frames), average)
@@ -443,6 +452,7 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
         per_origin.append([_selector_mask(selectors[index], n_all) for index in np.ndindex(sel_shape)])
     n_sub = len(per_origin[0])
     counts = np.array([[c for _, c in row] for row in per_origin]).reshape((len(origins),) + sel_shape)
+    counts = _global_counts(frames, counts)
     values = None
     for k, index in enumerate(np.ndindex(sel_shape)):
         masks = np.stack([row[k][0] for row in per_origin])

@@ -58,6 +58,16 @@ def unpack_partials(buf, sums_shape, hist_shape):
     return sums, hist
 
 
+def allreduce_counts(counts, comm, device):
+    """Sub-ensemble sizes per origin (host int array of any shape) summed over the shards."""
+    import torch
+    import torch.distributed as dist
+    group, _ = comm
+    t = torch.from_numpy(np.ascontiguousarray(counts, dtype=np.int64)).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().reshape(np.shape(counts))
+
+
 def allreduce_partials(sums, hist, n_atoms_local, comm):
     """Sum the per-shard partials over the group: ONE collective per correlation call."""
     import torch.distributed as dist

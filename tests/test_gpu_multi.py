@@ -36,6 +36,18 @@ for name, fn in (('msd', c.msd), ('isf', partial(c.isf, q=22.7)), ('vh', partial
     out[name] = r
 t, x4 = c.chi4(shard.nojump, 22.7)
 out['chi4'] = x4
+L = float(box[0])
+def slab(frame):
+    z = np.asarray(frame)[:, 2] %% L
+    return np.where(z < 0.4 * L)[0]
+def slabs(frame):
+    z = np.asarray(frame)[:, 2] %% L
+    return np.array([z < 0.3 * L, (z >= 0.3 * L) & (z < 0.7 * L), z >= 0.7 * L])
+t, out['sub'] = c.shifted_correlation(c.msd, shard.nojump, segments=9, window=0.4,
+                                      correlation=c.subensemble_correlation(slab))
+t, out['multi'], out['multi_n'] = c.shifted_correlation(partial(c.isf, q=22.7), shard.nojump, segments=9, window=0.4,
+                                                        average=True,
+                                                        correlation=c.multi_subensemble_correlation(slabs))
 if rank == 0:
     full = md.Coordinates.from_arrays(pos, box, times)
     for name, fn in (('msd', c.msd), ('isf', partial(c.isf, q=22.7)), ('vh', partial(c.van_hove_self, bins=bins))):
@@ -46,6 +58,11 @@ if rank == 0:
             assert np.allclose(out[name], r, rtol=1e-12, atol=1e-14), name
     t, x4 = c.chi4(full.nojump, 22.7)
     assert np.allclose(out['chi4'], x4, rtol=1e-9, atol=1e-12)
+    t, r = c.shifted_correlation(c.msd, full.nojump, segments=9, window=0.4, correlation=c.subensemble_correlation(slab))
+    assert np.allclose(out['sub'], r, rtol=1e-12, atol=1e-14)
+    t, r, n = c.shifted_correlation(partial(c.isf, q=22.7), full.nojump, segments=9, window=0.4, average=True,
+                                    correlation=c.multi_subensemble_correlation(slabs))
+    assert np.array_equal(out['multi_n'], n) and np.allclose(out['multi'], r, rtol=1e-9, atol=1e-12)
     print('MULTI_GPU_OK')
 dist.destroy_process_group()
 '''
