@@ -298,6 +298,7 @@ def _times(frames, idx):
 
 
 _schedule_cache = {}
+MAX_PAIRS_PER_LAUNCH = 1 << 22      # (origin, lag) pairs per kernel launch; more are batched by origin
 
 
 def _schedule(frames, index_distribution, segments, window, skip):
@@ -426,9 +427,24 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
     frame_ids = _frame_ids(start_frames, idx, len(frames))
     times = _times(frames, idx)
     if plain:
-        sums, hist, n_atoms, float32 = _run(frames, frame_ids, [spec])
-        values = spec.finalize(sums, hist, n_atoms, float32)
-        return times, _average(values, len(start_frames), average)
+        n_origins = len(start_frames)
+        batch = max(1, MAX_PAIRS_PER_LAUNCH // max(1, len(idx)))
+        if batch >= n_origins:
+            sums, hist, n_atoms, float32 = _run(frames, frame_ids, [spec])
+            values = spec.finalize(sums, hist, n_atoms, float32)
+            return times, _average(values, n_origins, average)
+        # very many (origin, lag) pairs (dense schedules): origins go through in batches so that the
+        # per-pair device buffers stay bounded; the average is accumulated origin by origin as above
+        acc = 0 if average else []
+        for s0 in range(0, n_origins, batch):
+            sums, hist, n_atoms, float32 = _run(frames, frame_ids[s0:s0 + batch], [spec])
+            values = spec.finalize(sums, hist, n_atoms, float32)
+            if average:
+                for row in values:
+                    acc = acc + row
+            else:
+                acc.append(values)
+        return times, (acc / n_origins if average else np.concatenate(acc, axis=0))
 
     # ---- sub-ensembles: the selector sees every origin frame on the host, the kernel gets masks ----
     origins = [frames[int(i)] for i in frame_ids[:, 0]]

@@ -412,3 +412,22 @@ def test_whole0_reference_frame(md):
     _, ref = orc.shifted_correlation(orc.msd, unw, segments=4)
     _, r = c.shifted_correlation(c.msd, coords.nojump, segments=4)
     close(r, ref, rtol=1e-11, atol=1e-13)
+
+
+def test_origin_batching_for_dense_schedules(small, md, monkeypatch):
+    """Dense schedules have S*L pairs far beyond one launch's buffers: origins are batched."""
+    g, coords = small
+    c = md.correlation
+    dense = lambda a, b: np.arange(a, b)
+    kw = dict(segments=60, window=0.3, index_distribution=dense)
+    t0, full = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, **kw)
+    t0, full_avg = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, average=True, **kw)
+    monkeypatch.setattr(c, 'MAX_PAIRS_PER_LAUNCH', 7 * full.shape[1])          # 7 origins per launch
+    t1, batched = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, **kw)
+    t1, batched_avg = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, average=True, **kw)
+    np.testing.assert_array_equal(batched, full)
+    np.testing.assert_array_equal(batched_avg, full_avg)
+    unw = orc.UnwrappedTrajectory(g['pos'], g['box'], g['times'])
+    _, ref = orc.shifted_correlation(partial(orc.isf, q=22.7), unw, segments=60, window=0.3, average=True,
+                                     index_distribution=orc.lin_indices)
+    close(batched_avg, ref)
