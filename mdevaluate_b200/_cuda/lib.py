@@ -71,9 +71,8 @@ def _declare(lib):
     lib.mdb_nojump_apply.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_void_p,
                                      C.c_void_p]
     for name in EXPORTS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ('mdb_abi_version', 'mdb_corr_last_launches'):
-            fn.restype = C.c_int
+        if name != 'mdb_last_error':
+            getattr(lib, name).restype = C.c_int        # every other entry point returns an int status / count
 
 
 def load(build_if_missing=True):
