@@ -95,7 +95,9 @@ __device__ __forceinline__ float rsqrt_approx(float y) {
 // (2-term Cody-Waite with FMA), sin on [-pi/2, pi/2] is an odd degree-11 polynomial (near-minimax,
 // 1e-10), the sign comes from the parity of the multiple.  Every float32 add / mul / fma is one
 // packed instruction for the pair.  y is clamped at 2^-100 (a power of four, so rsqrt, the Newton
-// step and the final product are exact there): y = 0 gives exactly 1.
+// step and the final product are exact there): y = 0 gives exactly 1.  Valid for sqrt(y) = q*r < 2^22*pi
+// (1.3e7 rad; beyond that the nearest-multiple trick runs out of mantissa) -- MD displacements times any
+// physical q stay orders of magnitude below.
 __device__ __forceinline__ void sinc_of_square_x2(float y0, float y1, float &r0, float &r1) {
     y0 = fmaxf(y0, 7.888609052210118e-31f);
     y1 = fmaxf(y1, 7.888609052210118e-31f);
