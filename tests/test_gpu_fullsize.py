@@ -131,3 +131,56 @@ def test_segmented_scan_equals_one_shot(big):
                        store.images.index_select(0, idx))
     assert torch.equal(compact.coords[torch.from_numpy(rows.astype(np.int64)).to(block.device), :3 * N],
                        block.index_select(0, idx)[:, :3 * N])
+
+
+def test_config3_van_hove_and_alpha2_full_size():
+    """BASELINE config 3: van Hove (500 bins) + non-Gaussian parameter in ONE pass, 500 000 atoms x
+    10 000 frames (60 GB of frames + 15 GB of image counts in HBM), S=10, L=82."""
+    import torch
+    import mdevaluate_b200 as md
+    from mdevaluate_b200._cuda import engine
+    from mdevaluate_b200.synthetic import random_walk_device, box_length
+    free, _ = torch.cuda.mem_get_info()
+    if free < 110e9:
+        pytest.skip('needs ~90 GB of free HBM')
+    n, t_frames = 500000, 10000
+    block, box, times = random_walk_device(n, t_frames, seed=3, box=box_length(n), pitch=engine.row_pitch(n),
+                                           frame_block=128)
+    coords = md.Coordinates.from_arrays(block, box, times, n_atoms=n)
+    c = md.correlation
+    bins = np.linspace(0, 8.0, 501)       # 11 sigma of the longest lag: nobody falls outside
+    t, out = c.shifted_correlation_multi({'vh': partial(c.van_hove_self, bins=bins), 'a2': c.non_gaussian},
+                                         coords.nojump, segments=10)
+    vh, a2 = out['vh'], out['a2']
+    assert vh.shape == (10, 82, 500) and a2.shape == (10, 82)
+    counts = np.rint(vh * n).astype(np.int64)
+    np.testing.assert_allclose(counts / n, vh, rtol=0, atol=1e-15)            # integer counts / N
+    assert (counts.sum(axis=-1) == n).all()                                   # every atom lands in a bin
+    assert (counts[:, 0, 0] == n).all()                                       # lag 0: all in the first bin
+    assert np.isnan(a2[:, 0]).all() and np.abs(a2[:, 1:]).max() < 0.01        # Gaussian walk: alpha_2 = 0
+    # the separate kernels give the same numbers as the fused pass
+    _, vh_alone = c.shifted_correlation(partial(c.van_hove_self, bins=bins), coords.nojump, segments=10)
+    np.testing.assert_array_equal(vh_alone, vh)
+    with np.errstate(all='ignore'):
+        _, a2_alone = c.shifted_correlation(c.non_gaussian, coords.nojump, segments=10)
+    np.testing.assert_array_equal(a2_alone, a2)
+    # oracle on an atom sub-block of the same trajectory: counts exact, alpha_2 to 1e-10
+    n_sub = 128
+    sub = block[:, :3 * n_sub].cpu().numpy().reshape(t_frames, n_sub, 3)
+    unw = orc.UnwrappedTrajectory(sub, box, times)
+    store = coords._resident().store_for(np.arange(t_frames), nojump=True)
+    sub_store = engine.DeviceStore(store.coords, n_sub, images=store.images, box=store.box, box_const=store.box_const)
+    starts, idx = c._schedule(coords, c.log_indices, 10, 0.5, None)
+    rows = (starts[:, None] + idx[None, :]).astype(np.int32)
+    spec_vh = c._kernel_spec(partial(c.van_hove_self, bins=bins))
+    corr = engine.CorrSpec(1 | 2 | 8, n_bins=500, bin_mode=spec_vh.corr.bin_mode, dx=spec_vh.corr.dx)
+    sums, hist = engine.correlate_device(sub_store, rows, corr)
+    got_vh = spec_vh.finalize(None, hist.cpu().numpy(), n_sub, False)
+    got_a2 = c._Spec('non_gaussian').finalize(sums.cpu().numpy(), None, n_sub, False)
+    with np.errstate(all='ignore'):
+        _, ref_vh = orc.shifted_correlation(partial(orc.van_hove_self, bins=bins), unw, segments=10)
+        _, ref_a2 = orc.shifted_correlation(orc.non_gaussian, unw, segments=10)
+    np.testing.assert_array_equal(got_vh, ref_vh)
+    np.testing.assert_allclose(got_a2[:, 1:], ref_a2[:, 1:], rtol=1e-10, atol=1e-12)
+    del coords, block, store, sub_store
+    torch.cuda.empty_cache()
