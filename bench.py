@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument('--atoms', type=int, default=100000, help='atoms per GPU')
     ap.add_argument('--frames', type=int, default=10000)
     ap.add_argument('--segments', type=int, default=100)
+    ap.add_argument('--window', type=float, default=0.5)
+    ap.add_argument('--skip', type=float, default=None)
     ap.add_argument('--cpu-atoms', type=int, default=16384, help='atom sub-block timed on the CPU')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-e2e', action='store_true')
@@ -58,8 +60,8 @@ def parse_args():
 
 
 def workload_name(a, world):
-    return ('config2: %s q=%.1f, %d atoms/GPU x %d frames, nojump, segments=%d, window=0.5, log lags'
-            % (a.function.upper(), Q, a.atoms, a.frames, a.segments))
+    return ('config2: %s q=%.1f, %d atoms/GPU x %d frames, nojump, segments=%d, window=%g, skip=%s, log lags'
+            % (a.function.upper(), Q, a.atoms, a.frames, a.segments, a.window, a.skip))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -129,14 +131,14 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------
 # CPU port of the reference (the checker / baseline)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(pos, box, times, segments, function):
+def cpu_reference_step(pos, box, times, segments, function, window=0.5, skip=None):
     """One full reference-style evaluation on host arrays: parse_jumps + nojump + shifted_correlation."""
     from oracle import md_oracle as orc
     fn = partial(orc.isf, q=Q) if function == 'isf' else orc.msd
     t0 = time.perf_counter()
     unw = orc.UnwrappedTrajectory(pos, box, times)
     t1 = time.perf_counter()
-    t, r = orc.shifted_correlation(fn, unw, segments=segments, window=0.5)
+    t, r = orc.shifted_correlation(fn, unw, segments=segments, window=window, skip=skip)
     t2 = time.perf_counter()
     return r, t1 - t0, t2 - t1
 
@@ -147,7 +149,7 @@ def reference_arm(a):
         return
     from mdevaluate_b200.synthetic import random_walk, box_length
     from oracle import md_oracle as orc
-    starts, num = orc.schedule(a.frames, a.segments, 0.5, 0)
+    starts, num = orc.schedule(a.frames, a.segments, a.window, a.skip or 0)
     S, L = len(starts), len(orc.log_indices(0, num))
     # bounded sample: aim at ~120 s for the whole run at ~1.5e7 evals/s on one core
     budget = 120.0 / max(1, a.steps + a.warmup)
@@ -156,11 +158,11 @@ def reference_arm(a):
     pos, box, times = random_walk(n, a.frames, seed=20240, box=box_length(a.atoms))
     evals = n * S * L
     for _ in range(a.warmup):
-        cpu_reference_step(pos, box, times, a.segments, a.function)
+        cpu_reference_step(pos, box, times, a.segments, a.function, a.window, a.skip)
     t0 = time.perf_counter()
     scan_s = corr_s = 0.0
     for _ in range(a.steps):
-        _, ts, tc = cpu_reference_step(pos, box, times, a.segments, a.function)
+        _, ts, tc = cpu_reference_step(pos, box, times, a.segments, a.function, a.window, a.skip)
         scan_s += ts
         corr_s += tc
     wall = time.perf_counter() - t0
@@ -256,11 +258,11 @@ def ours_arm(a):
                            'includes the host-side overflow check (one small D2H)'}
 
     frames = coords.nojump
-    t_axis, res = c.shifted_correlation(fn, frames, segments=a.segments, window=0.5)
+    t_axis, res = c.shifted_correlation(fn, frames, segments=a.segments, window=a.window, skip=a.skip)
     S, L = res.shape
     evals_step = N * world * S * L
     for _ in range(a.warmup):
-        c.shifted_correlation(fn, frames, segments=a.segments, window=0.5)
+        c.shifted_correlation(fn, frames, segments=a.segments, window=a.window, skip=a.skip)
 
     if a.pyprofile and rank == 0:
         import cProfile
@@ -268,7 +270,7 @@ def ours_arm(a):
         prof = cProfile.Profile()
         prof.enable()
         for _ in range(20):
-            c.shifted_correlation(fn, frames, segments=a.segments, window=0.5)
+            c.shifted_correlation(fn, frames, segments=a.segments, window=a.window, skip=a.skip)
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(25)
 
@@ -284,7 +286,7 @@ def ours_arm(a):
     w0 = time.time()
     ev[0].record()
     for _ in range(a.steps):
-        t_axis, res = c.shifted_correlation(fn, frames, segments=a.segments, window=0.5)
+        t_axis, res = c.shifted_correlation(fn, frames, segments=a.segments, window=a.window, skip=a.skip)
         kernel_ms.append(engine.last_kernel_ms())
     ev[1].record()
     barrier()
@@ -324,14 +326,14 @@ def ours_arm(a):
     for name, f in extra.items():
         ms = []
         for _ in range(3):
-            c.shifted_correlation(f, frames, segments=a.segments, window=0.5)
+            c.shifted_correlation(f, frames, segments=a.segments, window=a.window, skip=a.skip)
             ms.append(engine.last_kernel_ms())
         other[name] = {'kernel_ms': float(min(ms)), 'evals_per_s': N * S * L / (min(ms) * 1e-3),
                        'frac': alg_bytes / (min(ms) * 1e-3) / 1e9 / peak}
     ms = []
     for _ in range(3):
         c.shifted_correlation_multi({'vh': extra['van_hove_self_500bins'], 'a2': c.non_gaussian}, frames,
-                                    segments=a.segments, window=0.5)
+                                    segments=a.segments, window=a.window, skip=a.skip)
         ms.append(engine.last_kernel_ms())
     other['van_hove_self+non_gaussian (one pass)'] = {'kernel_ms': float(min(ms)),
                                                       'evals_per_s': N * S * L / (min(ms) * 1e-3),
@@ -344,10 +346,10 @@ def ours_arm(a):
     if rank == 0 and world == 1 and not a.no_cpu:
         n_sub = min(a.cpu_atoms, N)
         sub = block[:, :3 * n_sub].cpu().numpy().reshape(T, n_sub, 3)
-        ref, scan_s, corr_s = cpu_reference_step(sub, box, times, a.segments, a.function)
+        ref, scan_s, corr_s = cpu_reference_step(sub, box, times, a.segments, a.function, a.window, a.skip)
         sub_store = engine.DeviceStore(store.coords, n_sub, images=store.images, box=store.box,
                                        box_const=store.box_const)
-        starts, idx = c._schedule(frames, c.log_indices, a.segments, 0.5, None)
+        starts, idx = c._schedule(frames, c.log_indices, a.segments, a.window, a.skip)
         rows = (starts[:, None] + idx[None, :]).astype(np.int32)
         spec = c._kernel_spec(fn)
         sums, _ = engine.correlate_device(sub_store, rows, spec.corr)
@@ -379,7 +381,7 @@ def ours_arm(a):
         def e2e_step():
             hc = make_coords(host_np)
             hc._resident().force_compact = True
-            return c.shifted_correlation(fn, hc.nojump, segments=a.segments, window=0.5)
+            return c.shifted_correlation(fn, hc.nojump, segments=a.segments, window=a.window, skip=a.skip)
 
         e2e_step()
         barrier()
