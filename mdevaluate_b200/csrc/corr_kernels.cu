@@ -249,7 +249,9 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
                     const float dist = t - tr;
                     const float margin = fmaf(t, 8.0e-7f, 1.0e-6f);   // 2x the float32 error bound (3.9e-7 t)
                     bin = (__float_as_int(tb) - 0x4B400000) - (dist < 0.0f ? 1 : 0);
-                    fast = (fabsf(dist) > margin) && (t < 4.0e6f);
+                    // t >= 2^22 needs no test: the trick then yields some bin >= 2^22 - 1 > n_bins (dropped,
+                    // as the true bin would be); NaN (r = 0) fails the comparison and goes the exact way
+                    fast = fabsf(dist) > margin;
                 }
                 slow[a] = live && !fast;
                 any_slow |= slow[a];
