@@ -161,6 +161,39 @@ int mdb_nojump_scan(const mdb_nojump_args *args, void *stream);
 int mdb_nojump_apply(const float *coords_row, const uint8_t *images_row, const double box[3],
                      int32_t n_atoms, double *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense schedules: every origin of an arithmetic progression against a contiguous range of lags,
+ * averaged over the origins (BASELINE config 5: `index_distribution = lambda a, b: np.arange(a, b)`,
+ * `average=True`).  Pair (s, l) correlates frame  first_origin + s*origin_step  with the frame
+ * `first_lag + l` later.  Blocks of origins x lags are evaluated from frame rows held in shared
+ * memory (unwrapped once per row, reused by every pair of the block), so the kernel is bound by
+ * arithmetic instead of HBM.  Output `sums[l*2 + {0,1}]` = sum over origins and atoms of r^2 and
+ * sinc(q r) (the caller divides by n_origins * N).  Supported flags: MDB_SUM_R2 | MDB_SUM_SINC.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mdb_dense_args {
+    const float *coords;         /* DEVICE [n_rows][pitch] float32                              */
+    int64_t pitch;
+    const uint8_t *images;       /* DEVICE excess-128 image counts or NULL (raw)                */
+    int64_t img_pitch;
+    const double *box;           /* DEVICE [n_rows][3] or NULL: box_const                        */
+    double box_const[3];
+    const int32_t *frame_rows;   /* DEVICE [n_frames] storage row of every frame, or NULL (row = frame) */
+    int32_t n_atoms;
+    int32_t first_origin;        /* frame of origin 0                                            */
+    int32_t origin_step;         /* frames between consecutive origins (1..)                     */
+    int32_t n_origins;
+    int32_t first_lag;           /* lag of result 0 (frames)                                     */
+    int32_t n_lags;              /* result l is lag first_lag + l                                */
+    int32_t flags;
+    double q;
+    double *sums;                /* DEVICE out [n_lags*2]                                        */
+    void *workspace;             /* DEVICE scratch of mdb_dense_workspace_bytes()                */
+    size_t workspace_bytes;
+} mdb_dense_args;
+
+int mdb_dense_workspace_bytes(const mdb_dense_args *args, size_t *bytes);
+int mdb_dense_corr(const mdb_dense_args *args, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

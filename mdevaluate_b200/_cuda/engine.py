@@ -188,6 +188,54 @@ def correlate_device(store, rows, spec, stream=None, select=None):
     return sums, hist
 
 
+DENSE_MAX_ORIGIN_STEP = 4        # beyond that neighbouring origins share too few rows to pay off
+
+
+def dense_device(store, first_origin, origin_step, n_origins, first_lag, n_lags, flags, q=0.0, stream=None):
+    """Dense schedule (arithmetic origins x contiguous lags), summed over origins: device ``(L, 2)`` float64
+    with the sums of r^2 and sinc(q r) over all origins and atoms (mdb_dense_corr)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = store.device
+    if store.coords.dtype != torch.float32:
+        raise _lib.CudaPathError('the dense kernel takes float32 rows')
+    sums = torch.empty((n_lags, 2), dtype=torch.float64, device=dev)
+    a = _lib.DenseArgs()
+    a.coords = store.coords.data_ptr()
+    a.pitch = store.coords.stride(0)
+    if store.images is not None:
+        a.images = store.images.data_ptr()
+        a.img_pitch = store.images.stride(0)
+        if store.box_const is not None:
+            a.box_const[0], a.box_const[1], a.box_const[2] = store.box_const
+        else:
+            a.box = store.box.data_ptr()
+    if store.frame_to_row is not None:
+        rows_dev = store._cache.get('frame_rows')
+        if rows_dev is None:
+            rows_dev = store._cache['frame_rows'] = torch.from_numpy(
+                np.ascontiguousarray(store.frame_to_row, dtype=np.int32)).to(dev)
+        a.frame_rows = rows_dev.data_ptr()
+    a.n_atoms = store.n_atoms
+    a.first_origin, a.origin_step, a.n_origins = int(first_origin), int(origin_step), int(n_origins)
+    a.first_lag, a.n_lags = int(first_lag), int(n_lags)
+    a.flags = int(flags)
+    a.q = float(q)
+    a.sums = sums.data_ptr()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.mdb_dense_workspace_bytes(C.byref(a), C.byref(nbytes)), 'mdb_dense_workspace_bytes')
+    ws = store._cache.get('workspace')
+    if ws is None or ws.numel() < nbytes.value:
+        ws = store._cache['workspace'] = torch.empty((max(nbytes.value, 1),), dtype=torch.uint8, device=dev)
+    a.workspace = ws.data_ptr()
+    a.workspace_bytes = ws.numel()
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mdb_dense_corr(C.byref(a), C.c_void_p(st.cuda_stream)), 'mdb_dense_corr')
+    _count(2)
+    return sums
+
+
 def nojump_scan(coords_seg, n_atoms, box0, box_is_f32, prev, cum, first_segment, images=None, jumps=None,
                 out_row=None, coords_out=None, overflow=None, whole0=None, stream=None):
     """One segment of the jump scan (mdb_nojump_scan).  All tensors are device tensors."""

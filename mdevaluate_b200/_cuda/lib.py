@@ -23,6 +23,7 @@ EXPORTS = (
     'mdb_corr_workspace_bytes', 'mdb_shifted_corr', 'mdb_corr_last_launches',
     'mdb_corr_profile', 'mdb_corr_last_kernel_ms',
     'mdb_nojump_scan', 'mdb_nojump_apply',
+    'mdb_dense_workspace_bytes', 'mdb_dense_corr',
 )
 
 
@@ -53,6 +54,16 @@ class NojumpArgs(C.Structure):
     ]
 
 
+class DenseArgs(C.Structure):
+    _fields_ = [
+        ('coords', C.c_void_p), ('pitch', C.c_int64), ('images', C.c_void_p), ('img_pitch', C.c_int64),
+        ('box', C.c_void_p), ('box_const', C.c_double * 3), ('frame_rows', C.c_void_p),
+        ('n_atoms', C.c_int32), ('first_origin', C.c_int32), ('origin_step', C.c_int32), ('n_origins', C.c_int32),
+        ('first_lag', C.c_int32), ('n_lags', C.c_int32), ('flags', C.c_int32), ('q', C.c_double),
+        ('sums', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -68,6 +79,8 @@ def _declare(lib):
     lib.mdb_corr_profile.argtypes = [C.c_int]
     lib.mdb_corr_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
     lib.mdb_nojump_scan.argtypes = [C.POINTER(NojumpArgs), C.c_void_p]
+    lib.mdb_dense_workspace_bytes.argtypes = [C.POINTER(DenseArgs), C.POINTER(C.c_size_t)]
+    lib.mdb_dense_corr.argtypes = [C.POINTER(DenseArgs), C.c_void_p]
     lib.mdb_nojump_apply.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_void_p,
                                      C.c_void_p]
     for name in EXPORTS:

@@ -335,6 +335,47 @@ def _schedule(frames, index_distribution, segments, window, skip):
     return start_frames, idx
 
 
+DENSE_MIN_PAIRS = 2048          # below this the streaming kernel is just as good
+
+
+def _dense_average(frames, spec, start_frames, idx):
+    """``average=True`` over a dense schedule -- origins in arithmetic progression, lags a contiguous
+    range (``index_distribution=lambda a, b: np.arange(a, b)``) -- for msd / isf: the tiled kernel
+    (csrc/dense_kernels.cu) reuses every frame row for a whole block of (origin, lag) pairs and sums
+    over the origins on the device.  Returns ``None`` when the schedule or function does not qualify."""
+    from .coordinates import Coordinates
+    if spec.name not in ('msd', 'isf') or not isinstance(frames, Coordinates):
+        return None
+    S, L = len(start_frames), len(idx)
+    if S * L < DENSE_MIN_PAIRS or L < 2 or np.any(np.diff(idx) != 1) or idx[0] < 0:
+        return None
+    step = 1
+    if S > 1:
+        d = np.diff(start_frames)
+        step = int(d[0])
+        if step < 1 or step > engine.DENSE_MAX_ORIGIN_STEP or np.any(d != step):
+            return None
+    if start_frames[0] < 0 or start_frames[-1] + idx[-1] >= len(frames):
+        return None                                   # let the general path raise / wrap indices
+    res = frames._resident()
+    nojump = frames.mode == 'nojump'
+    if res.dtype != np.float32:
+        return None
+    store = res.store_for(np.arange(start_frames[0], start_frames[-1] + idx[-1] + 1), nojump=nojump)
+    if not nojump:
+        store = store.without_images()
+    # the origin of segment s is the FIRST frame of its iterator, start_s + idx[0] (correlation.py:21-24)
+    sums = engine.dense_device(store, start_frames[0] + idx[0], step, S, 0, L, spec.corr.flags, q=spec.corr.q)
+    n_atoms = res.n_atoms
+    if frames.comm is not None:
+        import torch.distributed as dist
+        group, n_atoms = frames.comm
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    sums = sums.cpu().numpy()
+    out = sums[:, 0 if spec.name == 'msd' else 1] / n_atoms / S
+    return out.astype(np.float32) if (not nojump) else out
+
+
 def _global_counts(frames, counts):
     """Sub-ensemble sizes: summed over the shards of an atom-sharded trajectory (every rank runs the
     selector on its own atoms)."""
@@ -426,6 +467,10 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
     start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
     frame_ids = _frame_ids(start_frames, idx, len(frames))
     times = _times(frames, idx)
+    if plain and average:
+        dense = _dense_average(frames, spec, start_frames, idx)
+        if dense is not None:
+            return times, dense
     if plain:
         n_origins = len(start_frames)
         batch = max(1, MAX_PAIRS_PER_LAUNCH // max(1, len(idx)))

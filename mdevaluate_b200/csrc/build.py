@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT_DIR = os.path.join(PKG, '_cuda')
 LIB = os.path.join(OUT_DIR, 'libmdevaluate_b200.so')
-SOURCES = ['abi.cu', 'corr_kernels.cu', 'nojump_kernels.cu']
+SOURCES = ['abi.cu', 'corr_kernels.cu', 'nojump_kernels.cu', 'dense_kernels.cu']
 HEADERS = ['common.cuh', os.path.join('..', '..', 'include', 'mdevaluate_b200.h')]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 

@@ -431,3 +431,48 @@ def test_origin_batching_for_dense_schedules(small, md, monkeypatch):
     _, ref = orc.shifted_correlation(partial(orc.isf, q=22.7), unw, segments=60, window=0.3, average=True,
                                      index_distribution=orc.lin_indices)
     close(batched_avg, ref)
+
+
+# ---- dense schedules: the tiled kernel (csrc/dense_kernels.cu), BASELINE config 5 -------------------
+@pytest.mark.parametrize('n_atoms,n_frames,segments,window,first', [
+    (96, 240, 120, 0.5, 0),      # every frame an origin (step 1), 120 lags
+    (131, 200, 50, 0.5, 0),      # origin step 2, atoms not a multiple of 64
+    (70, 180, 30, 0.35, 3),      # origin step 3-4 is irregular here -> falls back unless arithmetic
+    (300, 150, 75, 0.5, 2),      # lags start at 2
+])
+def test_dense_schedule_kernel(md, monkeypatch, n_atoms, n_frames, segments, window, first):
+    from mdevaluate_b200.synthetic import random_walk
+    from mdevaluate_b200._cuda import engine
+    pos, box, times = random_walk(n_atoms, n_frames, seed=n_atoms, sigma=0.08, box=1.7)
+    coords = md.Coordinates.from_arrays(pos, box, times)
+    unw = orc.UnwrappedTrajectory(pos, box, times)
+    c = md.correlation
+    dense = lambda a, b: np.arange(a + first, b)
+    calls = []
+    real = engine.dense_device
+    monkeypatch.setattr(engine, 'dense_device', lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    monkeypatch.setattr(c, 'DENSE_MIN_PAIRS', 1)
+    for name, ours, theirs in (('msd', c.msd, orc.msd), ('isf', partial(c.isf, q=22.7), partial(orc.isf, q=22.7))):
+        for mode, frames, ref_frames in (('nojump', coords.nojump, unw),
+                                         ('raw', coords, orc.ArrayTrajectory(pos, box, times))):
+            n0 = len(calls)
+            t, got = c.shifted_correlation(ours, frames, segments=segments, window=window, average=True,
+                                           index_distribution=dense)
+            starts, _ = c._schedule(frames, dense, segments, window, None)
+            arithmetic = len(starts) < 2 or (np.all(np.diff(starts) == np.diff(starts)[0]) and np.diff(starts)[0] <= 4)
+            assert (len(calls) > n0) == bool(arithmetic)           # the tiled kernel really ran (or really not)
+            t0, ref = orc.shifted_correlation(theirs, ref_frames, segments=segments, window=window, average=True,
+                                              index_distribution=dense)
+            np.testing.assert_array_equal(t, t0)
+            assert got.dtype == ref.dtype and got.shape == ref.shape
+            if name == 'msd' and mode == 'nojump':
+                close(got, ref, rtol=1e-11, atol=1e-13)
+            else:
+                close(got, ref, scale=float(np.abs(ref).max()), atol=2e-7 if mode == 'raw' else 1e-7)
+            # and it agrees with the streaming kernel on the same schedule
+            monkeypatch.setattr(c, 'DENSE_MIN_PAIRS', 1 << 60)
+            _, stream = c.shifted_correlation(ours, frames, segments=segments, window=window, average=True,
+                                              index_distribution=dense)
+            monkeypatch.setattr(c, 'DENSE_MIN_PAIRS', 1)
+            close(got, stream, scale=float(np.abs(ref).max()), rtol=1e-6 if mode == 'raw' else 1e-11,
+                  atol=2e-7 if name == 'isf' else 1e-12)

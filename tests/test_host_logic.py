@@ -131,7 +131,8 @@ def test_c_abi_exports_every_declared_symbol():
 def test_c_abi_struct_layout_matches_header():
     # field order/count of the ctypes mirrors vs the header structs
     header = open(os.path.join(ROOT, 'include', 'mdevaluate_b200.h')).read()
-    for cname, ctype in (('mdb_corr_args', L.CorrArgs), ('mdb_nojump_args', L.NojumpArgs)):
+    for cname, ctype in (('mdb_corr_args', L.CorrArgs), ('mdb_nojump_args', L.NojumpArgs),
+                         ('mdb_dense_args', L.DenseArgs)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), header, re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
         fields = [re.split(r'[\s\*]+', f.strip())[-1].split('[')[0] for f in body.split(';') if f.strip()]
@@ -146,6 +147,7 @@ def test_argument_errors_without_gpu():
     nj = L.NojumpArgs()
     assert lib.mdb_nojump_scan(C.byref(nj), None) == 1
     assert lib.mdb_nojump_apply(None, None, None, 0, None, None) == 1
+    assert lib.mdb_dense_corr(C.byref(L.DenseArgs()), None) == 1
 
 
 def test_no_cpu_fallback():
