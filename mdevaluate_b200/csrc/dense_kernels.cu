@@ -10,7 +10,7 @@
 //
 // One CTA owns one lag block for a slice of the atom tiles and walks over ALL origin blocks, so the
 // per-lag sums over origins and atoms live in registers until the very end: thread (atom i, slice j)
-// handles the lags l = j, j+4, j+8, j+12 of the block.  Partials per atom split are added by a small
+// handles the lags l = j, j+4, ..., j+28 of the block (kL = 32).  Partials per atom split are added by a small
 // second kernel in fixed order (bit-reproducible).
 #include "common.cuh"
 
@@ -20,9 +20,15 @@ namespace {
 constexpr int kTileAtoms = 64;
 constexpr int kSlices = 4;
 constexpr int kDenseThreads = kTileAtoms * kSlices;   // 256
-constexpr int kL = 16;                                // lags per block (4 per thread)
+#ifndef MDB_DENSE_KL
+#define MDB_DENSE_KL 32
+#endif
+constexpr int kL = MDB_DENSE_KL;                      // lags per block
+constexpr int kSlots = kL / kSlices;                  // lag slots per thread
 constexpr int kMaxS = 16;                             // origins per block (fewer for origin_step > 1)
-constexpr int kMaxPartnerRows = 48;
+constexpr int kMaxPartnerRows = 32 + kL;
+constexpr int kQuadsPerRow = 3 * kTileAtoms / 4;     // 48 float4 per row of the tile
+constexpr int kStageBatch = 5;
 
 struct DenseDev {
     const float *coords;
@@ -45,24 +51,50 @@ __device__ __forceinline__ int row_of(const DenseDev &p, int frame) {
     return p.frame_rows ? p.frame_rows[frame] : frame;
 }
 
-// Load one frame row of the tile (64 atoms = 192 interleaved values), unwrap, store as SoA doubles.
+// One quad (4 consecutive interleaved values = one 128-bit load + one 32-bit image word) of a frame
+// row of the tile.  Rows are 16-byte aligned (checked on the host); quads that start beyond the
+// shard's last component read nothing.
+struct Quad {
+    float4 x;
+    uint32_t n;
+};
+
 template <bool IMG>
-__device__ __forceinline__ void stage_row(const DenseDev &p, int frame, int atom0, double *dst /*[3][64]*/, int v) {
-    // v in [0, 192): interleaved component index inside the tile
-    const int atom = v / 3, c = v - 3 * atom;
-    double value = 0.0;
-    if (atom0 + atom < p.n_atoms) {
+__device__ __forceinline__ Quad load_quad(const DenseDev &p, int frame, int atom0, int qd) {
+    Quad q;
+    q.x = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.n = 0x80808080u;
+    const long long e = 3ll * atom0 + 4 * qd;
+    if (e < 3ll * p.n_atoms) {
         const int row = row_of(p, frame);
-        const long long e = 3ll * atom0 + v;
-        const float x = __ldg(p.coords + (long long)row * p.pitch + e);
-        value = (double)x;
-        if (IMG) {
-            const int n = (int)__ldg(p.images + (long long)row * p.img_pitch + e) - MDB_IMAGE_BIAS;
-            const double b = p.box ? __ldg(p.box + 3ll * row + c) : p.box_const[c];
-            value = fma(-(double)n, b, value);     // pbc.py:235-247, same expression as the streaming kernel
+        q.x = __ldg(reinterpret_cast<const float4 *>(p.coords + (long long)row * p.pitch + e));
+        if (IMG) q.n = __ldg(reinterpret_cast<const uint32_t *>(p.images + (long long)row * p.img_pitch + e));
+    }
+    return q;
+}
+
+// Unwrap the quad (pbc.py:235-247, the same expression as the streaming kernel) into the row's
+// structure-of-arrays float64 tile [3][64].
+template <bool IMG>
+__device__ __forceinline__ void store_quad(const DenseDev &p, const Quad &q, int frame, int qd, double *dst) {
+    double bx = 0.0, by = 0.0, bz = 0.0;
+    if (IMG) {
+        if (p.box) {
+            const int row = row_of(p, frame);
+            bx = __ldg(p.box + 3ll * row); by = __ldg(p.box + 3ll * row + 1); bz = __ldg(p.box + 3ll * row + 2);
+        } else {
+            bx = p.box_const[0]; by = p.box_const[1]; bz = p.box_const[2];
         }
     }
-    dst[c * kTileAtoms + atom] = value;
+    const float xs[4] = {q.x.x, q.x.y, q.x.z, q.x.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int v = 4 * qd + k;
+        const int atom = v / 3, c = v - 3 * atom;
+        double value = (double)xs[k];
+        if (IMG) value = fma(-image_count(q.n, k), c == 0 ? bx : (c == 1 ? by : bz), value);
+        dst[c * kTileAtoms + atom] = value;
+    }
 }
 
 template <bool IMG, int FLAGS>
@@ -70,7 +102,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_corr_kernel(const Dens
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     extern __shared__ __align__(16) double s_rows[];     // [ks + n_partner][3][64]
-    __shared__ double s_red[kDenseThreads / 32][4][2];
+    __shared__ double s_red[kDenseThreads / 32][kSlots][2];
 
     const int lb = blockIdx.x % p.n_lblocks;
     const int split = blockIdx.x / p.n_lblocks;
@@ -80,7 +112,9 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_corr_kernel(const Dens
     const int i = tid % kTileAtoms, j = tid / kTileAtoms;
     const int row_doubles = 3 * kTileAtoms;
 
-    double acc2[4] = {0.0, 0.0, 0.0, 0.0}, accs[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc2[kSlots], accs[kSlots];
+#pragma unroll
+    for (int m = 0; m < kSlots; ++m) acc2[m] = accs[m] = 0.0;
 
     const int t_begin = split * p.tiles_per_split;
     const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
@@ -95,37 +129,64 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_corr_kernel(const Dens
             const int n_partner = (ns - 1) * p.ostep + nl;
             __syncthreads();                              // the previous block is done with the rows
             const int n_rows = ns + n_partner;
-            for (int w = tid; w < n_rows * 192; w += kDenseThreads) {
-                const int r = w / 192, v = w - 192 * r;
-                const int frame = (r < ns) ? f_origin0 + r * p.ostep : f_partner0 + (r - ns);
-                stage_row<IMG>(p, frame, atom0, s_rows + (size_t)r * row_doubles, v);
+            // stage the rows: kStageBatch independent 128-bit loads per thread in flight, then unwrap + store
+            const int n_quads = n_rows * kQuadsPerRow;
+            for (int w0 = tid; w0 < n_quads; w0 += kDenseThreads * kStageBatch) {
+                Quad q[kStageBatch];
+#pragma unroll
+                for (int u = 0; u < kStageBatch; ++u) {
+                    const int w = w0 + u * kDenseThreads;
+                    if (w < n_quads) {
+                        const int r = w / kQuadsPerRow, qd = w - kQuadsPerRow * r;
+                        const int frame = (r < ns) ? f_origin0 + r * p.ostep : f_partner0 + (r - ns);
+                        q[u] = load_quad<IMG>(p, frame, atom0, qd);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kStageBatch; ++u) {
+                    const int w = w0 + u * kDenseThreads;
+                    if (w < n_quads) {
+                        const int r = w / kQuadsPerRow, qd = w - kQuadsPerRow * r;
+                        const int frame = (r < ns) ? f_origin0 + r * p.ostep : f_partner0 + (r - ns);
+                        store_quad<IMG>(p, q[u], frame, qd, s_rows + (size_t)r * row_doubles);
+                    }
+                }
             }
             __syncthreads();
             if (live) {
+                // Branch-free inner loop: the 4 lag slots of a thread are always evaluated.  In the last
+                // lag block some slots lie beyond n_lags: they read rows that are allocated (stale data)
+                // and their sums are simply never written out.
+                float fs[kSlots];                          // float32 sinc sums over the origins of this block
+#pragma unroll
+                for (int m = 0; m < kSlots; ++m) fs[m] = 0.f;
+                const double *rp0 = s_rows + (size_t)(ns + j) * row_doubles + i;
                 for (int a = 0; a < ns; ++a) {
                     const double *ro = s_rows + (size_t)a * row_doubles + i;
                     const double ox = ro[0], oy = ro[kTileAtoms], oz = ro[2 * kTileAtoms];
-                    float yq[4] = {0.f, 0.f, 0.f, 0.f};
+                    const double *rp = rp0 + (size_t)a * p.ostep * row_doubles;
+                    float yq[kSlots];
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const int l = j + kSlices * m;
-                        if (l < nl) {
-                            const double *rp = s_rows + (size_t)(ns + a * p.ostep + l) * row_doubles + i;
-                            const double dx = ox - rp[0], dy = oy - rp[kTileAtoms], dz = oz - rp[2 * kTileAtoms];
-                            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                            if constexpr (kR2) acc2[m] += r2;
-                            if constexpr (kSinc) yq[m] = (float)(r2 * p.q2);
-                        }
+                    for (int m = 0; m < kSlots; ++m) {
+                        const double *rq = rp + (size_t)(kSlices * m) * row_doubles;
+                        const double dx = ox - rq[0], dy = oy - rq[kTileAtoms], dz = oz - rq[2 * kTileAtoms];
+                        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        if constexpr (kR2) acc2[m] += r2;
+                        if constexpr (kSinc) yq[m] = (float)(r2 * p.q2);
                     }
                     if constexpr (kSinc) {
-                        float v0, v1, v2, v3;
-                        sinc_of_square_x2(yq[0], yq[1], v0, v1);
-                        sinc_of_square_x2(yq[2], yq[3], v2, v3);
-                        if (j < nl) accs[0] += (double)v0;
-                        if (j + kSlices < nl) accs[1] += (double)v1;
-                        if (j + 2 * kSlices < nl) accs[2] += (double)v2;
-                        if (j + 3 * kSlices < nl) accs[3] += (double)v3;
+#pragma unroll
+                        for (int m = 0; m < kSlots; m += 2) {
+                            float v0, v1;
+                            sinc_of_square_x2(yq[m], yq[m + 1], v0, v1);
+                            fs[m] += v0;
+                            fs[m + 1] += v1;
+                        }
                     }
+                }
+                if constexpr (kSinc) {
+#pragma unroll
+                    for (int m = 0; m < kSlots; ++m) accs[m] += (double)fs[m];
                 }
             }
         }
@@ -134,7 +195,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_corr_kernel(const Dens
     // ---- reduce over the 64 atoms of every (slice j, slot m): two warps per slice ----
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < kSlots; ++m) {
         const double v2 = warp_sum(acc2[m]);
         const double vs = warp_sum(accs[m]);
         if (lane == 0) {
@@ -175,6 +236,9 @@ int make_dense_plan(const mdb_dense_args *a, DensePlan *pl) {
     if (!(a->flags & (MDB_SUM_R2 | MDB_SUM_SINC)) || (a->flags & ~(MDB_SUM_R2 | MDB_SUM_SINC)))
         return fail(MDB_ERR_UNSUPPORTED, "dense: flags must be MDB_SUM_R2 and/or MDB_SUM_SINC");
     if (a->pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "pitch < 3*n_atoms");
+    if (reinterpret_cast<uintptr_t>(a->coords) % 16 || a->pitch % 4 ||
+        (a->images && (reinterpret_cast<uintptr_t>(a->images) % 4 || a->img_pitch % 4)))
+        return fail(MDB_ERR_UNSUPPORTED, "dense: rows must be 16-byte aligned (pitch % 4 == 0, image pitch % 4 == 0)");
     int ks = (kMaxPartnerRows - kL) / a->origin_step + 1;
     if (ks > kMaxS) ks = kMaxS;
     if (ks < 2) return fail(MDB_ERR_UNSUPPORTED, "dense: origin_step too large for row reuse (use mdb_shifted_corr)");
@@ -190,7 +254,7 @@ int make_dense_plan(const mdb_dense_args *a, DensePlan *pl) {
     if (want < 1) want = 1;
     pl->tiles_per_split = (int)((pl->n_tiles + want - 1) / want);
     pl->n_splits = (pl->n_tiles + pl->tiles_per_split - 1) / pl->tiles_per_split;
-    const int max_partner = (ks - 1) * a->origin_step + kL;
+    const int max_partner = (ks - 1) * a->origin_step + kL;       // also what the padded lag slots may touch
     pl->smem = (size_t)(ks + max_partner) * 3 * kTileAtoms * sizeof(double);
     return MDB_OK;
 }
