@@ -45,6 +45,9 @@ def slabs(frame):
     return np.array([z < 0.3 * L, (z >= 0.3 * L) & (z < 0.7 * L), z >= 0.7 * L])
 t, out['sub'] = c.shifted_correlation(c.msd, shard.nojump, segments=9, window=0.4,
                                       correlation=c.subensemble_correlation(slab))
+dense = lambda a, b: np.arange(a, b)
+t, out['dense'] = c.shifted_correlation(partial(c.isf, q=22.7), shard.nojump, segments=150, window=0.5, average=True,
+                                        index_distribution=dense)
 t, out['multi'], out['multi_n'] = c.shifted_correlation(partial(c.isf, q=22.7), shard.nojump, segments=9, window=0.4,
                                                         average=True,
                                                         correlation=c.multi_subensemble_correlation(slabs))
@@ -63,6 +66,9 @@ if rank == 0:
     t, r, n = c.shifted_correlation(partial(c.isf, q=22.7), full.nojump, segments=9, window=0.4, average=True,
                                     correlation=c.multi_subensemble_correlation(slabs))
     assert np.array_equal(out['multi_n'], n) and np.allclose(out['multi'], r, rtol=1e-9, atol=1e-12)
+    t, rd = c.shifted_correlation(partial(c.isf, q=22.7), full.nojump, segments=150, window=0.5, average=True,
+                                  index_distribution=dense)
+    assert np.allclose(out['dense'], rd, rtol=1e-9, atol=1e-12)
     print('MULTI_GPU_OK')
 dist.destroy_process_group()
 '''
