@@ -364,6 +364,9 @@ def _dense_average(frames, spec, start_frames, idx):
     store = res.store_for(np.arange(start_frames[0], start_frames[-1] + idx[-1] + 1), nojump=nojump)
     if not nojump:
         store = store.without_images()
+    if store.coords.stride(0) % 4 or store.coords.data_ptr() % 16 or (
+            store.images is not None and (store.images.stride(0) % 4 or store.images.data_ptr() % 4)):
+        return None                                   # unaligned rows: the streaming kernel has a scalar path
     # the origin of segment s is the FIRST frame of its iterator, start_s + idx[0] (correlation.py:21-24)
     sums = engine.dense_device(store, start_frames[0] + idx[0], step, S, 0, L, spec.corr.flags, q=spec.corr.q)
     n_atoms = res.n_atoms
