@@ -313,7 +313,7 @@ def ours_arm(a):
                 'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
                 'moved_bytes_per_launch': 15.0 * N * S * (L + 1),
                 'note': 'algorithmic bytes = 12 B (float32 xyz) per atom*origin*(lag+1); the kernel also reads 3 B of '
-                        'int8 image counts per coordinate triple (nojump), so moved bytes are 1.25x algorithmic'}
+                        'image-count bytes per coordinate triple (nojump), so moved bytes are 1.25x algorithmic'}
 
     # ---- the other kernels of the path on the same rows (kernel time only; informational) ------------
     # (every rank takes part: with N > 1 each call ends in the all-reduce of the partial sums)

@@ -36,7 +36,7 @@ class DeviceStore:
     def __init__(self, coords, n_atoms, images=None, box=None, frame_to_row=None, n_frames=None, box_const=None):
         self.coords = coords            # torch (n_rows, pitch) float32 / float64
         self.n_atoms = int(n_atoms)
-        self.images = images            # torch int8 (n_rows, img_pitch) or None
+        self.images = images            # torch uint8 (n_rows, img_pitch), excess-128, or None
         self.box = box                  # torch float64 (n_rows, 3) or None
         self.box_const = box_const      # 3 floats when every row has the same box
         self.frame_to_row = frame_to_row  # np.int32 (T,) with -1 = absent, or None = identity

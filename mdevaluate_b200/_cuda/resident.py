@@ -212,7 +212,7 @@ class Resident:
                                images=img_seg, jumps=jmp_seg, out_row=rows, coords_out=coords_out,
                                overflow=overflow, whole0=whole0)
         if int(overflow.item()):
-            raise _lib.CudaPathError('an atom crossed more than 127 periodic images; int8 image counts overflow')
+            raise _lib.CudaPathError('an atom crossed more than 127 periodic images; the one-byte image counts overflow')
 
     def _ensure_dense_images(self):
         torch = _lib.require_cuda()
