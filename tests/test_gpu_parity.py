@@ -439,6 +439,9 @@ def test_origin_batching_for_dense_schedules(small, md, monkeypatch):
     (131, 200, 50, 0.5, 0),      # origin step 2, atoms not a multiple of 64
     (70, 180, 30, 0.35, 3),      # origin step 3-4 is irregular here -> falls back unless arithmetic
     (300, 150, 75, 0.5, 2),      # lags start at 2
+    (65, 240, 30, 0.5, 0),       # origin step 4 (9 origins per block)
+    (200, 180, 30, 0.5, 1),      # origin step 3
+    (64, 400, 200, 0.5, 0),      # 200 lags = 6 full lag blocks + 8
 ])
 def test_dense_schedule_kernel(md, monkeypatch, n_atoms, n_frames, segments, window, first):
     from mdevaluate_b200.synthetic import random_walk
