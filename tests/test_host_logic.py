@@ -202,3 +202,60 @@ def test_atom_blocks_cover_everything():
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             for (a0, a1), (b0, b1) in zip(blocks, blocks[1:]):
                 assert a1 == b0 and (a0 % 4 == 0 or a0 == n) and (b0 % 4 == 0 or b0 == n)
+
+
+def test_selector_masks():
+    n = 10
+    for sel, expect in (
+            (np.array([1, 3, 4]), [1, 3, 4]),
+            ((np.array([0, 9]),), [0, 9]),                       # what np.where / mask2indices return
+            (slice(2, 8, 3), [2, 5]),
+            (np.arange(n) % 2 == 0, [0, 2, 4, 6, 8]),
+            (np.array([], dtype=int), []),
+            (np.array([-1]), [9])):
+        mask, count = corr._selector_mask(sel, n)
+        assert mask.dtype == np.uint8 and count == len(expect)
+        np.testing.assert_array_equal(np.nonzero(mask)[0], expect)
+    with pytest.raises(NotImplementedError):
+        corr._selector_mask(np.array([1, 1, 2]), n)
+    sels, shape = corr._selector_array(np.array([[0, 1], [2, 3], [4, 5]]))
+    assert shape == (3,)
+    ragged = np.empty(2, dtype=object)
+    ragged[0], ragged[1] = [0, 1, 2], []
+    sels, shape = corr._selector_array(ragged)
+    assert shape == (2,)
+    masks = np.array([[True, False], [False, True]])
+    assert corr._selector_array(masks)[1] == (2,)
+    np.testing.assert_array_equal(md.utils.mask2indices([True, False, True])[0], [0, 2])
+    assert md.utils.mask2indices([[True, True, False], [True, False, True]]).shape == (2, 1, 2)
+
+
+def test_frame_ids_follow_python_indexing():
+    starts = np.array([0, 5])
+    ids = corr._frame_ids(starts, np.array([0, 1, 4]), 10)
+    np.testing.assert_array_equal(ids, [[0, 1, 4], [5, 6, 9]])
+    ids = corr._frame_ids(starts, np.array([0, -1]), 10)          # negative frames count from the end
+    np.testing.assert_array_equal(ids, [[0, 9], [5, 4]])
+    with pytest.raises(IndexError):
+        corr._frame_ids(starts, np.array([0, 5]), 10)
+    with pytest.raises(IndexError):
+        corr._frame_ids(starts, np.array([0, -11]), 10)
+
+
+def test_strategy_objects_carry_their_selector():
+    sel = lambda frame: [0]
+    sub = corr.subensemble_correlation(sel)
+    assert sub._mdb_strategy == ('sub', sel, corr.correlation)
+    multi = corr.multi_subensemble_correlation(sel)
+    assert multi.has_counter and multi._mdb_strategy == ('multi', sel)
+    # a sub-ensemble strategy around a custom inner strategy is not on the GPU path
+    custom = corr.subensemble_correlation(sel, correlation_function=lambda f, fr: iter(()))
+    with pytest.raises(NotImplementedError):
+        corr.shifted_correlation(corr.msd, _Frames(10), correlation=custom)
+
+
+def test_rotational_spec():
+    sp = corr._kernel_spec(partial(corr.rotational_autocorrelation, order=4))
+    assert sp.corr.flags == L.SUM_LEGENDRE and sp.corr.order == 4
+    with pytest.raises(ValueError):
+        corr._kernel_spec(partial(corr.rotational_autocorrelation, order=2.5))
