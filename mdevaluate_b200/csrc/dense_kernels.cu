@@ -28,7 +28,7 @@ constexpr int kSlots = kL / kSlices;                  // lag slots per thread
 constexpr int kMaxS = 16;                             // origins per block (fewer for origin_step > 1)
 constexpr int kMaxPartnerRows = 32 + kL;
 constexpr int kQuadsPerRow = 3 * kTileAtoms / 4;     // 48 float4 per row of the tile
-constexpr int kStageBatch = 5;
+constexpr int kStageBatch = 5;                       // independent 128-bit loads per thread in flight while staging (12 was slower: 128 registers)
 
 struct DenseDev {
     const float *coords;
