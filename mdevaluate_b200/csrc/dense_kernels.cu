@@ -17,8 +17,15 @@
 namespace mdb {
 namespace {
 
-constexpr int kTileAtoms = 64;
-constexpr int kSlices = 4;
+#ifndef MDB_DENSE_ATOMS
+#define MDB_DENSE_ATOMS 64
+#endif
+#ifndef MDB_DENSE_CTAS
+#define MDB_DENSE_CTAS 2
+#endif
+constexpr int kTileAtoms = MDB_DENSE_ATOMS;           // atoms per tile (a multiple of 32)
+constexpr int kSlices = 256 / kTileAtoms;             // lag slices: thread = (atom, slice)
+constexpr int kWarpsPerSlice = kTileAtoms / 32;
 constexpr int kDenseThreads = kTileAtoms * kSlices;   // 256
 #ifndef MDB_DENSE_KL
 #define MDB_DENSE_KL 32
@@ -98,7 +105,7 @@ __device__ __forceinline__ void store_quad(const DenseDev &p, const Quad &q, int
 }
 
 template <bool IMG, int FLAGS>
-__global__ void __launch_bounds__(kDenseThreads, 2) dense_corr_kernel(const DenseDev p) {
+__global__ void __launch_bounds__(kDenseThreads, MDB_DENSE_CTAS) dense_corr_kernel(const DenseDev p) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     extern __shared__ __align__(16) double s_rows[];     // [ks + n_partner][3][64]
@@ -208,7 +215,9 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_corr_kernel(const Dens
         const int l = tid / 2, comp = tid & 1;          // lag of the block, component
         const int jj = l % kSlices, m = l / kSlices;    // which slice / slot holds it
         if (l < nl) {
-            const double v = s_red[2 * jj][m][comp] + s_red[2 * jj + 1][m][comp];
+            double v = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < kWarpsPerSlice; ++wv) v += s_red[kWarpsPerSlice * jj + wv][m][comp];
             p.partial[((long long)split * p.L + lam + l) * 2 + comp] = v;
         }
     }
