@@ -479,3 +479,36 @@ def test_dense_schedule_kernel(md, monkeypatch, n_atoms, n_frames, segments, win
             monkeypatch.setattr(c, 'DENSE_MIN_PAIRS', 1)
             close(got, stream, scale=float(np.abs(ref).max()), rtol=1e-6 if mode == 'raw' else 1e-11,
                   atol=2e-7 if name == 'isf' else 1e-12)
+
+
+def test_custom_reader_protocol(golden, md):
+    """Coordinates over ANY reader with the reference protocol (len, reader[i].positions/.box/.time,
+    reader.py:254-286): frames are pulled one by one into pinned staging and streamed through the scan."""
+    g = golden('walk_small')
+    pos, box, times = g['pos'], g['box'], g['times']          # NpzFile decompresses on every access
+
+    class Frame:
+        def __init__(self, positions, box, time):
+            self.positions, self.box, self.time = positions, box, time
+            self.coordinates = positions
+
+    class Reader:
+        filename = 'custom'
+
+        def __len__(self):
+            return len(pos)
+
+        def __getitem__(self, i):
+            return Frame(pos[i], np.diag(box), times[i])
+
+    coords = md.Coordinates(Reader())
+    c = md.correlation
+    for forced in (False, True):
+        coords = md.Coordinates(Reader())
+        coords._resident().force_compact = forced
+        t, r = c.shifted_correlation(c.msd, coords.nojump, segments=12, window=0.4)
+        np.testing.assert_array_equal(t, g['t_nojump'])
+        close(r, g['msd_nojump'], rtol=1e-11, atol=1e-13)
+        t, r = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords, segments=12, window=0.4)
+        np.testing.assert_array_equal(r, g['vh_raw'])
+    np.testing.assert_array_equal(np.asarray(coords.nojump[100]), g['nojump_100'])
