@@ -481,6 +481,26 @@ def test_dense_schedule_kernel(md, monkeypatch, n_atoms, n_frames, segments, win
                   atol=2e-7 if name == 'isf' else 1e-12)
 
 
+def test_dense_kernel_on_a_compact_store(md, monkeypatch):
+    """The tiled kernel follows the frame -> row map of a compact (streamed) store."""
+    from mdevaluate_b200.synthetic import random_walk
+    pos, box, times = random_walk(90, 300, seed=4, sigma=0.08, box=1.7)
+    c = md.correlation
+    monkeypatch.setattr(c, 'DENSE_MIN_PAIRS', 1)
+    dense = lambda a, b: np.arange(a, b)
+    unw = orc.UnwrappedTrajectory(pos, box, times)
+    kw = dict(segments=40, window=0.3, skip=0.2, average=True, index_distribution=dense)
+    _, ref = orc.shifted_correlation(partial(orc.isf, q=22.7), unw, **kw)
+    coords = md.Coordinates.from_arrays(pos, box, times)
+    res = coords._resident()
+    res.force_compact = True
+    res.SEGMENT_BYTES = 16384
+    _, got = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, **kw)
+    store = next(iter(res._compact.values()))
+    assert store.frame_to_row is not None and store.coords.shape[0] < 300        # really a compact store
+    close(got, ref)
+
+
 def test_custom_reader_protocol(golden, md):
     """Coordinates over ANY reader with the reference protocol (len, reader[i].positions/.box/.time,
     reader.py:254-286): frames are pulled one by one into pinned staging and streamed through the scan."""
