@@ -507,8 +507,10 @@ __device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32
     raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
     raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
     raw[8] = c.x; raw[9] = c.y; raw[10] = c.z; raw[11] = c.w;
-    // the values are in registers: hand the stage back (one arrive per warp; the warp's loads are a
-    // single converged instruction ahead of it in program order)
+    // the values are in registers: hand the stage back.  One arrive per warp: __syncwarp() makes sure
+    // every lane has issued its loads of this stage (lanes may have diverged in the rare exact-bin
+    // path of the previous group) before lane 0 releases it.
+    __syncwarp();
     mbar_arrive_if(empty0 + 8 * ring.stage, (tid & 31) == 0);
     ring.advance();
     // a box that is the same for every row comes from the kernel parameters (constant bank operands)

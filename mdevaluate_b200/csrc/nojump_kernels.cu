@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(kScanBulkThreads, 2) nojump_scan_bulk_kernel(c
 #pragma unroll
         for (int r = 0; r < kRowsPerStage; ++r)
             rows[r] = reinterpret_cast<const float4 *>(smem_raw + (size_t)(stage * kRowsPerStage + r) * kSlabBytes)[tid];
+        __syncwarp();                                  // every lane has read its rows (lanes diverge in slow_jumps)
         mbar_arrive_if(empty0 + 8 * stage, (tid & 31) == 0);
         if (++stage == kScanStages) { stage = 0; phase ^= 1; }
 #pragma unroll
