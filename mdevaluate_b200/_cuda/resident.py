@@ -13,6 +13,8 @@ holds these frames (with image counts if nojump)" with the cheapest of:
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
 from . import engine
@@ -30,7 +32,18 @@ class Resident:
 
     def __init__(self, reader, atom_filter, device=None):
         torch = _lib.require_cuda()
-        self.reader = reader
+        # Coordinates caches this object ON the reader (one Resident per reader and selection), so a strong
+        # reference back would form a cycle and the HBM buffers (GBs) would wait for the garbage collector
+        # instead of being released with the last Coordinates: measured as 70 ms of cudaMalloc per
+        # end-to-end step.  The reader outlives us through Coordinates.frames.
+        self._reader_ref = None
+        self._reader_obj = reader
+        if hasattr(reader, '__dict__'):
+            try:
+                self._reader_ref = weakref.ref(reader)
+                self._reader_obj = None
+            except TypeError:
+                pass
         self.n_frames = len(reader)
         first = reader[0].positions
         m_all = len(first)
@@ -53,6 +66,15 @@ class Resident:
         self._dense_images = False
         self._compact = {}              # (mode, hash of frame ids) -> DeviceStore
         self.force_compact = False
+
+    @property
+    def reader(self):
+        if self._reader_ref is None:
+            return self._reader_obj
+        reader = self._reader_ref()
+        if reader is None:
+            raise ReferenceError('the trajectory reader of this store no longer exists')
+        return reader
 
     # -- box / time helpers --------------------------------------------------------------------
     def _box_of(self, i):

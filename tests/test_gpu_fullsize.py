@@ -122,7 +122,8 @@ def test_segmented_scan_equals_one_shot(big):
     # the same trajectory through the streaming path: many time segments with carried (prev, cum),
     # only 500 frames kept (compaction)
     keep = np.unique(np.random.default_rng(0).integers(0, T, 500))
-    res2 = md.Coordinates.from_arrays(block, box, times, n_atoms=N)._resident()
+    coords2 = md.Coordinates.from_arrays(block, box, times, n_atoms=N)      # keeps the reader alive
+    res2 = coords2._resident()
     res2.force_compact = True
     compact = res2._build_compact(keep, nojump=True)
     rows = compact.rows_for(keep)

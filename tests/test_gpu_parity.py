@@ -532,3 +532,22 @@ def test_custom_reader_protocol(golden, md):
         t, r = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords, segments=12, window=0.4)
         np.testing.assert_array_equal(r, g['vh_raw'])
     np.testing.assert_array_equal(np.asarray(coords.nojump[100]), g['nojump_100'])
+
+
+def test_store_released_without_garbage_collector(small, md):
+    """The HBM store of a trajectory goes away with the last Coordinates by reference counting alone
+    (no reader <-> store cycle): a streamed step must not leave GBs behind for the garbage collector."""
+    import gc
+    import weakref
+    g, _ = small
+    gc.collect()
+    gc.disable()
+    try:
+        coords = md.Coordinates.from_arrays(g['pos'], g['box'], g['times'])
+        md.correlation.shifted_correlation(md.correlation.msd, coords.nojump, segments=4)
+        res = weakref.ref(coords._resident())
+        store = weakref.ref(coords._resident().store_for(np.arange(4), nojump=True))
+        del coords
+        assert res() is None and store() is None
+    finally:
+        gc.enable()
