@@ -157,6 +157,28 @@ typedef struct mdb_nojump_args {
 
 int mdb_nojump_scan(const mdb_nojump_args *args, void *stream);
 
+/* nojump from STORED jump matrices (the reference's `.{traj}.nojump.npz` cache: three CSR int8 matrices
+ * J_d of shape frames x atoms, reader.py:189-241).  The caller re-sorts them by column into ONE compressed
+ * list over the 3*n_atoms interleaved components (column c = 3*atom + d): the stored jumps of column c are
+ * entries indptr[c] .. indptr[c+1]-1 of `frames` (ascending) / `jumps`.  Writes the running image count
+ * sum_{t <= keep[r]} J[t, c]  -- `m[:step+1].sum(axis=0)` of pbc.py:235-237 -- of every kept frame in the
+ * excess-128 byte format the correlation kernels read.  With the matrices at hand only the frames a
+ * schedule touches have to be read from the trajectory (no scan over all frames). */
+typedef struct mdb_jumpmat_args {
+    const int64_t *indptr;       /* DEVICE [3*n_atoms + 1] offsets per component column          */
+    const int32_t *frames;       /* DEVICE [nnz] frame of every stored jump, ascending per column */
+    const int8_t *jumps;         /* DEVICE [nnz] the jump J[frame, column]                        */
+    int64_t nnz;
+    int32_t n_atoms;
+    const int32_t *keep;         /* DEVICE [n_keep] ascending frames to produce rows for; NULL = 0..n_keep-1 */
+    int32_t n_keep;
+    uint8_t *images;             /* DEVICE out [n_keep][img_pitch] excess-128                     */
+    int64_t img_pitch;           /* bytes per row, >= 3*n_atoms                                   */
+    int32_t *overflow;           /* DEVICE int, set to 1 if a count left [-128, 127]; or NULL     */
+} mdb_jumpmat_args;
+
+int mdb_nojump_images_from_jumps(const mdb_jumpmat_args *args, void *stream);
+
 /* nojump, consumer side (pbc.py:235-247): out = x - n*box in float64 for one frame row. */
 int mdb_nojump_apply(const float *coords_row, const uint8_t *images_row, const double box[3],
                      int32_t n_atoms, double *out, void *stream);

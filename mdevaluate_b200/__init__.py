@@ -10,7 +10,7 @@ Drop-in for ``mdevaluate.correlation.shifted_correlation`` with ``msd`` / ``isf`
 
 Everything outside that path (file readers, selections, pair/tree analyses) is out of scope.
 """
-from . import correlation, coordinates, pbc, reader, utils, parallel, synthetic  # noqa: F401
+from . import autosave, checksum, correlation, coordinates, pbc, reader, utils, parallel, synthetic  # noqa: F401
 from .coordinates import Coordinates, CoordinateFrame  # noqa: F401
 from .reader import MemoryReader, NojumpError  # noqa: F401
 from ._cuda.lib import CudaPathError  # noqa: F401

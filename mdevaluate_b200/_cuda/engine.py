@@ -269,6 +269,34 @@ def nojump_scan(coords_seg, n_atoms, box0, box_is_f32, prev, cum, first_segment,
     _count(1)
 
 
+def images_from_jumps(indptr, frames, jumps, n_atoms, images, keep=None, overflow=None, stream=None):
+    """Image counts of the kept frames from jump matrices re-sorted by component column
+    (mdb_nojump_images_from_jumps).  All tensors are device tensors; ``keep`` int32 ascending or None."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    if indptr.dtype != torch.int64 or indptr.numel() != 3 * n_atoms + 1:
+        raise ValueError('indptr must be int64 with 3*n_atoms + 1 entries')
+    if frames.dtype != torch.int32 or jumps.dtype != torch.int8 or frames.numel() != jumps.numel():
+        raise ValueError('frames must be int32 and jumps int8, one entry per stored jump')
+    a = _lib.JumpMatArgs()
+    a.indptr = indptr.data_ptr()
+    a.nnz = frames.numel()
+    a.frames = frames.data_ptr() if a.nnz else None
+    a.jumps = jumps.data_ptr() if a.nnz else None
+    a.n_atoms = n_atoms
+    a.keep = keep.data_ptr() if keep is not None else None
+    a.n_keep = keep.numel() if keep is not None else images.shape[0]
+    a.images = images.data_ptr()
+    a.img_pitch = images.stride(0)
+    a.overflow = overflow.data_ptr() if overflow is not None else None
+    dev = images.device
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mdb_nojump_images_from_jumps(C.byref(a), C.c_void_p(st.cuda_stream)),
+                   'mdb_nojump_images_from_jumps')
+    _count(1)
+
+
 def nojump_apply(coords_row, images_row, box_diag, n_atoms):
     """float64 unwrapped frame ``x - n*box`` of one stored row (device tensor (3N,))."""
     torch = _lib.require_cuda()

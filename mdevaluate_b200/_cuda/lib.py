@@ -22,7 +22,7 @@ EXPORTS = (
     'mdb_last_error', 'mdb_abi_version', 'mdb_device_info',
     'mdb_corr_workspace_bytes', 'mdb_shifted_corr', 'mdb_corr_last_launches',
     'mdb_corr_profile', 'mdb_corr_last_kernel_ms',
-    'mdb_nojump_scan', 'mdb_nojump_apply',
+    'mdb_nojump_scan', 'mdb_nojump_apply', 'mdb_nojump_images_from_jumps',
     'mdb_dense_workspace_bytes', 'mdb_dense_corr',
 )
 
@@ -54,6 +54,14 @@ class NojumpArgs(C.Structure):
     ]
 
 
+class JumpMatArgs(C.Structure):
+    _fields_ = [
+        ('indptr', C.c_void_p), ('frames', C.c_void_p), ('jumps', C.c_void_p), ('nnz', C.c_int64),
+        ('n_atoms', C.c_int32), ('keep', C.c_void_p), ('n_keep', C.c_int32),
+        ('images', C.c_void_p), ('img_pitch', C.c_int64), ('overflow', C.c_void_p),
+    ]
+
+
 class DenseArgs(C.Structure):
     _fields_ = [
         ('coords', C.c_void_p), ('pitch', C.c_int64), ('images', C.c_void_p), ('img_pitch', C.c_int64),
@@ -79,6 +87,7 @@ def _declare(lib):
     lib.mdb_corr_profile.argtypes = [C.c_int]
     lib.mdb_corr_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
     lib.mdb_nojump_scan.argtypes = [C.POINTER(NojumpArgs), C.c_void_p]
+    lib.mdb_nojump_images_from_jumps.argtypes = [C.POINTER(JumpMatArgs), C.c_void_p]
     lib.mdb_dense_workspace_bytes.argtypes = [C.POINTER(DenseArgs), C.POINTER(C.c_size_t)]
     lib.mdb_dense_corr.argtypes = [C.POINTER(DenseArgs), C.c_void_p]
     lib.mdb_nojump_apply.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_void_p,

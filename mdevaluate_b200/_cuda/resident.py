@@ -55,6 +55,8 @@ class Resident:
                     self.atom_filter = np.nonzero(atom_filter)[0]
             else:
                 self.atom_filter = atom_filter.astype(np.int64)
+        self.n_atoms_all = m_all
+        self._jump_lists = None         # (matrices, indptr, frames, jumps) on the device
         self.n_atoms = m_all if self.atom_filter is None else len(self.atom_filter)
         self.dtype = np.asarray(first).dtype
         block = getattr(reader, 'device_block', None)
@@ -236,6 +238,44 @@ class Resident:
         if int(overflow.item()):
             raise _lib.CudaPathError('an atom crossed more than 127 periodic images; the one-byte image counts overflow')
 
+    # -- stored jump matrices (the reference's nojump cache) ----------------------------------------
+    def _matrices(self):
+        """``reader.nojump_matrixes`` if the reader carries them (loaded from a ``.nojump.npz`` cache or set by
+        ``generate_nojump_matrixes``), else None.  When present they DEFINE the unwrapping, as in the reference
+        (pbc.py:233-237 reads nothing else), and only the frames a schedule touches have to be read."""
+        mats = getattr(self.reader, '_nojump_matrixes', None)
+        if mats is None:
+            try:
+                mats = self.reader.nojump_matrixes
+            except Exception:
+                return None
+        if mats is None:
+            return None
+        if len(mats) != 3:
+            raise ValueError('nojump_matrixes must hold three matrices (x, y, z)')
+        for m in mats:
+            if m.shape[0] != self.n_frames or m.shape[1] != self.n_atoms_all:
+                raise ValueError('nojump matrix of shape %s does not fit a trajectory of %d frames x %d atoms'
+                                 % (m.shape, self.n_frames, self.n_atoms_all))
+        return mats
+
+    def _images_from_matrices(self, mats, images, keep=None):
+        """Fill ``images`` (rows = ``keep`` ascending, or every frame) from the jump matrices."""
+        torch = _lib.require_cuda()
+        from ..reader import jump_columns
+        lists = self._jump_lists
+        if lists is None or lists[0] is not mats:
+            indptr, frames, jumps = jump_columns(mats, self.atom_filter)
+            lists = self._jump_lists = (mats,) + tuple(torch.from_numpy(a).to(self.device)
+                                                       for a in (indptr, frames, jumps))
+        overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        keep_dev = None
+        if keep is not None:
+            keep_dev = torch.from_numpy(np.ascontiguousarray(keep, dtype=np.int32)).to(self.device)
+        engine.images_from_jumps(lists[1], lists[2], lists[3], self.n_atoms, images, keep=keep_dev, overflow=overflow)
+        if int(overflow.item()):
+            raise _lib.CudaPathError('an atom crossed more than 127 periodic images; the one-byte image counts overflow')
+
     def _ensure_dense_images(self):
         torch = _lib.require_cuda()
         store = self._ensure_dense()
@@ -243,7 +283,11 @@ class Resident:
             if store.coords.dtype != torch.float32:
                 raise _lib.CudaPathError('nojump needs float32 wrapped positions')
             images = torch.empty((self.n_frames, self.pitch), dtype=torch.uint8, device=self.device)
-            self._scan_all(images=images)
+            mats = self._matrices()
+            if mats is not None:
+                self._images_from_matrices(mats, images)
+            else:
+                self._scan_all(images=images)
             store.images = images
             store.box = self._box_rows(range(self.n_frames))
             store.box_const = self._box_const()
@@ -265,33 +309,42 @@ class Resident:
         f2r = np.full((self.n_frames,), -1, dtype=np.int32)
         f2r[frame_ids] = np.arange(n_rows, dtype=np.int32)
         n3 = 3 * self.n_atoms
-        if nojump:
+        mats = self._matrices() if nojump else None
+        if nojump and mats is None:
+            # no stored jumps: every frame streams through the scan, the kept ones are written as they pass
             coords = torch.empty((n_rows, self.pitch), dtype=torch.float32, device=self.device)
             images = torch.empty((n_rows, self.pitch), dtype=torch.uint8, device=self.device)
             out_row = torch.from_numpy(f2r).to(self.device)
             self._scan_all(images=images, out_row=out_row, coords_out=coords)
-            store = engine.DeviceStore(coords, self.n_atoms, images=images, box=self._box_rows(frame_ids),
-                                       frame_to_row=f2r, n_frames=self.n_frames, box_const=self._box_const())
+            return engine.DeviceStore(coords, self.n_atoms, images=images, box=self._box_rows(frame_ids),
+                                      frame_to_row=f2r, n_frames=self.n_frames, box_const=self._box_const())
+        tdt = torch.float32 if self.dtype == np.float32 else torch.float64
+        if nojump and tdt != torch.float32:
+            raise _lib.CudaPathError('nojump needs float32 wrapped positions (got %s)' % self.dtype)
+        coords = torch.empty((n_rows, self.pitch), dtype=tdt, device=self.device)
+        block = getattr(self.reader, 'device_block', None)
+        if block is not None and self.atom_filter is None:
+            idx = torch.from_numpy(frame_ids).to(self.device)
+            w = min(block.shape[1], self.pitch)
+            coords[:, :w] = block.index_select(0, idx)[:, :w]
         else:
-            tdt = torch.float32 if self.dtype == np.float32 else torch.float64
-            coords = torch.empty((n_rows, self.pitch), dtype=tdt, device=self.device)
-            block = getattr(self.reader, 'device_block', None)
-            if block is not None and self.atom_filter is None:
-                idx = torch.from_numpy(frame_ids).to(self.device)
-                w = min(block.shape[1], self.pitch)
-                coords[:, :w] = block.index_select(0, idx)[:, :w]
-            else:
-                chunk = max(1, (256 << 20) // (self.pitch * coords.element_size()))
-                host = torch.empty((min(chunk, n_rows), self.pitch), dtype=tdt).pin_memory()
-                for r0 in range(0, n_rows, chunk):
-                    r1 = min(n_rows, r0 + chunk)
-                    view = host[:r1 - r0, :n3].numpy().reshape(r1 - r0, self.n_atoms, 3)
-                    for r in range(r0, r1):
-                        pos = np.asarray(self.reader[int(frame_ids[r])].positions)
-                        view[r - r0] = pos if self.atom_filter is None else pos[self.atom_filter]
-                    coords[r0:r1].copy_(host[:r1 - r0], non_blocking=True)
-                    torch.cuda.current_stream(self.device).synchronize()
-            store = engine.DeviceStore(coords, self.n_atoms, frame_to_row=f2r, n_frames=self.n_frames)
+            # only the kept frames are read from the reader
+            chunk = max(1, (256 << 20) // (self.pitch * coords.element_size()))
+            host = torch.empty((min(chunk, n_rows), self.pitch), dtype=tdt).pin_memory()
+            for r0 in range(0, n_rows, chunk):
+                r1 = min(n_rows, r0 + chunk)
+                view = host[:r1 - r0, :n3].numpy().reshape(r1 - r0, self.n_atoms, 3)
+                for r in range(r0, r1):
+                    pos = np.asarray(self.reader[int(frame_ids[r])].positions)
+                    view[r - r0] = pos if self.atom_filter is None else pos[self.atom_filter]
+                coords[r0:r1].copy_(host[:r1 - r0], non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+        if not nojump:
+            return engine.DeviceStore(coords, self.n_atoms, frame_to_row=f2r, n_frames=self.n_frames)
+        images = torch.empty((n_rows, self.pitch), dtype=torch.uint8, device=self.device)
+        self._images_from_matrices(mats, images, keep=frame_ids)
+        store = engine.DeviceStore(coords, self.n_atoms, images=images, box=self._box_rows(frame_ids),
+                                   frame_to_row=f2r, n_frames=self.n_frames, box_const=self._box_const())
         return store
 
     # -- public ---------------------------------------------------------------------------------
@@ -304,8 +357,12 @@ class Resident:
         frame_ids = np.unique(np.asarray(frame_ids, dtype=np.int64))
         if frame_ids.size and (frame_ids[0] < 0 or frame_ids[-1] >= self.n_frames):
             raise IndexError('frame index out of range')
-        if not self.force_compact:
-            block = getattr(self.reader, 'device_block', None)
+        block = getattr(self.reader, 'device_block', None)
+        # a file-backed reader whose jumps are already stored: read only the frames the schedule touches
+        # (what the reference does, reader.py:254-286 + pbc.py:215-247) instead of the whole trajectory
+        sparse_io = (nojump and self._dense is None and block is None
+                     and getattr(self.reader, 'host_block', None) is None and self._matrices() is not None)
+        if not self.force_compact and not sparse_io:
             on_device = self._dense is not None or (block is not None and self.atom_filter is None)
             have_images = self._dense is not None and self._dense.images is not None
             extra = 0 if on_device else self._dense_bytes(False)
@@ -313,11 +370,16 @@ class Resident:
                 extra += self.pitch * self.n_frames
             if extra <= _mem_budget(torch, self.device):
                 return self._ensure_dense_images() if nojump else self._ensure_dense()
-        key = ('nojump' if nojump else 'raw', frame_ids.tobytes())
+        mode = 'nojump' if nojump else 'raw'
+        key = (mode, frame_ids.tobytes())
         store = self._compact.get(key)
         if store is None:
+            for (have_mode, _), have in self._compact.items():       # e.g. single frames of a schedule's store
+                if have_mode == mode and have.has_frames(frame_ids):
+                    return have
             logger.debug('building compact store of %d frames (nojump=%s)', len(frame_ids), nojump)
-            self._compact.clear()        # one compact store at a time: they are large
+            if len(frame_ids) > 4 or len(self._compact) > 16:
+                self._compact.clear()    # one schedule-sized compact store at a time: they are large
             store = self._build_compact(frame_ids, nojump)
             self._compact[key] = store
         return store

@@ -202,6 +202,11 @@ class Coordinates:
     def __len__(self):
         return len(self.frames)
 
+    def __checksum__(self):
+        # coordinates.py:295-296
+        from .checksum import checksum
+        return checksum(self.frames, self.atom_filter, self._slice, self.mode)
+
     def __repr__(self):
         return "Coordinates <{}>: {} atoms, mode={}".format(
             getattr(self.frames, 'filename', '?'), int(np.count_nonzero(self.atom_filter))

@@ -25,6 +25,8 @@ import numpy as np
 from ._cuda import engine
 from ._cuda import lib as _lib
 from ._cuda.lib import CudaPathError  # noqa: F401  (re-exported)
+from .autosave import autosave_data
+from .checksum import checksum
 from .utils import bin_rule, runningmean  # noqa: F401
 
 __all__ = ['log_indices', 'correlation', 'subensemble_correlation', 'multi_subensemble_correlation',
@@ -294,6 +296,11 @@ def _times(frames, idx):
     times = getattr(reader, 'times', None)
     if times is not None:
         return np.asarray(times)[idx] - np.asarray(times)[0]
+    from .coordinates import Coordinates
+    if isinstance(frames, Coordinates):
+        # CoordinateFrame.time is the reader frame's time (coordinates.py:117-119): no need to gather /
+        # unwrap the positions of every lag frame just to read it
+        return np.array([reader[int(i)].time for i in idx]) - reader[0].time
     return np.array([frames[int(i)].time for i in idx]) - frames[0].time       # correlation.py:151
 
 
@@ -449,13 +456,29 @@ def _average(values, n_origins, average):
     return result / n_origins
 
 
+def _fixed_checksum(function, version_nr):
+    """Key the autosave files of this package's own functions by name and version instead of by source
+    text (what checksum.version does, without wrapping: the functions are recognised by identity)."""
+    fixed = checksum(function.__name__, version_nr)
+    function.__checksum__ = lambda: fixed
+
+
+for _f in (log_indices, correlation, msd, isf, van_hove_self, non_gaussian, rotational_autocorrelation):
+    _fixed_checksum(_f, 1)
+del _f
+
+
+@autosave_data(nargs=2, kwargs_keys=(
+    'index_distribution', 'correlation', 'segments', 'window', 'skip', 'average'
+), version='shifted_correlation-1')
 def shifted_correlation(function, frames, index_distribution=log_indices, correlation=correlation,
-                        segments=10, window=0.5, skip=None, average=False,
-                        description=None, autoload=None):
+                        segments=10, window=0.5, skip=None, average=False):
     """Calculate the time series of a correlation function over shifted time origins.
 
-    Same call as the reference (correlation.py:86-201); ``description`` / ``autoload`` are the
-    keyword arguments its autosave decorator accepts (autosave.py:157-158) and are ignored.
+    Same call as the reference (correlation.py:83-201), including its autosave decorator: with
+    ``autosave.enable(dir)`` the result is written to / read from
+    ``shifted_correlation_<function>_<description>.npz``; ``description=`` and ``autoload=`` are the
+    decorator's extra keyword arguments (autosave.py:157-158).
 
     Returns ``(times, result)`` with ``result`` of shape ``(segments, lags[, bins])`` or, with
     ``average=True``, ``(lags[, bins])``.

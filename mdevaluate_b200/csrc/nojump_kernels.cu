@@ -331,6 +331,58 @@ __global__ void __launch_bounds__(kScanBulkThreads, 2) nojump_scan_bulk_kernel(c
     if (overflow && p.overflow) atomicExch(p.overflow, 1);
 }
 
+// Image counts from stored jump matrices (the reference's `.nojump.npz` cache, reader.py:189-241): the
+// three CSR matrices J_d (frames x atoms) arrive re-sorted by component column (CSC over the 3N interleaved
+// components c = 3*atom + d), so a thread owns 4 consecutive components, walks the kept frames in ascending
+// order and advances through each component's (frame, jump) list -- the prefix sum
+// `m[:step+1].sum(axis=0)` of pbc.py:235-237 -- writing one packed excess-128 word per kept frame
+// (a warp writes 128 contiguous bytes of the image row).  Jumps are rare (one entry per wall crossing),
+// so the lists are short and the kernel is bound by the image rows it writes.
+struct JumpMatDev {
+    const long long *indptr;
+    const int *frames;
+    const int8_t *jumps;
+    int n_vals;
+    const int *keep;
+    int n_keep;
+    uint8_t *images;
+    long long img_pitch;
+    int *overflow;
+    int vec;
+};
+
+__global__ void __launch_bounds__(kThreads) nojump_images_from_jumps_kernel(const JumpMatDev p) {
+    const int c0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (c0 >= p.n_vals) return;
+    long long pos[4], end[4];
+    int cum[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool live = c0 + j < p.n_vals;
+        pos[j] = live ? p.indptr[c0 + j] : 0;
+        end[j] = live ? p.indptr[c0 + j + 1] : 0;
+    }
+    bool overflow = false;
+    for (int r = 0; r < p.n_keep; ++r) {
+        const int frame = p.keep ? p.keep[r] : r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            while (pos[j] < end[j] && p.frames[pos[j]] <= frame) cum[j] += (int)p.jumps[pos[j]++];
+            overflow |= (cum[j] < -128) | (cum[j] > 127);
+        }
+        uint8_t *row = p.images + (long long)r * p.img_pitch + c0;
+        if (p.vec) {
+            *reinterpret_cast<uint32_t *>(row) =
+                pack4(cum[0] + MDB_IMAGE_BIAS, cum[1] + MDB_IMAGE_BIAS, cum[2] + MDB_IMAGE_BIAS, cum[3] + MDB_IMAGE_BIAS);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < p.n_vals) row[j] = (uint8_t)(cum[j] + MDB_IMAGE_BIAS);
+        }
+    }
+    if (overflow && p.overflow) atomicExch(p.overflow, 1);
+}
+
 __global__ void nojump_apply_kernel(const float *__restrict__ x, const uint8_t *__restrict__ n, double b0, double b1,
                                     double b2, int n_vals, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,6 +477,34 @@ extern "C" int mdb_nojump_apply(const float *coords_row, const uint8_t *images_r
     const int n_vals = 3 * n_atoms;
     nojump_apply_kernel<<<(n_vals + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         coords_row, images_row, box[0], box[1], box[2], n_vals, out);
+    MDB_CUDA_CHECK(cudaGetLastError());
+    return MDB_OK;
+}
+
+extern "C" int mdb_nojump_images_from_jumps(const mdb_jumpmat_args *a, void *stream) {
+    if (!a) return fail(MDB_ERR_ARGUMENT, "args is NULL");
+    if (a->n_atoms <= 0 || a->n_keep < 0) return fail(MDB_ERR_ARGUMENT, "bad n_atoms / n_keep");
+    if (!a->indptr || !a->images) return fail(MDB_ERR_ARGUMENT, "indptr and images are required");
+    if (a->nnz < 0 || (a->nnz > 0 && (!a->frames || !a->jumps)))
+        return fail(MDB_ERR_ARGUMENT, "frames and jumps are required when nnz > 0");
+    if (a->img_pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "img_pitch < 3*n_atoms");
+    if (a->n_keep == 0) return MDB_OK;
+    JumpMatDev p;
+    p.indptr = reinterpret_cast<const long long *>(a->indptr);
+    p.frames = a->frames;
+    p.jumps = a->jumps;
+    p.n_vals = 3 * a->n_atoms;
+    p.keep = a->keep;
+    p.n_keep = a->n_keep;
+    p.images = a->images;
+    p.img_pitch = a->img_pitch;
+    p.overflow = a->overflow;
+    // whole words only when every row is word-aligned and the padding can take the last partial word
+    p.vec = (reinterpret_cast<uintptr_t>(a->images) % 4 == 0) && (a->img_pitch % 4 == 0) &&
+            (a->img_pitch >= (p.n_vals + 3) / 4 * 4);
+    const int n_threads = (p.n_vals + 3) / 4;
+    nojump_images_from_jumps_kernel<<<(n_threads + kThreads - 1) / kThreads, kThreads, 0,
+                                      static_cast<cudaStream_t>(stream)>>>(p);
     MDB_CUDA_CHECK(cudaGetLastError());
     return MDB_OK;
 }

@@ -10,10 +10,15 @@ trajectory that lives in host memory (NumPy, optionally pinned) or already in HB
 """
 from __future__ import annotations
 
+import builtins
+import os
+import pickle
 from collections import namedtuple
+from zipfile import BadZipFile
 
 import numpy as np
 
+from .checksum import checksum
 from .logging import logger
 
 
@@ -91,6 +96,17 @@ class MemoryReader:
                       else np.asarray(times, dtype=np.float64))
         if self.times.shape != (self.n_frames,):
             raise ValueError('times must have shape (T,)')
+        # like BaseReader.__init__ (reader.py:283-285): pick up a stored nojump cache next to the trajectory
+        if not filename.startswith('<') and os.path.exists(nojump_filename(self)):
+            load_nojump_matrixes(self)
+
+    def __checksum__(self):
+        """Identity of the trajectory for the on-disk caches (the reference hashes the file name and the
+        frame index of its file reader, reader.py:288-295): name, shape, box and the first and last frame."""
+        def frame_bytes(i):
+            return np.ascontiguousarray(self[i].positions).tobytes()
+        return checksum(self.filename, str((self.n_frames, self.n_atoms)), np.asarray(self.box_diag),
+                        frame_bytes(0), frame_bytes(self.n_frames - 1))
 
     # -- reader protocol ---------------------------------------------------------------------
     def __len__(self):
@@ -142,15 +158,152 @@ def parse_jumps(trajectory):
 
 
 def generate_nojump_matrixes(trajectory):
-    """Create the three CSR jump matrices and attach them to the reader (reader.py:189-202).
-
-    The on-disk ``.nojump.npz`` cache of the reference (reader.py:205-241) is not written here.
-    """
+    """Create the three CSR jump matrices, attach them to the reader and -- when the trajectory has a
+    file name -- store them in the reference's cache format next to it (reader.py:189-202)."""
     from scipy import sparse
     logger.info('generate Nojump Matrixes for: {}'.format(trajectory))
     jump_data = parse_jumps(trajectory)
     n_frames = len(trajectory)
     n_atoms = trajectory._resident().n_atoms
-    trajectory.frames.nojump_matrixes = tuple(
+    reader = trajectory.frames
+    reader.nojump_matrixes = tuple(
         sparse.csr_matrix((np.array(m.data), (m.row, m.col)), shape=(n_frames, n_atoms)) for m in jump_data
     )
+    if not str(getattr(reader, 'filename', '<memory>')).startswith('<'):
+        save_nojump_matrixes(reader)
+
+
+# --------------------------------------------------------------------------------------------------
+# the on-disk nojump cache `.{trajectory}.nojump.npz` (reader.py:125-241)
+# --------------------------------------------------------------------------------------------------
+CSR_ATTRS = ('data', 'indices', 'indptr')
+NOJUMP_MAGIC = 2016
+
+
+def is_writeable(fname):
+    """Whether a file can be created next to ``fname`` -- tested by creating one (reader.py:125-140)."""
+    fdir = os.path.dirname(fname)
+    if not os.access(fdir, os.W_OK):
+        return False
+    probe = os.path.join(fdir, str(np.random.randint(999999999)))
+    while os.path.exists(probe):
+        probe = os.path.join(fdir, str(np.random.randint(999999999)))
+    try:
+        with builtins.open(probe, 'w'):
+            pass
+        os.remove(probe)
+        return True
+    except PermissionError:
+        return False
+
+
+def nojump_filename(reader):
+    """``<dir>/.<trajectory>.nojump.npz``, or the same below ``~/.mdevaluate/nojump`` when the trajectory's
+    directory is read-only (reader.py:143-158)."""
+    directory, fname = os.path.split(reader.filename)
+    local = os.path.join(directory, '.{}.nojump.npz'.format(fname))
+    if os.path.exists(local) or is_writeable(directory):
+        return local
+    fallback = os.path.join(os.path.join(os.environ['HOME'], '.mdevaluate/nojump'), directory.lstrip('/'),
+                            '.{}.nojump.npz'.format(local))
+    logger.info('Saving nojump to {}, since original location is not writeable.'.format(fallback))
+    os.makedirs(os.path.dirname(fallback), exist_ok=True)
+    return fallback
+
+
+def _nojump_checksum(reader):
+    return checksum(NOJUMP_MAGIC, checksum(reader))
+
+
+def save_nojump_matrixes(reader, matrixes=None):
+    """Write the jump matrices in the reference's format (reader.py:205-213): ``checksum``, ``shape`` and
+    ``data_d / indices_d / indptr_d`` of the three CSR matrices, uncompressed npz."""
+    if matrixes is None:
+        matrixes = reader.nojump_matrixes
+    data = {'checksum': _nojump_checksum(reader)}
+    for d, mat in enumerate(matrixes):
+        data['shape'] = mat.shape
+        for attr in CSR_ATTRS:
+            data['{}_{}'.format(attr, d)] = getattr(mat, attr)
+    np.savez(nojump_filename(reader), **data)
+
+
+def read_nojump_file(filename):
+    """``(checksum, (Jx, Jy, Jz))`` of a ``.nojump.npz`` file written by this package or by the reference.
+    The checksum is a 160-bit Python integer, which NumPy stores as a pickled object entry: the file is
+    opened with ``allow_pickle`` -- load only cache files you (or the reference) wrote."""
+    from scipy import sparse
+    with np.load(filename, allow_pickle=True) as data:
+        stored = data['checksum'][()] if 'checksum' in data else None
+        shape = tuple(int(n) for n in data['shape'])
+        mats = tuple(
+            sparse.csr_matrix(tuple(data['{}_{}'.format(attr, d)] for attr in CSR_ATTRS), shape=shape)
+            for d in range(3)
+        )
+    return stored, mats
+
+
+def load_nojump_matrixes(reader, filename=None, verify=True):
+    """Attach the stored jump matrices to ``reader`` if the file belongs to it (reader.py:216-241): a
+    file with another checksum is ignored, an unreadable one is removed.  ``filename`` reads a specific
+    file; ``verify=False`` accepts a foreign checksum (a cache the reference wrote through its own file
+    reader hashes that reader's frame index, which only the reference can recompute).  Returns True when
+    the matrices were attached."""
+    zipname = nojump_filename(reader) if filename is None else filename
+    try:
+        stored, mats = read_nojump_file(zipname)
+    except (AttributeError, BadZipFile, OSError, KeyError, ValueError, EOFError, pickle.UnpicklingError):
+        logger.info('Removing zip-File: %s', zipname)
+        if filename is None:
+            os.remove(zipname)
+        return False
+    if verify and stored != _nojump_checksum(reader):
+        logger.info('Invlaid Nojump Data: {}'.format(zipname))
+        return False
+    reader.nojump_matrixes = mats
+    logger.info('Loaded Nojump Matrixes: {}'.format(zipname))
+    return True
+
+
+def correct_nojump_matrixes_for_whole(trajectory):
+    """Row 0 of the matrices := jumps of frame 0 against ``frame0.whole`` (reader.py:244-251)."""
+    reader = trajectory.frames
+    frame = trajectory[0]
+    box = frame.box.diagonal()
+    cor = ((frame - frame.whole) / box).round().astype(np.int8)
+    mats = tuple(m.tolil() for m in reader.nojump_matrixes)
+    for d in range(3):
+        mats[d][0] = cor[:, d]
+    reader.nojump_matrixes = tuple(m.tocsr() for m in mats)
+    if not str(getattr(reader, 'filename', '<memory>')).startswith('<'):
+        save_nojump_matrixes(reader)
+
+
+def jump_columns(matrixes, atom_filter=None):
+    """The three jump matrices (frames x atoms, any scipy sparse format) as ONE column-compressed list over
+    the interleaved components ``c = 3*atom + d`` -- the layout ``mdb_nojump_images_from_jumps`` walks:
+    ``indptr`` int64 ``(3N+1,)``, ``frames`` int32 ``(nnz,)`` ascending inside a column, ``jumps`` int8.
+    ``atom_filter`` (index array) selects columns first, like ``m[..., selection]`` in pbc.py:243."""
+    from scipy import sparse
+    cols = []
+    for m in matrixes:
+        m = sparse.csc_matrix(m)
+        if atom_filter is not None:
+            m = m[:, np.asarray(atom_filter)]
+        m.sort_indices()
+        if m.nnz and (np.abs(m.data.astype(np.int64)) > 127).any():
+            raise ValueError('jump matrices must hold int8 jumps')
+        cols.append(m)
+    n_atoms = cols[0].shape[1]
+    counts = np.stack([np.diff(m.indptr) for m in cols], axis=1).reshape(-1).astype(np.int64)
+    indptr = np.zeros(3 * n_atoms + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    frames = np.empty(int(indptr[-1]), dtype=np.int32)
+    jumps = np.empty(int(indptr[-1]), dtype=np.int8)
+    for d, m in enumerate(cols):
+        per_col = np.diff(m.indptr)
+        col_of = np.repeat(np.arange(n_atoms, dtype=np.int64), per_col)
+        dest = indptr[3 * col_of + d] + (np.arange(m.nnz, dtype=np.int64) - m.indptr[col_of])
+        frames[dest] = m.indices
+        jumps[dest] = m.data
+    return indptr, frames, jumps

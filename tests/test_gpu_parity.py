@@ -551,3 +551,169 @@ def test_store_released_without_garbage_collector(small, md):
         assert res() is None and store() is None
     finally:
         gc.enable()
+
+
+# ---- stored jump matrices (the reference's .nojump.npz cache) and autosave -----------------------------
+class FileLikeReader:
+    """Frames only through ``reader[i]`` (like a trajectory file), counting the reads."""
+
+    def __init__(self, md, g, filename='<file-like>'):
+        self._md, self._g = md, g
+        self.filename = filename
+        self.reads = []
+        self.nojump_matrixes = None
+
+    def __len__(self):
+        return len(self._g['pos'])
+
+    def __getitem__(self, i):
+        i = int(i)
+        self.reads.append(i)
+        box = self._g['box']
+        return self._md.reader.MemoryFrame(self._g['pos'][i], np.diag(box).astype(box.dtype), self._g['times'][i], i)
+
+
+def _golden_file(name):
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name)
+
+
+def _ref_matrices(md):
+    return md.reader.read_nojump_file(_golden_file('ref.nojump.npz'))[1]
+
+
+def test_stored_jump_matrices_replace_the_scan(small, md):
+    """With the reference's jump-matrix cache attached only the frames of the schedule are read, and the
+    image counts / unwrapped frames / correlations are those of the scan (bit-exact integers)."""
+    g, _ = small
+    reader = FileLikeReader(md, g)
+    reader.nojump_matrixes = _ref_matrices(md)
+    coords = md.Coordinates(reader)
+    T = len(coords)
+    t, r = md.correlation.shifted_correlation(md.correlation.msd, coords.nojump, segments=12, window=0.4)
+    np.testing.assert_array_equal(t, g['t_nojump'])
+    close(r, g['msd_nojump'], scale=float(np.nanmax(g['msd_nojump'])), rtol=1e-11, atol=1e-13)
+    starts, idx = md.correlation._schedule(coords, md.correlation.log_indices, 12, 0.4, None)
+    needed = set((starts[:, None] + idx[None, :]).ravel().tolist())
+    assert set(reader.reads) <= needed | {0} and len(set(reader.reads)) < T
+    # image counts of the kept frames
+    res = coords._resident()
+    keep = np.array(sorted(needed))
+    store = res.store_for(keep, nojump=True)
+    rows = store.rows_for(keep).astype(np.int64)
+    n3 = 3 * res.n_atoms
+    images = store.images[:, :n3].cpu().numpy().astype(np.int64)[rows].reshape(len(keep), -1, 3) - 128
+    np.testing.assert_array_equal(images, np.cumsum(g['jumps'], axis=0, dtype=np.int64)[keep])
+    # unwrapped frames, also one that is not part of the schedule's store
+    for i in (0, 17, 100, 239):
+        np.testing.assert_array_equal(np.asarray(coords.nojump[i]), g['nojump_%d' % i])
+
+
+def test_stored_jump_matrices_dense_selection_and_authority(small, md):
+    g, _ = small
+    mats = _ref_matrices(md)
+    want = np.cumsum(g['jumps'], axis=0, dtype=np.int64)
+    # in-memory trajectory: dense residency, every frame's counts from the matrices
+    reader = md.MemoryReader(g['pos'], g['box'], g['times'])
+    reader.nojump_matrixes = mats
+    coords = md.Coordinates(reader)
+    store = coords._resident().store_for(np.arange(len(coords)), nojump=True)
+    images = store.images[:, :3 * 96].cpu().numpy().astype(np.int64).reshape(len(coords), 96, 3) - 128
+    np.testing.assert_array_equal(images, want)
+    # behind an atom selection (columns of the matrices are picked like m[..., selection], pbc.py:243)
+    sel = g['sel']
+    fr = FileLikeReader(md, g)
+    fr.nojump_matrixes = mats
+    t, r = md.correlation.shifted_correlation(md.correlation.msd, md.Coordinates(fr, atom_filter=sel).nojump,
+                                              segments=6, window=0.4)
+    close(r, g['msd_sel'], scale=float(np.nanmax(g['msd_sel'])), rtol=1e-11, atol=1e-13)
+    # the matrices are authoritative: an extra jump in row 0 (e.g. correct_nojump_matrixes_for_whole) shifts
+    # that component's count in every frame
+    from scipy import sparse
+    extra = sparse.lil_matrix(mats[0].shape, dtype=np.int8)
+    extra[0, 3] = 1
+    changed = md.MemoryReader(g['pos'], g['box'], g['times'])
+    changed.nojump_matrixes = ((mats[0] + extra.tocsr()).astype(np.int8), mats[1], mats[2])
+    store2 = md.Coordinates(changed)._resident().store_for(np.arange(len(coords)), nojump=True)
+    images2 = store2.images[:, :3 * 96].cpu().numpy().astype(np.int64).reshape(len(coords), 96, 3) - 128
+    shifted = want.copy()
+    shifted[:, 3, 0] += 1
+    np.testing.assert_array_equal(images2, shifted)
+    # a matrix that does not fit the trajectory is refused
+    bad = md.MemoryReader(g['pos'], g['box'], g['times'])
+    bad.nojump_matrixes = tuple(m[:, :50] for m in mats)
+    with pytest.raises(ValueError):
+        md.Coordinates(bad)._resident().store_for(np.arange(4), nojump=True)
+
+
+def test_images_from_jumps_unaligned_rows_and_overflow(small, md):
+    """The scalar store path (rows that are not word-aligned), kept-frame subsets and the overflow flag."""
+    import torch
+    from mdevaluate_b200._cuda import engine
+    g, _ = small
+    mats = _ref_matrices(md)
+    indptr, frames, jumps = (torch.from_numpy(a).cuda() for a in md.reader.jump_columns(mats))
+    want = np.cumsum(g['jumps'], axis=0, dtype=np.int64).reshape(len(g['pos']), -1)
+    keep = np.unique(np.random.default_rng(11).integers(0, len(g['pos']), 50)).astype(np.int32)
+    for pitch in (288, 289, 291):
+        buf = torch.full((len(keep) * pitch + 1,), 7, dtype=torch.uint8, device='cuda')
+        images = buf[1:].view(len(keep), pitch) if pitch == 288 else buf[:len(keep) * pitch].view(len(keep), pitch)
+        flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        engine.images_from_jumps(indptr, frames, jumps, 96, images, keep=torch.from_numpy(keep).cuda(), overflow=flag)
+        got = images.cpu().numpy()
+        np.testing.assert_array_equal(got[:, :288].astype(np.int64) - 128, want[keep])
+        assert (got[:, 288:] == 7).all() and int(flag.item()) == 0
+    big = jumps.clone()
+    big[:] = 100                                            # two crossings of 100 images: past one byte
+    images = torch.empty((len(g['pos']), 288), dtype=torch.uint8, device='cuda')
+    flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+    engine.images_from_jumps(indptr, frames, big, 96, images, overflow=flag)
+    assert int(flag.item()) == 1
+
+
+def test_generate_nojump_matrixes_writes_the_cache(small, md, tmp_path):
+    """generate_nojump_matrixes on a named trajectory: GPU scan -> CSR matrices -> `.traj.nojump.npz` in the
+    reference's layout; a new reader of the same trajectory picks the file up (reader.py:189-202, 283-285)."""
+    g, _ = small
+    name = str(tmp_path / 'walk.xtc')
+    coords = md.Coordinates(md.MemoryReader(g['pos'], g['box'], g['times'], filename=name))
+    md.reader.generate_nojump_matrixes(coords)
+    path = tmp_path / '.walk.xtc.nojump.npz'
+    assert path.exists()
+    with np.load(path, allow_pickle=True) as a, np.load(_golden_file('ref.nojump.npz'), allow_pickle=True) as b:
+        for key in b.files:
+            if key != 'checksum':
+                assert a[key].dtype == b[key].dtype and np.array_equal(a[key], b[key]), key
+    again = md.MemoryReader(g['pos'], g['box'], g['times'], filename=name)
+    dense = np.stack([m.toarray() for m in again.nojump_matrixes], axis=-1)
+    np.testing.assert_array_equal(dense, g['jumps'])
+    t, r = md.correlation.shifted_correlation(md.correlation.msd, md.Coordinates(again).nojump, segments=12, window=0.4)
+    close(r, g['msd_nojump'], scale=float(np.nanmax(g['msd_nojump'])), rtol=1e-11, atol=1e-13)
+
+
+def test_autosave_round_trip(small, md, tmp_path):
+    """autosave.enable(): the first call computes on the GPU and writes shifted_correlation_<fn>_<desc>.npz,
+    the second returns the stored arrays without touching the GPU (doc/special/autosave.rst)."""
+    from mdevaluate_b200._cuda import engine
+    g, _ = small
+    coords = md.Coordinates(md.MemoryReader(g['pos'], g['box'], g['times'], filename=str(tmp_path / 'walk.xtc')))
+    fn = partial(md.correlation.isf, q=22.7)
+    md.autosave.enable('data', verbose=False)
+    try:
+        t1, r1 = md.correlation.shifted_correlation(fn, coords.nojump, segments=12, window=0.4, average=True,
+                                                    description='OW')
+        assert (tmp_path / 'data' / 'shifted_correlation_isf_OW.npz').exists()
+        before = engine.launches()
+        t2, r2 = md.correlation.shifted_correlation(fn, coords.nojump, segments=12, window=0.4, average=True,
+                                                    description='OW')
+        assert engine.launches() == before
+        np.testing.assert_array_equal(t1, t2)
+        np.testing.assert_array_equal(r1, r2)
+        t3, r3 = md.correlation.shifted_correlation(fn, coords.nojump, segments=12, window=0.4, description='OW')
+        assert engine.launches() > before and r3.shape == g['isf_nojump'].shape     # other arguments: recomputed
+        close(r3, g['isf_nojump'])
+        t4, r4 = md.correlation.shifted_correlation(fn, coords.nojump, segments=12, window=0.4, description='OW')
+        np.testing.assert_array_equal(r3, r4)                                        # ragged (times, result) file
+        np.testing.assert_array_equal(t3, t4)
+    finally:
+        md.autosave.disable()
