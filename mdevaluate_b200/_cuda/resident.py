@@ -23,8 +23,11 @@ from ..logging import logger
 
 
 def _mem_budget(torch, device):
+    """Bytes a new store may take: 70 % of what the driver reports free plus what torch's allocator holds
+    cached but unused (a store that was just released is still 'reserved' for the driver)."""
     free, _total = torch.cuda.mem_get_info(device)
-    return int(free * 0.70)
+    cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return int((free + max(0, cached)) * 0.70)
 
 
 class Resident:
@@ -55,6 +58,10 @@ class Resident:
                     self.atom_filter = np.nonzero(atom_filter)[0]
             else:
                 self.atom_filter = atom_filter.astype(np.int64)
+        # a selection that is one contiguous run of atoms is copied as a slice, not gathered
+        self._filter_run = None
+        if self.atom_filter is not None and len(self.atom_filter) and np.all(np.diff(self.atom_filter) == 1):
+            self._filter_run = (int(self.atom_filter[0]), int(self.atom_filter[-1]) + 1)
         self.n_atoms_all = m_all
         self._jump_lists = None         # (matrices, indptr, frames, jumps) on the device
         self.n_atoms = m_all if self.atom_filter is None else len(self.atom_filter)
@@ -110,6 +117,8 @@ class Resident:
         if block is not None:
             if self.atom_filter is None:
                 np.copyto(view, block[t0:t1], casting='same_kind')
+            elif self._filter_run is not None:
+                np.copyto(view, block[t0:t1, self._filter_run[0]:self._filter_run[1]], casting='same_kind')
             else:
                 np.take(block[t0:t1], self.atom_filter, axis=1, out=view)
         else:
@@ -121,11 +130,14 @@ class Resident:
         """Yield ``(t0, t1, device_tensor)`` over the whole trajectory, double-buffered."""
         torch = _lib.require_cuda()
         block = getattr(self.reader, 'device_block', None)
-        if block is not None and self.atom_filter is None and block.dtype == torch.float32:
+        if block is not None and block.dtype == torch.float32 and (self.atom_filter is None or self._filter_run):
+            # already in HBM: views of the block (all atoms, or the columns of one contiguous run of atoms)
+            c0, c1 = (0, block.shape[1]) if self.atom_filter is None else (3 * self._filter_run[0],
+                                                                            3 * self._filter_run[1])
             seg = max(1, min(self.n_frames, (2 << 30) // (block.stride(0) * 4)))
             for t0 in range(0, self.n_frames, seg):
                 t1 = min(self.n_frames, t0 + seg)
-                yield t0, t1, block[t0:t1]
+                yield t0, t1, block[t0:t1, c0:c1]
             return
         if self.dtype != np.float32:
             raise _lib.CudaPathError('nojump needs float32 wrapped positions (got %s)' % self.dtype)
@@ -133,12 +145,7 @@ class Resident:
         main = torch.cuda.current_stream(self.device)
         copy_stream = torch.cuda.Stream(self.device)
         n3 = 3 * self.n_atoms
-        direct = None
-        host_block = getattr(self.reader, 'host_block', None)
-        if host_block is not None and self.atom_filter is None and host_block.flags.c_contiguous:
-            as_t = torch.from_numpy(host_block).view(self.n_frames, n3)
-            if as_t.is_pinned():
-                direct = as_t
+        direct = self._pinned_block()
         pinned = ([] if direct is not None else
                   [torch.empty((seg, self.pitch), dtype=torch.float32).pin_memory() for _ in range(2)])
         staged = [torch.empty((seg, self.pitch), dtype=torch.float32, device=self.device) for _ in range(2)]
@@ -173,6 +180,48 @@ class Resident:
             consumed[slot].record(main)
         main.synchronize()
 
+    def _pinned_block(self):
+        """The whole host trajectory as a page-locked ``(T, 3N)`` tensor if it can be DMA'd as it is."""
+        torch = _lib.require_cuda()
+        host_block = getattr(self.reader, 'host_block', None)
+        if host_block is None or self.atom_filter is not None or not host_block.flags.c_contiguous:
+            return None
+        if host_block.dtype != np.float32:
+            return None
+        as_t = torch.from_numpy(host_block).view(self.n_frames, 3 * self.n_atoms)
+        return as_t if as_t.is_pinned() else None
+
+    def _upload_rows(self, coords):
+        """Host trajectory -> the rows of ``coords`` (float32), entirely on a copy stream: nothing is queued
+        on the compute stream, so the upload of one atom slab runs under the kernel of the previous one.
+        The caller guarantees that no kernel still reads memory ``coords`` may have been carved from."""
+        torch = _lib.require_cuda()
+        main = torch.cuda.current_stream(self.device)
+        copy_stream = torch.cuda.Stream(self.device)
+        n3 = 3 * self.n_atoms
+        seg = self._segment_frames()
+        starts = range(0, self.n_frames, seg)
+        direct = self._pinned_block()
+        if direct is not None:
+            with torch.cuda.stream(copy_stream):
+                for t0 in starts:
+                    t1 = min(self.n_frames, t0 + seg)
+                    coords[t0:t1, :n3].copy_(direct[t0:t1], non_blocking=True)
+        else:
+            pinned = [torch.empty((seg, self.pitch), dtype=torch.float32).pin_memory() for _ in range(2)]
+            sent = [torch.cuda.Event() for _ in range(2)]
+            for k, t0 in enumerate(starts):
+                t1 = min(self.n_frames, t0 + seg)
+                slot = k % 2
+                if k >= 2:
+                    sent[slot].synchronize()          # the staging buffer has left the host
+                self._host_segment(t0, t1, pinned[slot])
+                with torch.cuda.stream(copy_stream):
+                    coords[t0:t1].copy_(pinned[slot][:t1 - t0], non_blocking=True)
+                    sent[slot].record(copy_stream)
+        copy_stream.synchronize()                     # only the copies: the compute stream keeps running
+        main.wait_stream(copy_stream)
+
     # -- dense residency -------------------------------------------------------------------------
     def _dense_bytes(self, with_images):
         per = self.pitch * 4 + (self.pitch if with_images else 0)
@@ -190,10 +239,11 @@ class Resident:
                 raise _lib.CudaPathError('positions must be float32 or float64')
             tdt = torch.float32 if self.dtype == np.float32 else torch.float64
             coords = torch.empty((self.n_frames, self.pitch), dtype=tdt, device=self.device)
-            if tdt == torch.float32:
-                for t0, t1, seg in self._segments():
-                    coords[t0:t1].copy_(seg, non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
+            if tdt == torch.float32 and block is not None and self._filter_run:
+                for t0, t1, seg in self._segments():          # a contiguous run of atoms of a device block
+                    coords[t0:t1, :seg.shape[1]].copy_(seg, non_blocking=True)
+            elif tdt == torch.float32:
+                self._upload_rows(coords)
             else:
                 n3 = 3 * self.n_atoms
                 for t in range(self.n_frames):
@@ -348,6 +398,20 @@ class Resident:
         return store
 
     # -- public ---------------------------------------------------------------------------------
+    def on_device(self):
+        """Whether the trajectory already lives in HBM (a device block or a dense store)."""
+        block = getattr(self.reader, 'device_block', None)
+        return self._dense is not None or (block is not None and self.atom_filter is None)
+
+    def memory_budget(self):
+        return _mem_budget(_lib.require_cuda(), self.device)
+
+    def atom_slab(self, a0, a1):
+        """A Resident over atoms [a0, a1) of this selection (out-of-core passes, slab by slab).  Not cached
+        on the reader: its HBM store lives as long as the caller holds it."""
+        own = np.arange(self.n_atoms_all) if self.atom_filter is None else self.atom_filter
+        return Resident(self.reader, own[a0:a1], device=self.device)
+
     def store_for(self, frame_ids, nojump):
         """A DeviceStore holding (at least) ``frame_ids``; with image counts if ``nojump``."""
         if (self._dense is not None and not self.force_compact

@@ -343,6 +343,38 @@ def _schedule(frames, index_distribution, segments, window, skip):
 
 
 DENSE_MIN_PAIRS = 2048          # below this the streaming kernel is just as good
+DENSE_SLAB_ATOMS = None         # atoms per slab of an out-of-core dense run; None = from the free HBM
+
+
+def _dense_slabs(res, nojump):
+    """Atom ranges of one dense pass.  A trajectory that is (or fits) in HBM is one slab.  A larger one --
+    BASELINE config 5: 200 000 atoms x 50 000 frames = 120 GB of frames + 30 GB of image counts -- is cut
+    into atom slabs (atoms are independent, the per-lag sums add up): every slab's rows stream from the
+    host in time segments while the tiled kernel still works on the previous slab, so two slabs are
+    resident at a time."""
+    n = res.n_atoms
+    slab = DENSE_SLAB_ATOMS
+    if slab is None:
+        if res.on_device():
+            return [(0, n)]
+        per_atom = res.n_frames * (12 + (3 if nojump else 0))
+        budget = res.memory_budget()
+        if per_atom * n <= budget:
+            return [(0, n)]
+        slab = budget // 2 // per_atom
+    slab = max(1024, int(slab) // 1024 * 1024)          # whole 1024-atom tiles (bulk copies, alignment)
+    return [(a0, min(n, a0 + slab)) for a0 in range(0, n, slab)]
+
+
+def _dense_sums(res, nojump, spec, first_frame, last_frame, first_origin, step, S, L):
+    """Device ``(L, 2)`` sums of one resident trajectory (or atom slab); None if its rows are unaligned."""
+    store = res.store_for(np.arange(first_frame, last_frame + 1), nojump=nojump)
+    if not nojump:
+        store = store.without_images()
+    if store.coords.stride(0) % 4 or store.coords.data_ptr() % 16 or (
+            store.images is not None and (store.images.stride(0) % 4 or store.images.data_ptr() % 4)):
+        return None                                   # unaligned rows: the streaming kernel has a scalar path
+    return engine.dense_device(store, first_origin, step, S, 0, L, spec.corr.flags, q=spec.corr.q)
 
 
 def _dense_average(frames, spec, start_frames, idx):
@@ -368,14 +400,33 @@ def _dense_average(frames, spec, start_frames, idx):
     nojump = frames.mode == 'nojump'
     if res.dtype != np.float32:
         return None
-    store = res.store_for(np.arange(start_frames[0], start_frames[-1] + idx[-1] + 1), nojump=nojump)
-    if not nojump:
-        store = store.without_images()
-    if store.coords.stride(0) % 4 or store.coords.data_ptr() % 16 or (
-            store.images is not None and (store.images.stride(0) % 4 or store.images.data_ptr() % 4)):
-        return None                                   # unaligned rows: the streaming kernel has a scalar path
     # the origin of segment s is the FIRST frame of its iterator, start_s + idx[0] (correlation.py:21-24)
-    sums = engine.dense_device(store, start_frames[0] + idx[0], step, S, 0, L, spec.corr.flags, q=spec.corr.q)
+    span = (int(start_frames[0]), int(start_frames[-1] + idx[-1]), int(start_frames[0] + idx[0]), step, S, L)
+    slabs = _dense_slabs(res, nojump)
+    if len(slabs) == 1:
+        sums = _dense_sums(res, nojump, spec, *span)
+        if sums is None:
+            return None
+    else:
+        torch = _lib.require_cuda()
+        sums = None
+        in_flight = []                                # (event after the slab's kernel, the slab)
+        for a0, a1 in slabs:
+            if len(in_flight) == 2:
+                # two slabs are resident: the older one's kernel must be through before its rows are
+                # released (the next slab's upload, on another stream, may be carved from them)
+                kernel_done, old = in_flight.pop(0)
+                kernel_done.synchronize()
+                del old
+            slab = res.atom_slab(a0, a1)
+            part = _dense_sums(slab, nojump, spec, *span)       # uploads under the previous slab's kernel
+            if part is None:
+                return None
+            sums = part if sums is None else sums.add_(part)
+            kernel_done = torch.cuda.Event()
+            kernel_done.record(torch.cuda.current_stream(res.device))
+            in_flight.append((kernel_done, slab))
+        del in_flight
     n_atoms = res.n_atoms
     if frames.comm is not None:
         import torch.distributed as dist

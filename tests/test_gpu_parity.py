@@ -501,6 +501,56 @@ def test_dense_kernel_on_a_compact_store(md, monkeypatch):
     close(got, ref)
 
 
+@pytest.mark.parametrize('source', ['host', 'pinned', 'device'])
+def test_dense_schedule_in_atom_slabs(md, monkeypatch, source):
+    """Out-of-core dense pass (BASELINE config 5 is larger than HBM): atom slabs whose rows stream from the
+    host while the previous slab's kernel runs give the sums of the single pass."""
+    import torch
+    from mdevaluate_b200.synthetic import random_walk
+    from mdevaluate_b200._cuda import engine
+    N, T = 2500, 200
+    pos, box, times = random_walk(N, T, seed=9, sigma=0.08, box=2.5)
+    c = md.correlation
+    dense = lambda a, b: np.arange(a, b)
+    kw = dict(segments=T // 2, window=0.5, average=True, index_distribution=dense)
+
+    def make():
+        if source == 'host':
+            return md.Coordinates.from_arrays(pos, box, times)
+        if source == 'pinned':
+            pinned = torch.from_numpy(pos).pin_memory()
+            return md.Coordinates.from_arrays(pinned.numpy(), box, times)
+        pitch = engine.row_pitch(N)
+        block = torch.zeros((T, pitch), dtype=torch.float32, device='cuda')
+        block[:, :3 * N] = torch.from_numpy(pos.reshape(T, 3 * N)).cuda()
+        return md.Coordinates.from_arrays(block, box, times, n_atoms=N)
+
+    calls = []
+    real = engine.dense_device
+    monkeypatch.setattr(engine, 'dense_device', lambda *a, **k: (calls.append(a[0].n_atoms), real(*a, **k))[1])
+    unw = orc.UnwrappedTrajectory(pos, box, times)
+    _, ref = orc.shifted_correlation(orc.msd, unw, **kw)
+    for name, fn in (('msd', c.msd), ('isf', partial(c.isf, q=22.7))):
+        for mode in ('nojump', 'raw'):
+            coords = make()
+            frames = coords.nojump if mode == 'nojump' else coords
+            del calls[:]
+            _, one = c.shifted_correlation(fn, frames, **kw)
+            assert calls == [N]
+            monkeypatch.setattr(c, 'DENSE_SLAB_ATOMS', 1024)
+            coords = make()                                     # nothing resident yet: the slabs load themselves
+            frames = coords.nojump if mode == 'nojump' else coords
+            del calls[:]
+            t, got = c.shifted_correlation(fn, frames, **kw)
+            monkeypatch.setattr(c, 'DENSE_SLAB_ATOMS', None)
+            assert calls == [1024, 1024, N - 2048]
+            assert got.dtype == one.dtype
+            close(got, one, scale=float(np.abs(one).max()), rtol=1e-6 if mode == 'raw' else 1e-12,
+                  atol=1e-6 if mode == 'raw' else 1e-13)
+            if name == 'msd' and mode == 'nojump':
+                close(got, ref, rtol=1e-11, atol=1e-13)
+
+
 def test_custom_reader_protocol(golden, md):
     """Coordinates over ANY reader with the reference protocol (len, reader[i].positions/.box/.time,
     reader.py:254-286): frames are pulled one by one into pinned staging and streamed through the scan."""
