@@ -183,6 +183,13 @@ int mdb_nojump_images_from_jumps(const mdb_jumpmat_args *args, void *stream);
 int mdb_nojump_apply(const float *coords_row, const uint8_t *images_row, const double box[3],
                      int32_t n_atoms, double *out, void *stream);
 
+/* Trajectory ingestion (the reference pulls frames one by one through its reader, coordinates.py:257-271):
+ * `n_rows` rows of `width_bytes` from page-locked host memory (row stride `src_pitch_bytes`) into device rows
+ * (stride `dst_pitch_bytes`) as ONE strided DMA on `stream` -- e.g. the columns of an atom slab of a
+ * (frames x 3N) float32 trajectory.  Asynchronous when the source is page-locked. */
+int mdb_copy_rows_h2d(const void *src_host, int64_t src_pitch_bytes, void *dst_dev, int64_t dst_pitch_bytes,
+                      int64_t width_bytes, int64_t n_rows, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense schedules: every origin of an arithmetic progression against a contiguous range of lags,
  * averaged over the origins (BASELINE config 5: `index_distribution = lambda a, b: np.arange(a, b)`,

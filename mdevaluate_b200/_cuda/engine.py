@@ -297,6 +297,17 @@ def images_from_jumps(indptr, frames, jumps, n_atoms, images, keep=None, overflo
     _count(1)
 
 
+def copy_rows_h2d(src_ptr, src_pitch_bytes, dst, width_bytes, n_rows, stream):
+    """Strided DMA of ``n_rows`` rows from page-locked host memory into the rows of device tensor ``dst``
+    (mdb_copy_rows_h2d) on ``stream``."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    with torch.cuda.device(dst.device):
+        _lib.check(lib.mdb_copy_rows_h2d(C.c_void_p(src_ptr), src_pitch_bytes, C.c_void_p(dst.data_ptr()),
+                                         dst.stride(0) * dst.element_size(), width_bytes, n_rows,
+                                         C.c_void_p(stream.cuda_stream)), 'mdb_copy_rows_h2d')
+
+
 def nojump_apply(coords_row, images_row, box_diag, n_atoms):
     """float64 unwrapped frame ``x - n*box`` of one stored row (device tensor (3N,))."""
     torch = _lib.require_cuda()

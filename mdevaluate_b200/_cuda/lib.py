@@ -23,7 +23,7 @@ EXPORTS = (
     'mdb_corr_workspace_bytes', 'mdb_shifted_corr', 'mdb_corr_last_launches',
     'mdb_corr_profile', 'mdb_corr_last_kernel_ms',
     'mdb_nojump_scan', 'mdb_nojump_apply', 'mdb_nojump_images_from_jumps',
-    'mdb_dense_workspace_bytes', 'mdb_dense_corr',
+    'mdb_dense_workspace_bytes', 'mdb_dense_corr', 'mdb_copy_rows_h2d',
 )
 
 
@@ -88,6 +88,7 @@ def _declare(lib):
     lib.mdb_corr_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
     lib.mdb_nojump_scan.argtypes = [C.POINTER(NojumpArgs), C.c_void_p]
     lib.mdb_nojump_images_from_jumps.argtypes = [C.POINTER(JumpMatArgs), C.c_void_p]
+    lib.mdb_copy_rows_h2d.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
     lib.mdb_dense_workspace_bytes.argtypes = [C.POINTER(DenseArgs), C.POINTER(C.c_size_t)]
     lib.mdb_dense_corr.argtypes = [C.POINTER(DenseArgs), C.c_void_p]
     lib.mdb_nojump_apply.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_void_p,

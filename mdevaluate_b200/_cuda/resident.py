@@ -191,6 +191,19 @@ class Resident:
         as_t = torch.from_numpy(host_block).view(self.n_frames, 3 * self.n_atoms)
         return as_t if as_t.is_pinned() else None
 
+    def _pinned_run(self):
+        """``(address of the run's first value in frame 0, bytes per frame)`` when the selection is one
+        contiguous run of atoms of a page-locked C-contiguous float32 host trajectory, else None."""
+        torch = _lib.require_cuda()
+        host_block = getattr(self.reader, 'host_block', None)
+        if (host_block is None or self._filter_run is None or host_block.dtype != np.float32
+                or not host_block.flags.c_contiguous):
+            return None
+        if not torch.from_numpy(host_block).is_pinned():
+            return None
+        row_bytes = host_block.shape[1] * 12
+        return host_block.ctypes.data + self._filter_run[0] * 12, row_bytes
+
     def _upload_rows(self, coords):
         """Host trajectory -> the rows of ``coords`` (float32), entirely on a copy stream: nothing is queued
         on the compute stream, so the upload of one atom slab runs under the kernel of the previous one.
@@ -202,11 +215,18 @@ class Resident:
         seg = self._segment_frames()
         starts = range(0, self.n_frames, seg)
         direct = self._pinned_block()
+        run = self._pinned_run()
         if direct is not None:
             with torch.cuda.stream(copy_stream):
                 for t0 in starts:
                     t1 = min(self.n_frames, t0 + seg)
                     coords[t0:t1, :n3].copy_(direct[t0:t1], non_blocking=True)
+        elif run is not None:
+            # the columns of a contiguous run of atoms out of the page-locked trajectory: strided DMA
+            base, row_bytes = run
+            for t0 in starts:
+                t1 = min(self.n_frames, t0 + seg)
+                engine.copy_rows_h2d(base + t0 * row_bytes, row_bytes, coords[t0:t1], n3 * 4, t1 - t0, copy_stream)
         else:
             pinned = [torch.empty((seg, self.pitch), dtype=torch.float32).pin_memory() for _ in range(2)]
             sent = [torch.cuda.Event() for _ in range(2)]
