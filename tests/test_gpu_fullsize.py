@@ -25,9 +25,10 @@ def big():
     import mdevaluate_b200 as md
     from mdevaluate_b200._cuda import engine
     from mdevaluate_b200.synthetic import random_walk_device, box_length
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 40e9:
-        pytest.skip('needs ~20 GB of free HBM')
+        pytest.skip('needs ~20 GB of free HBM (free: %.0f GB)' % (free / 1e9))
     block, box, times = random_walk_device(N, T, seed=20240, box=box_length(N), pitch=engine.row_pitch(N))
     coords = md.Coordinates.from_arrays(block, box, times, n_atoms=N)
     yield md, coords, block, box, times
@@ -141,9 +142,12 @@ def test_config3_van_hove_and_alpha2_full_size():
     import mdevaluate_b200 as md
     from mdevaluate_b200._cuda import engine
     from mdevaluate_b200.synthetic import random_walk_device, box_length
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()            # blocks cached by the earlier tests count as used for the driver
     free, _ = torch.cuda.mem_get_info()
     if free < 110e9:
-        pytest.skip('needs ~90 GB of free HBM')
+        pytest.skip('needs ~90 GB of free HBM (free: %.0f GB)' % (free / 1e9))
     n, t_frames = 500000, 10000
     block, box, times = random_walk_device(n, t_frames, seed=3, box=box_length(n), pitch=engine.row_pitch(n),
                                            frame_block=128)
