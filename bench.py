@@ -310,6 +310,7 @@ def ours_arm(a):
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'kernel': 'corr_kernel<float, images, SINC>' if a.function == 'isf'
                 else 'corr_kernel<float, images, R2>', 'kernel_ms': k_ms, 'kernel_ms_min': float(np.min(kernel_ms)),
+                'kernel_ms_median': float(np.median(kernel_ms)), 'kernel_ms_max': float(np.max(kernel_ms)),
                 'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
                 'moved_bytes_per_launch': 15.0 * N * S * (L + 1),
                 'note': 'algorithmic bytes = 12 B (float32 xyz) per atom*origin*(lag+1); the kernel also reads 3 B of '
