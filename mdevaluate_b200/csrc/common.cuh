@@ -84,6 +84,17 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// Byte j of a packed excess-128 image word as the float 2^23 + byte: ONE byte-permute splices the byte
+// into the mantissa of 8388608.0f.  Differences of two such floats are the (exact) differences of the
+// image counts -- no integer-to-float conversion.
+__device__ __forceinline__ float image_float(uint32_t w, int j) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j));
+}
 __device__ __forceinline__ float rsqrt_approx(float y) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));   // bare MUFU.RSQ

@@ -63,6 +63,7 @@ struct CorrDev {
     long long sel_pitch;
     int n_chunks, n_ablocks;
     double q2;
+    int sinc_f32;        // ISF alone, constant float32 box: displacements in float32 (process_tile_sinc_f32)
     int leg_order;
     int n_bins;
     int bin_mode;
@@ -490,16 +491,15 @@ struct Ring {
     }
 };
 
-// Take the calling thread's 4 atoms out of the current stage, release the stage, unwrap.
-template <bool IMG, bool BOXC>
-__device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
-                                            const unsigned char *stages, int stage_bytes, int tid,
-                                            const double *bx, double (&u)[12], float (&raw)[12]) {
+// Take the calling thread's 4 atoms out of the current stage and release the stage.
+template <bool IMG>
+__device__ __forceinline__ void fetch_raw(Ring &ring, uint32_t full0, uint32_t empty0, const unsigned char *stages,
+                                          int stage_bytes, int tid, float (&raw)[12], uint32_t (&wds)[3]) {
     mbar_wait(full0 + 8 * ring.stage, ring.phase);
     const unsigned char *src = stages + (size_t)ring.stage * stage_bytes;
     const float4 *c4 = reinterpret_cast<const float4 *>(src) + 3 * tid;
     const float4 a = c4[0], b = c4[1], c = c4[2];
-    uint32_t wds[3] = {0x80808080u, 0x80808080u, 0x80808080u};
+    wds[0] = wds[1] = wds[2] = 0x80808080u;
     if (IMG) {
         const uint32_t *iw = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes) + 3 * tid;
         wds[0] = iw[0]; wds[1] = iw[1]; wds[2] = iw[2];
@@ -513,8 +513,83 @@ __device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32
     __syncwarp();
     mbar_arrive_if(empty0 + 8 * ring.stage, (tid & 31) == 0);
     ring.advance();
+}
+
+// ... and unwrap to float64.
+template <bool IMG, bool BOXC>
+__device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
+                                            const unsigned char *stages, int stage_bytes, int tid,
+                                            const double *bx, double (&u)[12], float (&raw)[12]) {
+    uint32_t wds[3];
+    fetch_raw<IMG>(ring, full0, empty0, stages, stage_bytes, tid, raw, wds);
     // a box that is the same for every row comes from the kernel parameters (constant bank operands)
     unwrap12<IMG>(raw, wds, BOXC ? p.box_const : bx, u);
+}
+
+// ISF alone on unwrapped float32 rows with one constant box: the displacement in FLOAT32, without
+// conversions and without the float64 pipe.  d = (x0 - n0 L) - (xt - nt L) = x0 - xt - k L with k = n0 - nt.
+// k = 0 (the common case): fl(x0 - xt) is the exact difference rounded once (relative 2^-24).  k != 0: the
+// operand on the far side of the boundary is moved first -- k > 0: (x0 - kL) - xt, k < 0: x0 - (xt + kL) --
+// one FMA each, so the moved operand is the exact value rounded once and, being within |d| of the boundary
+// (Sterbenz: exact when it lies in [L/2, L]), carries an error of at most ulp(d)/2; moving the OTHER
+// operand would cost ulp(L)/2.  Every component of d is thus good to ~2^-23 relative, the same order as
+// the float32 sinc that follows (sinc_of_square_x2), which is why this path exists for the ISF only:
+// MSD / alpha_2 / van Hove keep the float64 arithmetic of the reference.  Image counts become floats by
+// one byte-permute (image_float); all adds / fmas are packed pairs (components 2j, 2j+1 of the 12).
+template <bool MASKED>
+__device__ __forceinline__ void process_tile_sinc_f32(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
+                                                      const unsigned char *stages, int stage_bytes, int tid,
+                                                      uint32_t vmask, int nl, double *s_acc) {
+    const float lx = (float)p.box_const[0], ly = (float)p.box_const[1], lz = (float)p.box_const[2];
+    const f32x2 neg_box[3] = {pack2(-lx, -ly), pack2(-lz, -lx), pack2(-ly, -lz)};   // dims of pair j: j % 3
+    const f32x2 q2 = bcast2((float)p.q2);
+    f32x2 x0[6], f0[6];
+    {
+        float raw0[12];
+        uint32_t w0[3];
+        fetch_raw<true>(ring, full0, empty0, stages, stage_bytes, tid, raw0, w0);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            x0[j] = pack2(raw0[2 * j], raw0[2 * j + 1]);
+            f0[j] = pack2(image_float(w0[(2 * j) >> 2], (2 * j) & 3), image_float(w0[(2 * j + 1) >> 2], (2 * j + 1) & 3));
+        }
+    }
+#pragma unroll 1
+    for (int k = 0; k < nl; ++k) {
+        float rawt[12];
+        uint32_t wt[3];
+        fetch_raw<true>(ring, full0, empty0, stages, stage_bytes, tid, rawt, wt);
+        float d[12];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const f32x2 ft = pack2(image_float(wt[(2 * j) >> 2], (2 * j) & 3),
+                                   image_float(wt[(2 * j + 1) >> 2], (2 * j + 1) & 3));
+            const f32x2 dn = sub2(f0[j], ft);                    // n0 - nt, exact
+            float dn0, dn1;
+            unpack2(dn, dn0, dn1);
+            const f32x2 up = pack2(fmaxf(dn0, 0.0f), fmaxf(dn1, 0.0f));     // images the origin is moved by
+            const f32x2 dw = sub2(up, dn);                                   // images the lag frame is moved by
+            const f32x2 o = fma2(up, neg_box[j % 3], x0[j]);
+            const f32x2 t = fma2(dw, neg_box[j % 3], pack2(rawt[2 * j], rawt[2 * j + 1]));
+            unpack2(sub2(o, t), d[2 * j], d[2 * j + 1]);
+        }
+        float r2[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            r2[a] = fmaf(d[3 * a + 2], d[3 * a + 2], fmaf(d[3 * a + 1], d[3 * a + 1], d[3 * a] * d[3 * a]));
+        float y0, y1, y2, y3, v0, v1, v2, v3;
+        unpack2(mul2(pack2(r2[0], r2[1]), q2), y0, y1);
+        unpack2(mul2(pack2(r2[2], r2[3]), q2), y2, y3);
+        sinc_of_square_x2(y0, y1, v0, v1);
+        sinc_of_square_x2(y2, y3, v2, v3);
+        if (MASKED) {
+            v0 = (vmask & 1u) ? v0 : 0.0f;
+            v1 = (vmask & 2u) ? v1 : 0.0f;
+            v2 = (vmask & 4u) ? v2 : 0.0f;
+            v3 = (vmask & 8u) ? v3 : 0.0f;
+        }
+        s_acc[(size_t)k * kThreads + tid] += (double)((v0 + v1) + (v2 + v3));
+    }
 }
 
 // One tile of 1024 atoms: origin group into registers, then the lag rows of the chunk one by one.
@@ -532,6 +607,12 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
     constexpr bool kHistF32 = kHist && !IMG;
     constexpr int NV = (kR2 ? 1 : 0) + (kR4 ? 1 : 0) + (kSinc ? 1 : 0);
+    if constexpr (FLAGS == MDB_SUM_SINC && IMG && BOXC) {
+        if (p.sinc_f32) {          // uniform over the launch
+            process_tile_sinc_f32<MASKED>(p, ring, full0, empty0, stages, stage_bytes, tid, vmask, nl, s_acc);
+            return;
+        }
+    }
     double u0[12];
     float raw0[12];
     fetch_group<IMG, BOXC>(p, ring, full0, empty0, stages, stage_bytes, tid, s_box[0], u0, raw0);
@@ -883,6 +964,9 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     p.n_chunks = plan.n_chunks;
     p.n_ablocks = plan.n_ablocks;
     p.q2 = a->q * a->q;
+    // ISF alone with one float32-representable box (what trajectory formats store): float32 displacements
+    p.sinc_f32 = a->flags == MDB_SUM_SINC && a->images && !a->box && getenv("MDB_SINC_F64") == nullptr;
+    for (int d = 0; d < 3; ++d) p.sinc_f32 = p.sinc_f32 && (double)(float)a->box_const[d] == a->box_const[d];
     p.leg_order = a->legendre_order;
     p.n_bins = hist ? a->n_bins : 0;
     p.bin_mode = a->bin_mode;

@@ -767,3 +767,34 @@ def test_autosave_round_trip(small, md, tmp_path):
         np.testing.assert_array_equal(t3, t4)
     finally:
         md.autosave.disable()
+
+
+def test_isf_float32_displacement_path_against_float64_path(md, monkeypatch):
+    """ISF alone with a constant float32 box computes displacements in float32 (operand on the far side of
+    the boundary moved first, csrc/corr_kernels.cu::process_tile_sinc_f32); MDB_SINC_F64=1 forces the float64
+    chain the other functions use.  Both against the oracle, and against each other, in a small box where
+    most atoms cross several images (|n0 - nt| up to 3 and more) and in a large one."""
+    from mdevaluate_b200.synthetic import random_walk
+    c = md.correlation
+    for n_atoms, box, sigma in ((1500, 1.3, 0.12), (1100, 14.4, 0.05)):
+        pos, bx, times = random_walk(n_atoms, 160, seed=n_atoms, sigma=sigma, box=box)
+        unw = orc.UnwrappedTrajectory(pos, bx, times)
+        if box < 2:
+            assert np.abs(unw.counts[:-60] - unw.counts[60:]).max() >= 3
+        _, ref = orc.shifted_correlation(partial(orc.isf, q=22.7), unw, segments=9, window=0.5)
+        coords = md.Coordinates.from_arrays(pos, bx, times)
+        _, fast = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=9, window=0.5)
+        monkeypatch.setenv('MDB_SINC_F64', '1')
+        _, slow = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=9, window=0.5)
+        monkeypatch.delenv('MDB_SINC_F64')
+        assert not np.array_equal(fast, slow)             # really two code paths
+        close(fast, ref)
+        close(slow, ref)
+        assert np.abs(fast - slow).max() < 5e-8
+        # sub-ensembles run the masked instantiation of the same path
+        sel = c.subensemble_correlation(lambda f: np.where(np.asarray(f)[:, 0] % box < 0.5 * box)[0])
+        _, fast_m = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=9, window=0.5, correlation=sel)
+        _, ref_m = orc.shifted_correlation(partial(orc.isf, q=22.7), unw, segments=9, window=0.5,
+                                           correlation=orc.subensemble_pairwise(
+                                               lambda f: np.where(np.asarray(f)[:, 0] % box < 0.5 * box)[0]))
+        close(fast_m, ref_m)
