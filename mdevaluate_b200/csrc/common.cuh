@@ -105,14 +105,14 @@ __device__ __forceinline__ float rsqrt_approx(float y) {
 // few 1e4:  one MUFU.RSQ + a Newton step give 1/x and x = y/x;  x is reduced by multiples of pi
 // (2-term Cody-Waite with FMA), sin on [-pi/2, pi/2] is an odd degree-11 polynomial (near-minimax,
 // 1e-10), the sign comes from the parity of the multiple.  Every float32 add / mul / fma is one
-// packed instruction for the pair.  y is clamped at 2^-100 (a power of four, so rsqrt, the Newton
+// packed instruction for the pair.  y is offset by 2^-100 (a power of four, so rsqrt, the Newton
 // step and the final product are exact there): y = 0 gives exactly 1.  Valid for sqrt(y) = q*r < 2^22*pi
 // (1.3e7 rad; beyond that the nearest-multiple trick runs out of mantissa) -- MD displacements times any
 // physical q stay orders of magnitude below.
 __device__ __forceinline__ void sinc_of_square_x2(float y0, float y1, float &r0, float &r1) {
-    y0 = fmaxf(y0, 7.888609052210118e-31f);
-    y1 = fmaxf(y1, 7.888609052210118e-31f);
-    const f32x2 y = pack2(y0, y1);
+    // y + 2^-100 instead of max(y, 2^-100): one packed add; any y that matters (> 2^-76) is unchanged by it
+    const f32x2 y = add2(pack2(y0, y1), bcast2(7.888609052210118e-31f));
+    unpack2(y, y0, y1);
     f32x2 rs = pack2(rsqrt_approx(y0), rsqrt_approx(y1));
     f32x2 t = mul2(mul2(y, bcast2(-0.5f)), rs);
     t = fma2(t, rs, bcast2(1.5f));
@@ -131,8 +131,10 @@ __device__ __forceinline__ void sinc_of_square_x2(float y0, float y1, float &r0,
     float kb0, kb1, sn0, sn1;
     unpack2(kb, kb0, kb1);
     unpack2(sn, sn0, sn1);
-    sn0 = __int_as_float(__float_as_int(sn0) ^ (__float_as_int(kb0) << 31));
-    sn1 = __int_as_float(__float_as_int(sn1) ^ (__float_as_int(kb1) << 31));
+    // parity of the multiple -> sign: adding (kb << 31) flips bit 31 exactly like the xor would, and the
+    // shift-and-add is ONE integer multiply-add
+    sn0 = __uint_as_float(__float_as_uint(sn0) + (__float_as_uint(kb0) << 31));
+    sn1 = __uint_as_float(__float_as_uint(sn1) + (__float_as_uint(kb1) << 31));
     unpack2(mul2(pack2(sn0, sn1), rs), r0, r1);
 }
 

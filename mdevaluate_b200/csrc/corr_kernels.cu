@@ -64,6 +64,8 @@ struct CorrDev {
     int n_chunks, n_ablocks;
     double q2;
     int sinc_f32;        // ISF alone, constant float32 box: displacements in float32 (process_tile_sinc_f32)
+    float q2f;           // float(q^2) and the negated box as the packed pairs (x,y) (z,x) (y,z) of that path:
+    alignas(8) float neg_box2[6];   // kernel parameters = constant bank, read as 64-bit operands
     int leg_order;
     int n_bins;
     int bin_mode;
@@ -540,9 +542,8 @@ template <bool MASKED>
 __device__ __forceinline__ void process_tile_sinc_f32(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
                                                       const unsigned char *stages, int stage_bytes, int tid,
                                                       uint32_t vmask, int nl, double *s_acc) {
-    const float lx = (float)p.box_const[0], ly = (float)p.box_const[1], lz = (float)p.box_const[2];
-    const f32x2 neg_box[3] = {pack2(-lx, -ly), pack2(-lz, -lx), pack2(-ly, -lz)};   // dims of pair j: j % 3
-    const f32x2 q2 = bcast2((float)p.q2);
+    const f32x2 *neg_box = reinterpret_cast<const f32x2 *>(p.neg_box2);      // dims of pair j: j % 3
+    const f32x2 q2 = bcast2(p.q2f);
     f32x2 x0[6], f0[6];
     {
         float raw0[12];
@@ -967,6 +968,12 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     // ISF alone with one float32-representable box (what trajectory formats store): float32 displacements
     p.sinc_f32 = a->flags == MDB_SUM_SINC && a->images && !a->box && getenv("MDB_SINC_F64") == nullptr;
     for (int d = 0; d < 3; ++d) p.sinc_f32 = p.sinc_f32 && (double)(float)a->box_const[d] == a->box_const[d];
+    p.q2f = (float)p.q2;
+    {
+        const float nb[3] = {-(float)a->box_const[0], -(float)a->box_const[1], -(float)a->box_const[2]};
+        const int dims[6] = {0, 1, 2, 0, 1, 2};
+        for (int i = 0; i < 6; ++i) p.neg_box2[i] = nb[dims[i]];
+    }
     p.leg_order = a->legendre_order;
     p.n_bins = hist ? a->n_bins : 0;
     p.bin_mode = a->bin_mode;
