@@ -162,9 +162,16 @@ def generate_nojump_matrixes(trajectory):
     file name -- store them in the reference's cache format next to it (reader.py:189-202)."""
     from scipy import sparse
     logger.info('generate Nojump Matrixes for: {}'.format(trajectory))
+    res = trajectory._resident()
+    if res.n_atoms != res.n_atoms_all:
+        # the matrices belong to the READER and are indexed by each Coordinates' selection afterwards
+        # (pbc.py:243), so they always cover all atoms, whatever subset this Coordinates shows
+        from .coordinates import Coordinates
+        trajectory = Coordinates(trajectory.frames)
+        res = trajectory._resident()
     jump_data = parse_jumps(trajectory)
     n_frames = len(trajectory)
-    n_atoms = trajectory._resident().n_atoms
+    n_atoms = res.n_atoms
     reader = trajectory.frames
     reader.nojump_matrixes = tuple(
         sparse.csr_matrix((np.array(m.data), (m.row, m.col)), shape=(n_frames, n_atoms)) for m in jump_data

@@ -798,3 +798,16 @@ def test_isf_float32_displacement_path_against_float64_path(md, monkeypatch):
                                            correlation=orc.subensemble_pairwise(
                                                lambda f: np.where(np.asarray(f)[:, 0] % box < 0.5 * box)[0]))
         close(fast_m, ref_m)
+
+
+def test_generate_nojump_matrixes_from_a_subset_covers_all_atoms(small, md):
+    """The jump matrices belong to the reader and are indexed by every Coordinates' own selection afterwards
+    (pbc.py:243): generating them through a subset still scans all atoms."""
+    g, _ = small
+    reader = md.MemoryReader(g['pos'], g['box'], g['times'])
+    subset = md.Coordinates(reader, atom_filter=g['sel'])
+    md.reader.generate_nojump_matrixes(subset)
+    dense = np.stack([m.toarray() for m in reader.nojump_matrixes], axis=-1)
+    np.testing.assert_array_equal(dense, g['jumps'])
+    t, r = md.correlation.shifted_correlation(md.correlation.msd, subset.nojump, segments=6, window=0.4)
+    close(r, g['msd_sel'], scale=float(np.nanmax(g['msd_sel'])), rtol=1e-11, atol=1e-13)
