@@ -34,6 +34,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its version banner
+    to file descriptor 1).  Keep the real stdout for the result line and point fd 1 at stderr for everyone else."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 Q = 22.7
 METRIC = 'atom*origin*lag evals/s (ISF via shifted_correlation, nojump unwrap)'
 UNIT = 'evals/s'
@@ -179,7 +197,7 @@ def reference_arm(a):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -391,7 +409,7 @@ def ours_arm(a):
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': int(launches),
             'clocks': clocks, 'parity': parity, 'nojump_pass': nojump_pass, 'other_kernels': other,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -434,6 +452,7 @@ def main():
                '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29541'),
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    claim_stdout()
     if a.impl == 'reference':
         reference_arm(a)
     else:

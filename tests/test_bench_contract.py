@@ -29,3 +29,14 @@ def test_reference_arm_other_ranks_exit_quietly():
            '--warmup', '0', '--atoms', '100', '--frames', '100']
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ''
+
+
+def test_stdout_carries_only_the_json_line():
+    """Whatever a library writes to file descriptor 1 (NCCL prints its version banner there) must not end up
+    in front of the result line: bench.py keeps the real stdout for the line and points fd 1 at stderr."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "os.write(1, b'NCCL version 0.0\\n'); print('python-level noise'); bench.emit({'ok': 1})" % ROOT)
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout == '{"ok": 1}\n'
+    assert 'NCCL version 0.0' in res.stderr and 'python-level noise' in res.stderr
