@@ -402,7 +402,9 @@ def ours_arm(a):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': elapsed_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic',
+            # the arithmetic of the timed path: ISF = float32 displacements + float32 sinc, summed in float64
+            # (csrc/corr_kernels.cu::process_tile_sinc_f32); MSD = float64 throughout, like the reference
+            'dtype': 'f32' if a.function == 'isf' else 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name(a, world), 'atoms_total': N * world, 'frames': T, 'origins': int(S),
                        'lags': int(L), 'evals_per_step': int(evals_step), 'parallelism': 'atom-shard x%d' % world,
                        'l2': 'inputs larger than L2: each step streams %.1f GB of frame rows' % (alg_bytes / 1e9)},
