@@ -290,3 +290,26 @@ def test_autosave_name_of_shifted_correlation(golden, tmp_path, autosave_on):
     assert base != key(partial(c.isf, q=22.7), coords.nojump[24:], segments=10)
     assert base != key(partial(c.isf, q=20.0), coords.nojump, segments=10)
     assert base != key(partial(c.isf, q=22.7), coords.nojump, segments=11)
+
+
+def test_correct_nojump_matrixes_for_whole(golden, tmp_path):
+    """Row 0 of the stored matrices := jumps of frame 0 against frame0.whole (reader.py:244-251); for the
+    single-atom residues of this package `whole` is the identity, so row 0 becomes zero -- and the file is
+    rewritten."""
+    from mdevaluate_b200 import Coordinates, MemoryReader
+    g = golden('walk_small')
+    name = str(tmp_path / 'traj.xtc')
+    reader = MemoryReader(g['pos'], g['box'], g['times'], filename=name)
+    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'))
+    from scipy import sparse
+    seeded = sparse.lil_matrix(mats[1].shape, dtype=np.int8)
+    seeded[0, 5] = -1
+    reader.nojump_matrixes = (mats[0], (mats[1] + seeded.tocsr()).astype(np.int8), mats[2])
+    assert reader.nojump_matrixes[1][0, 5] == -1
+    rd.correct_nojump_matrixes_for_whole(Coordinates(reader))
+    fixed = reader.nojump_matrixes
+    assert all(sparse.isspmatrix_csr(m) and m.dtype == np.int8 for m in fixed)
+    assert all(m[0].nnz == 0 for m in fixed)
+    assert (fixed[1][1:] != mats[1][1:]).nnz == 0                      # the other rows are untouched
+    _, stored = rd.read_nojump_file(rd.nojump_filename(reader))
+    assert all((a != b).nnz == 0 for a, b in zip(stored, fixed))

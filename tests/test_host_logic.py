@@ -259,3 +259,36 @@ def test_rotational_spec():
     assert sp.corr.flags == L.SUM_LEGENDRE and sp.corr.order == 4
     with pytest.raises(ValueError):
         corr._kernel_spec(partial(corr.rotational_autocorrelation, order=2.5))
+
+
+def test_dense_slab_plan():
+    """Atom slabs of an out-of-core dense pass (correlation._dense_slabs): one slab when the trajectory is or
+    fits in HBM, otherwise whole 1024-atom tiles sized so that two slabs fit the memory budget."""
+    from mdevaluate_b200 import correlation as c
+
+    class FakeResident:
+        def __init__(self, n_atoms, n_frames, budget, device=False):
+            self.n_atoms, self.n_frames, self._budget, self._device = n_atoms, n_frames, budget, device
+
+        def on_device(self):
+            return self._device
+
+        def memory_budget(self):
+            return self._budget
+
+    # BASELINE config 5: 200 000 atoms x 50 000 frames, 15 B per atom and frame with image counts = 150 GB
+    slabs = c._dense_slabs(FakeResident(200000, 50000, int(125e9)), nojump=True)
+    assert slabs == [(0, 82944), (82944, 165888), (165888, 200000)]
+    per_atom = 50000 * 15
+    assert 2 * 82944 * per_atom <= 125e9 < 2 * (82944 + 1024) * per_atom
+    assert c._dense_slabs(FakeResident(200000, 50000, int(160e9)), nojump=True) == [(0, 200000)]      # fits
+    assert c._dense_slabs(FakeResident(200000, 50000, int(125e9)), nojump=False) == [(0, 200000)]     # 120 GB raw
+    assert c._dense_slabs(FakeResident(200000, 50000, int(1e9), device=True), nojump=True) == [(0, 200000)]
+    tiny = c._dense_slabs(FakeResident(5000, 50000, int(1e6)), nojump=True)                           # never below a tile
+    assert tiny[0] == (0, 1024) and tiny[-1] == (4096, 5000)
+    try:
+        c.DENSE_SLAB_ATOMS = 2500                                                                     # forced: rounded to tiles
+        assert c._dense_slabs(FakeResident(5000, 100, int(1e12), device=True), nojump=True) == [
+            (0, 2048), (2048, 4096), (4096, 5000)]
+    finally:
+        c.DENSE_SLAB_ATOMS = None
