@@ -1,13 +1,17 @@
-"""Result files for expensive evaluations (reference: mdevaluate/autosave.py).
+"""Result files for expensive evaluations -- the reference's ``autosave`` workflow (mdevaluate/autosave.py,
+doc/special/autosave.rst) on top of a small ``ResultFile`` abstraction.
 
-``enable(dir)`` switches it on; from then on a function decorated with ``autosave_data`` --
-``correlation.shifted_correlation`` is -- writes ``(times, result)`` to
-``<trajectory dir>/<dir>/<function>_<correlation function>_<description>.npz`` together with a
-checksum of its relevant arguments, and returns the stored data instead of recomputing when a file
-with the same checksum exists.  File names, the npz layout (``checksum``, ``data``) and the checksum
-rule (checksum.py) are the reference's (autosave.py:85-183), so its tooling keeps working on the
-files; checksums of plain Python functions depend on their source text and therefore differ between
-the two packages -- a result the reference stored is recomputed here, not silently trusted.
+``enable(dir)`` switches it on; from then on a function wrapped by ``autosave_data`` --
+``correlation.shifted_correlation`` is -- stores ``(times, result)`` in
+
+    <trajectory dir>/<dir>/<function>_<correlation function>_<description>.npz
+
+next to a checksum of the arguments that determine the result, and a later call with the same
+arguments returns the stored arrays instead of launching anything.  What is kept compatible with the
+reference (autosave.py:85-183) is what its users and tooling see: the public names of this module,
+the file names, the npz layout (entries ``checksum`` and ``data``) and the digest rule (checksum.py).
+Checksums of plain Python functions hash their source text and therefore differ between the two
+packages: a result the reference stored under such a key is recomputed here, never silently trusted.
 """
 import functools
 import inspect
@@ -18,6 +22,7 @@ import numpy as np
 from .checksum import checksum
 from .logging import logger
 
+# Module state, readable like the reference's globals (autosave.py:8-11); enable() / disable() set it.
 autosave_directory = None
 load_autosave_data = False
 verbose_print = True
@@ -25,147 +30,166 @@ user_autosave_directory = os.path.join(os.environ.get('HOME', os.path.expanduser
 
 
 def notify(msg):
-    (logger.info if verbose_print else logger.debug)(msg)
+    """Progress messages: INFO when ``enable(..., verbose=True)``, else DEBUG."""
+    logger.log(20 if verbose_print else 10, msg)
 
 
 def enable(dir, load_data=True, verbose=True):
-    """Save the results of decorated functions below ``dir`` (relative to the trajectory's directory)
-    and, with ``load_data``, load matching results instead of recomputing (autosave.py:24-39)."""
+    """Store results of decorated functions below ``dir`` -- a path relative to each trajectory's own
+    directory -- and, unless ``load_data=False``, reuse stored results whose checksum matches."""
     global autosave_directory, load_autosave_data, verbose_print
-    verbose_print = verbose
-    autosave_directory = dir
-    load_autosave_data = load_data
+    autosave_directory, load_autosave_data, verbose_print = dir, load_data, verbose
     notify('Enabled autosave in directory: {}'.format(autosave_directory))
 
 
 def disable():
-    """Switch autosave off (autosave.py:42-46)."""
+    """No result files are written or read until the next ``enable``."""
     global autosave_directory, load_autosave_data
-    autosave_directory = None
-    load_autosave_data = False
+    autosave_directory, load_autosave_data = None, False
 
 
 class disabled:
-    """Context manager: no autosave inside the block; the previous directory is re-enabled afterwards
-    (autosave.py:49-70)."""
+    """``with autosave.disabled(): ...`` -- autosave is off inside the block and back on, with the
+    directory it had, afterwards."""
 
     def __enter__(self):
         self._autosave_directory = autosave_directory
         disable()
+        return self
 
-    def __exit__(self, *args):
+    def __exit__(self, *exc):
         enable(self._autosave_directory)
+        return False
+
+
+class ResultFile:
+    """One ``.npz`` result file: ``checksum`` (a 160-bit Python integer, which NumPy can only store as a
+    pickled object entry -- hence ``allow_pickle`` on the read side) and ``data``."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def stored_checksum(self):
+        """The checksum inside the file; 0 when the file is absent or carries none."""
+        if not os.path.exists(self.path):
+            return 0
+        with np.load(self.path, allow_pickle=True) as archive:
+            return archive['checksum'][()] if 'checksum' in archive else 0
+
+    def holds(self, *checksums):
+        stored = self.stored_checksum()
+        return any(stored == c for c in checksums)
+
+    def write(self, csum, result):
+        """A tuple of equally shaped arrays becomes one array; anything ragged -- ``(times (L,), result
+        (S, L))``, the ``(times, result, count)`` of multi-sub-ensemble runs -- an object array, one
+        entry per item."""
+        notify('Saving result to file: {}'.format(self.path))
+        try:
+            packed = np.array(result)
+        except ValueError:
+            packed = np.empty((len(result),), dtype=object)
+            for slot, item in enumerate(result):
+                packed[slot] = item
+        np.savez(self.path, checksum=csum, data=packed)
+
+    def read(self):
+        """The stored result.  Files from before the ``data`` entry existed hold positional ``arr_*``
+        entries instead; they are returned as a tuple and rewritten in today's layout."""
+        notify('Loading result from file: {}'.format(self.path))
+        with np.load(self.path, allow_pickle=True) as archive:
+            if 'data' in archive:
+                return archive['data']
+            legacy = tuple(archive[name] for name in sorted(archive) if 'arr' in name)
+            csum = archive['checksum'][()]
+        self.write(csum, legacy)
+        return legacy
 
 
 def get_directory(reader):
-    """The autosave directory for a trajectory reader, created on demand; falls back to
-    ``~/.mdevaluate/autosave/...`` when the trajectory's directory is read-only (autosave.py:73-86)."""
-    savedir = os.path.join(os.path.dirname(reader.filename), autosave_directory)
-    if not os.path.exists(savedir):
-        try:
-            os.makedirs(savedir)
-        except PermissionError:
-            pass
-    if not os.access(savedir, os.W_OK):
-        savedir = os.path.join(user_autosave_directory, savedir.lstrip('/'))
-        logger.info('Switched autosave directory to {}, since original location is not writeable.'.format(savedir))
-    os.makedirs(savedir, exist_ok=True)
-    return savedir
+    """Where the results of ``reader``'s trajectory go: ``<dirname(reader.filename)>/<autosave dir>``,
+    created on demand; a read-only location is mirrored below ``~/.mdevaluate/autosave``."""
+    target = os.path.join(os.path.dirname(reader.filename), autosave_directory)
+    try:
+        os.makedirs(target, exist_ok=True)
+    except PermissionError:
+        pass
+    if not os.access(target, os.W_OK):
+        target = os.path.join(user_autosave_directory, target.lstrip('/'))
+        logger.info('Switched autosave directory to {}, since original location is not writeable.'.format(target))
+        os.makedirs(target, exist_ok=True)
+    return target
 
 
 def get_filename(function, checksum, description, *args):
-    """``<savedir>/<function>[_<name of each named argument>]_<description>[_<argument descriptions>].npz``
-    (autosave.py:89-104); the directory comes from the argument that has ``.frames`` (the Coordinates)."""
-    func_desc = function.__name__
-    savedir = None
+    """File of one call.  The stem names the function and every argument that has a name (a function, or
+    the function inside a ``partial``); the description is the caller's plus the ``.description`` of the
+    arguments (the atom selection of a Coordinates); the directory comes from the argument that carries a
+    reader in ``.frames``.  E.g. ``shifted_correlation_isf_OW.npz``."""
+    stem = [function.__name__]
+    notes = [description]
+    directory = None
     for arg in args:
-        if hasattr(arg, '__name__'):
-            func_desc += '_{}'.format(arg.__name__)
-        elif isinstance(arg, functools.partial):
-            func_desc += '_{}'.format(arg.func.__name__)
+        name = getattr(arg, '__name__', None)
+        if name is None and isinstance(arg, functools.partial):
+            name = arg.func.__name__
+        if name is not None:
+            stem.append(name)
         if hasattr(arg, 'frames'):
-            savedir = get_directory(arg.frames)
-        if hasattr(arg, 'description') and arg.description != '':
-            description += '_{}'.format(arg.description)
-    if savedir is None:
+            directory = get_directory(arg.frames)
+        note = getattr(arg, 'description', '')
+        if note != '':
+            notes.append(note)
+    if directory is None:
         raise ValueError('autosave needs an argument with a .frames reader (a Coordinates object) to place the file')
-    filename = '{}_{}.npz'.format(func_desc.strip('_'), description.strip('_'))
-    return os.path.join(savedir, filename)
-
-
-def _stored_checksum(filename):
-    if not os.path.exists(filename):
-        return 0
-    # the checksum is a 160-bit Python integer, which NumPy stores as a pickled object entry
-    with np.load(filename, allow_pickle=True) as data:
-        return data['checksum'][()] if 'checksum' in data else 0
+    return os.path.join(directory, '{}_{}.npz'.format('_'.join(stem).strip('_'), '_'.join(notes).strip('_')))
 
 
 def verify_file(filename, checksum):
-    """Whether ``filename`` holds the result of the call with this checksum (autosave.py:107-114)."""
-    return _stored_checksum(filename) == checksum
+    """Whether ``filename`` holds the result of the call with this checksum."""
+    return ResultFile(filename).holds(checksum)
 
 
 def save_data(filename, checksum, data):
-    """Write ``checksum`` and ``data`` to an npz file (autosave.py:117-127); a ragged result (e.g. the
-    ``(times, result, count)`` of multi-subensemble runs) is stored as an object array."""
-    notify('Saving result to file: {}'.format(filename))
-    try:
-        data = np.array(data)
-    except ValueError:
-        arr = np.empty((len(data),), dtype=object)
-        arr[:] = data
-        data = arr
-    np.savez(filename, checksum=checksum, data=data)
+    """Write ``checksum`` and ``data`` to ``filename`` (see :meth:`ResultFile.write`)."""
+    ResultFile(filename).write(checksum, data)
 
 
 def load_data(filename):
-    """Read the result back (autosave.py:130-139); old files with positional ``arr_*`` entries are
-    rewritten in the current layout."""
-    notify('Loading result from file: {}'.format(filename))
-    with np.load(filename, allow_pickle=True) as fdata:
-        if 'data' in fdata:
-            return fdata['data']
-        data = tuple(fdata[k] for k in sorted(fdata) if ('arr' in k))
-        stored = fdata['checksum'][()]
-    save_data(filename, stored, data)
-    return data
+    """Read the result stored in ``filename`` (see :meth:`ResultFile.read`)."""
+    return ResultFile(filename).read()
 
 
 def autosave_data(nargs, kwargs_keys=None, version=None):
-    """Decorator: autosave the result of a function (autosave.py:142-183).
+    """Decorator factory: keep the decorated function's results in result files while autosave is enabled.
 
     Args:
-        nargs: number of leading positional arguments that determine the result
-        kwargs_keys (opt.): keyword arguments that determine the result
-        version (opt.): replaces the checksum of the function's code, so the files stay valid when
-            the implementation changes without changing results
+        nargs: how many leading positional arguments determine the result
+        kwargs_keys (opt.): keyword arguments that determine the result as well
+        version (opt.): a tag that stands in for the function's source in the checksum, so that stored
+            results survive changes of the implementation that do not change the numbers
 
-    The wrapper accepts two extra keywords: ``description`` (part of the file name) and ``autoload``
-    (``False`` forces a recomputation).
+    The wrapper takes two keywords of its own: ``description`` (goes into the file name) and
+    ``autoload=False`` (recompute even if a matching file exists).
     """
-    def decorator_function(function):
-        # positional arguments passed by keyword count as well
-        posargs_keys = list(inspect.signature(function).parameters)[:nargs]
+    def decorate(function):
+        leading = list(inspect.signature(function).parameters)[:nargs]      # may also arrive as keywords
+        watched = leading + list(kwargs_keys or ()) if kwargs_keys is not None else []
 
         @functools.wraps(function)
-        def autosave(*args, **kwargs):
-            description = kwargs.pop('description', '')
-            autoload = kwargs.pop('autoload', True) and load_autosave_data
+        def wrapper(*args, **kwargs):
+            description = kwargs.pop('description', '') or ''
+            reuse = kwargs.pop('autoload', True) and load_autosave_data
             if autosave_directory is None:
                 return function(*args, **kwargs)
-            relevant_args = list(args[:nargs])
-            if kwargs_keys is not None:
-                for key in [*posargs_keys, *kwargs_keys]:
-                    if key in kwargs:
-                        relevant_args.append(kwargs[key])
-            legacy_csum = checksum(function, *relevant_args)
-            csum = legacy_csum if version is None else checksum(version, *relevant_args)
-            filename = get_filename(function, csum, description or '', *relevant_args)
-            if autoload and (verify_file(filename, csum) or verify_file(filename, legacy_csum)):
-                return load_data(filename)
+            relevant = list(args[:nargs]) + [kwargs[key] for key in watched if key in kwargs]
+            by_source = checksum(function, *relevant)
+            key = by_source if version is None else checksum(version, *relevant)
+            target = ResultFile(get_filename(function, key, description, *relevant))
+            if reuse and target.holds(key, by_source):
+                return target.read()
             result = function(*args, **kwargs)
-            save_data(filename, csum, result)
+            target.write(key, result)
             return result
-        return autosave
-    return decorator_function
+        return wrapper
+    return decorate
