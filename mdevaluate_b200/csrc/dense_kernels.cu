@@ -12,6 +12,10 @@
 // per-lag sums over origins and atoms live in registers until the very end: thread (atom i, slice j)
 // handles the lags l = j, j+4, ..., j+28 of the block (kL = 32).  Partials per atom split are added by a small
 // second kernel in fixed order (bit-reproducible).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mdb {
@@ -104,7 +108,87 @@ __device__ __forceinline__ void store_quad(const DenseDev &p, const Quad &q, int
     }
 }
 
-template <bool IMG, int FLAGS>
+// Candidate staging (MDB_DENSE_STAGE=warp, NOT the default: written at the end of round 1 without GPU time left
+// to measure it).  The loop above spends ~170 instructions per quad on index arithmetic -- a division by 48
+// per quad, v / 3 per value, bounds and row-map tests -- which is 58 % (MSD) / 39 % (ISF) of all instructions the
+// kernel executes (scripts/sass_budget.py).  Here a WARP owns rows r = warp, warp + 8, ...; lane l always takes
+// quad l and, for l < kQuadsPerRow - 32, quad l + 32 of a row, so the position of each of its values in the
+// [3][tile] row (component, atom) and the box length it needs are per-lane constants computed once per kernel;
+// kRowBatch rows are loaded before any is unwrapped (memory parallelism as before).
+constexpr int kRowBatch = 4;
+
+struct LaneMap {
+    double *dst[2][4];    // where value k of the lane's quad 0 / 1 goes in row 0 of the structure-of-arrays tile
+    double box[2][4];     // box length of that value's component (constant box only)
+};
+
+__device__ __forceinline__ LaneMap make_lane_map(const DenseDev &p, int lane, double *s_rows) {
+    LaneMap m;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = 4 * (lane + 32 * h) + k;
+            const int atom = v / 3, c = v - 3 * atom;
+            m.dst[h][k] = s_rows + c * kTileAtoms + atom;
+            m.box[h][k] = c == 0 ? p.box_const[0] : (c == 1 ? p.box_const[1] : p.box_const[2]);
+        }
+    return m;
+}
+
+// FULL: every quad of the tile lies inside the shard (all tiles but the last): no bounds tests at all.
+// Rows past the end of the block are clamped to its last row: a few warps then stage that row again with the
+// same values, which is cheaper than predicating every load and store of the batch.
+template <bool IMG, bool FULL>
+__device__ __forceinline__ void stage_rows_warp(const DenseDev &p, const LaneMap &map, int lane, int warp, int atom0,
+                                                int ns, int n_rows, int f_origin0, int f_partner0) {
+    static_assert(kQuadsPerRow > 32 && kQuadsPerRow <= 64, "two quads per lane cover a row");
+    constexpr int row_doubles = 3 * kTileAtoms;
+    const bool second = lane + 32 < kQuadsPerRow;
+    const long long e0 = 3ll * atom0 + 4 * lane, e_end = 3ll * p.n_atoms;
+    const bool live0 = FULL || e0 < e_end, live1 = second && (FULL || e0 + 128 < e_end);
+    const float *src0 = p.coords + e0;
+    const uint8_t *img0 = IMG ? p.images + e0 : nullptr;
+    for (int rb = warp; rb < n_rows; rb += 8 * kRowBatch) {
+        float4 x[kRowBatch][2];
+        uint32_t n[kRowBatch][2];
+#pragma unroll
+        for (int u = 0; u < kRowBatch; ++u) {
+            const int r = min(rb + 8 * u, n_rows - 1);
+            const int frame = (r < ns) ? f_origin0 + r * p.ostep : f_partner0 + (r - ns);
+            const long long row = row_of(p, frame);
+            x[u][0] = x[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            n[u][0] = n[u][1] = 0x80808080u;
+            if (live0) {
+                x[u][0] = __ldg(reinterpret_cast<const float4 *>(src0 + row * p.pitch));
+                if (IMG) n[u][0] = __ldg(reinterpret_cast<const uint32_t *>(img0 + row * p.img_pitch));
+            }
+            if (live1) {
+                x[u][1] = __ldg(reinterpret_cast<const float4 *>(src0 + row * p.pitch + 128));
+                if (IMG) n[u][1] = __ldg(reinterpret_cast<const uint32_t *>(img0 + row * p.img_pitch + 128));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kRowBatch; ++u) {
+            const int r = min(rb + 8 * u, n_rows - 1);
+            const int shift = r * row_doubles;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 0 || second) {
+                    const float xs[4] = {x[u][h].x, x[u][h].y, x[u][h].z, x[u][h].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double value = (double)xs[k];
+                        if (IMG) value = fma(-image_count(n[u][h], k), map.box[h][k], value);
+                        map.dst[h][k][shift] = value;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool IMG, int FLAGS, bool STAGE_WARP>
 __global__ void __launch_bounds__(kDenseThreads, MDB_DENSE_CTAS) dense_corr_kernel(const DenseDev p) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
@@ -122,6 +206,8 @@ __global__ void __launch_bounds__(kDenseThreads, MDB_DENSE_CTAS) dense_corr_kern
     double acc2[kSlots], accs[kSlots];
 #pragma unroll
     for (int m = 0; m < kSlots; ++m) acc2[m] = accs[m] = 0.0;
+    LaneMap lane_map;
+    if constexpr (STAGE_WARP) lane_map = make_lane_map(p, tid & 31, s_rows);
 
     const int t_begin = split * p.tiles_per_split;
     const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
@@ -136,6 +222,12 @@ __global__ void __launch_bounds__(kDenseThreads, MDB_DENSE_CTAS) dense_corr_kern
             const int n_partner = (ns - 1) * p.ostep + nl;
             __syncthreads();                              // the previous block is done with the rows
             const int n_rows = ns + n_partner;
+            if constexpr (STAGE_WARP) {
+                if (atom0 + kTileAtoms <= p.n_atoms)
+                    stage_rows_warp<IMG, true>(p, lane_map, tid & 31, tid >> 5, atom0, ns, n_rows, f_origin0, f_partner0);
+                else
+                    stage_rows_warp<IMG, false>(p, lane_map, tid & 31, tid >> 5, atom0, ns, n_rows, f_origin0, f_partner0);
+            } else {
             // stage the rows: kStageBatch independent 128-bit loads per thread in flight, then unwrap + store
             const int n_quads = n_rows * kQuadsPerRow;
             for (int w0 = tid; w0 < n_quads; w0 += kDenseThreads * kStageBatch) {
@@ -158,6 +250,7 @@ __global__ void __launch_bounds__(kDenseThreads, MDB_DENSE_CTAS) dense_corr_kern
                         store_quad<IMG>(p, q[u], frame, qd, s_rows + (size_t)r * row_doubles);
                     }
                 }
+            }
             }
             __syncthreads();
             if (live) {
@@ -326,16 +419,22 @@ extern "C" int mdb_dense_corr(const mdb_dense_args *a, void *stream) {
     };
     int rc;
     const bool img = a->images != nullptr;
+    const char *stage = getenv("MDB_DENSE_STAGE");
+    const bool warp_stage = stage && strcmp(stage, "warp") == 0 && kDenseThreads == 256 && !(img && a->box);   // candidate, off by default; constant box only
+    auto pick = [&](auto flags_c) -> int {
+        constexpr int F = decltype(flags_c)::value;
+        if (warp_stage) return img ? launch(dense_corr_kernel<true, F, true>) : launch(dense_corr_kernel<false, F, true>);
+        return img ? launch(dense_corr_kernel<true, F, false>) : launch(dense_corr_kernel<false, F, false>);
+    };
     switch (a->flags) {
         case MDB_SUM_R2:
-            rc = img ? launch(dense_corr_kernel<true, MDB_SUM_R2>) : launch(dense_corr_kernel<false, MDB_SUM_R2>);
+            rc = pick(std::integral_constant<int, MDB_SUM_R2>{});
             break;
         case MDB_SUM_SINC:
-            rc = img ? launch(dense_corr_kernel<true, MDB_SUM_SINC>) : launch(dense_corr_kernel<false, MDB_SUM_SINC>);
+            rc = pick(std::integral_constant<int, MDB_SUM_SINC>{});
             break;
         default:
-            rc = img ? launch(dense_corr_kernel<true, MDB_SUM_R2 | MDB_SUM_SINC>)
-                     : launch(dense_corr_kernel<false, MDB_SUM_R2 | MDB_SUM_SINC>);
+            rc = pick(std::integral_constant<int, MDB_SUM_R2 | MDB_SUM_SINC>{});
     }
     if (rc) return rc;
     const int n_out = a->n_lags * 2;

@@ -811,3 +811,25 @@ def test_generate_nojump_matrixes_from_a_subset_covers_all_atoms(small, md):
     np.testing.assert_array_equal(dense, g['jumps'])
     t, r = md.correlation.shifted_correlation(md.correlation.msd, subset.nojump, segments=6, window=0.4)
     close(r, g['msd_sel'], scale=float(np.nanmax(g['msd_sel'])), rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('MDB_TEST_CANDIDATES'),
+                    reason='unmeasured round-2 candidates run only with MDB_TEST_CANDIDATES=1')
+@pytest.mark.parametrize('n_atoms,n_frames,segments', [(96, 240, 120), (131, 200, 50), (300, 150, 75), (1000, 130, 65)])
+def test_candidate_dense_warp_staging(md, monkeypatch, n_atoms, n_frames, segments):
+    """MDB_DENSE_STAGE=warp (csrc/dense_kernels.cu::stage_rows_warp): same sums as the default staging, bit for bit
+    (the staged rows are identical, the evaluation code is shared)."""
+    from mdevaluate_b200.synthetic import random_walk
+    pos, box, times = random_walk(n_atoms, n_frames, seed=n_atoms, sigma=0.08, box=1.7)
+    c = md.correlation
+    monkeypatch.setattr(c, 'DENSE_MIN_PAIRS', 1)
+    dense = lambda a, b: np.arange(a, b)
+    for fn in (c.msd, partial(c.isf, q=22.7)):
+        for mode in ('nojump', 'raw'):
+            coords = md.Coordinates.from_arrays(pos, box, times)
+            frames = coords.nojump if mode == 'nojump' else coords
+            _, ref = c.shifted_correlation(fn, frames, segments=segments, window=0.5, average=True, index_distribution=dense)
+            monkeypatch.setenv('MDB_DENSE_STAGE', 'warp')
+            _, got = c.shifted_correlation(fn, frames, segments=segments, window=0.5, average=True, index_distribution=dense)
+            monkeypatch.delenv('MDB_DENSE_STAGE')
+            np.testing.assert_array_equal(got, ref)
