@@ -71,6 +71,8 @@ struct CorrDev {
     int bin_mode;
     double dx, inv_dx;
     float inv_dx_f;
+    int hist_f32;        // candidate (MDB_HIST_F32=1): van Hove alone, float32 displacements for the bin estimate
+                         // (sits in what was padding: the parameter offsets of the measured kernels do not move)
     const double *edges;
     double *partial;     // [S*L][n_ablocks][3]
     unsigned long long *hist;
@@ -593,6 +595,94 @@ __device__ __forceinline__ void process_tile_sinc_f32(const CorrDev &p, Ring &ri
     }
 }
 
+// ---- CANDIDATE, not the default (MDB_HIST_F32=1; written after the round-1 GPU budget was spent, unmeasured) ------
+// van Hove alone, uniform bins, one constant float32 box: the same float32 displacements as the ISF path feed the
+// branch-free bin ESTIMATE; a sample within the (wider) margin of a bin edge is recomputed from the raw values with the
+// reference's float64 arithmetic and utils.histogram's rule, so the counts stay exact.  The margin 1.6e-6 t + 1e-6
+// covers the estimate's error with float32 displacements (tests/test_histogram_estimate.py replays it on the CPU).
+constexpr int kVariantF32 = 64;      // pseudo flag bit that selects this instantiation
+
+__device__ __noinline__ void exact_hist_from_raw(double bx, double by, double bz, double dx, double inv_dx, int n_bins,
+                                                 float x0, float y0, float z0, uint32_t n0, float xt, float yt, float zt,
+                                                 uint32_t nt, unsigned int *s_hist_k) {
+    // n0 / nt: the three excess-128 image bytes of the atom in bytes 0..2; scalars, not the parameter struct,
+    // cross the call (a reference to it would force a local copy)
+    const double ddx = fma(-image_count(n0, 0), bx, (double)x0) - fma(-image_count(nt, 0), bx, (double)xt);
+    const double ddy = fma(-image_count(n0, 1), by, (double)y0) - fma(-image_count(nt, 1), by, (double)yt);
+    const double ddz = fma(-image_count(n0, 2), bz, (double)z0) - fma(-image_count(nt, 2), bz, (double)zt);
+    // exact_bin()'s uniform-bin rule, spelled out here so that exact_bin keeps exactly the callers it was measured with
+    const long long kk = exact_floor_div(sqrt(r2_unfused(ddx, ddy, ddz)), dx, inv_dx);
+    if (kk < n_bins) atomicAdd(&s_hist_k[(int)kk], 1u);
+}
+
+// bytes of components 3a, 3a+1, 3a+2 of the group's 12 (three packed words) in bytes 0..2 of one word
+__device__ __forceinline__ uint32_t atom_image_bytes(const uint32_t (&w)[3], int a) {
+    const int c = 3 * a;
+    const uint32_t lo = w[c >> 2], hi = w[(c + 2) >> 2];
+    return __byte_perm(lo, hi, (uint32_t)((c & 3) | ((((c + 1) >> 2) == (c >> 2) ? ((c + 1) & 3) : (4 + ((c + 1) & 3))) << 4) |
+                                          ((((c + 2) >> 2) == (c >> 2) ? ((c + 2) & 3) : (4 + ((c + 2) & 3))) << 8) | (0x4u << 12)));
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void process_tile_hist_f32(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
+                                                      const unsigned char *stages, int stage_bytes, int tid,
+                                                      uint32_t vmask, int nl, unsigned int *s_hist) {
+    const f32x2 *neg_box = reinterpret_cast<const f32x2 *>(p.neg_box2);
+    float raw0[12];
+    uint32_t w0[3];
+    fetch_raw<true>(ring, full0, empty0, stages, stage_bytes, tid, raw0, w0);
+    f32x2 x0[6], f0[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        x0[j] = pack2(raw0[2 * j], raw0[2 * j + 1]);
+        f0[j] = pack2(image_float(w0[(2 * j) >> 2], (2 * j) & 3), image_float(w0[(2 * j + 1) >> 2], (2 * j + 1) & 3));
+    }
+#pragma unroll 1
+    for (int k = 0; k < nl; ++k) {
+        float rawt[12];
+        uint32_t wt[3];
+        fetch_raw<true>(ring, full0, empty0, stages, stage_bytes, tid, rawt, wt);
+        float d[12];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const f32x2 ft = pack2(image_float(wt[(2 * j) >> 2], (2 * j) & 3),
+                                   image_float(wt[(2 * j + 1) >> 2], (2 * j + 1) & 3));
+            const f32x2 dn = sub2(f0[j], ft);
+            float dn0, dn1;
+            unpack2(dn, dn0, dn1);
+            const f32x2 up = pack2(fmaxf(dn0, 0.0f), fmaxf(dn1, 0.0f));
+            const f32x2 dw = sub2(up, dn);
+            const f32x2 o = fma2(up, neg_box[j % 3], x0[j]);
+            const f32x2 t = fma2(dw, neg_box[j % 3], pack2(rawt[2 * j], rawt[2 * j + 1]));
+            unpack2(sub2(o, t), d[2 * j], d[2 * j + 1]);
+        }
+        unsigned int *s_hist_k = s_hist + k * p.n_bins;
+        uint32_t slow = 0u;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float r2f = fmaf(d[3 * a + 2], d[3 * a + 2], fmaf(d[3 * a + 1], d[3 * a + 1], d[3 * a] * d[3 * a]));
+            const bool live = !MASKED || ((vmask >> a) & 1u);
+            const float t = (r2f * rsqrt_approx(r2f)) * p.inv_dx_f;               // NaN for r = 0 -> exact path
+            const float tb = t + 12582912.0f;
+            const float tr = tb - 12582912.0f;                                    // rint(t) for t < 2^22
+            const float dist = t - tr;
+            const float margin = fmaf(t, 1.6e-6f, 1.0e-6f);
+            const int bin = (__float_as_int(tb) - 0x4B400000) - (dist < 0.0f ? 1 : 0);
+            const bool fast = fabsf(dist) > margin;
+            if (live && fast && bin < p.n_bins) atomicAdd(&s_hist_k[bin], 1u);
+            slow |= (live && !fast) ? (1u << a) : 0u;
+        }
+        if (slow) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (slow & (1u << a))
+                    exact_hist_from_raw(p.box_const[0], p.box_const[1], p.box_const[2], p.dx, p.inv_dx, p.n_bins, raw0[3 * a],
+                                        raw0[3 * a + 1], raw0[3 * a + 2], atom_image_bytes(w0, a), rawt[3 * a],
+                                        rawt[3 * a + 1], rawt[3 * a + 2], atom_image_bytes(wt, a), s_hist_k);
+        }
+    }
+}
+
 // One tile of 1024 atoms: origin group into registers, then the lag rows of the chunk one by one.
 // The loop over lags is NOT unrolled (the body is 4 evaluations, ~1 KiB of code, and stays in the
 // instruction cache); per-lag accumulators live in shared memory, one private column per thread.
@@ -608,6 +698,10 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
     constexpr bool kHistF32 = kHist && !IMG;
     constexpr int NV = (kR2 ? 1 : 0) + (kR4 ? 1 : 0) + (kSinc ? 1 : 0);
+    if constexpr (FLAGS == (MDB_HIST | kVariantF32) && IMG && BOXC) {
+        process_tile_hist_f32<MASKED>(p, ring, full0, empty0, stages, stage_bytes, tid, vmask, nl, s_hist);
+        return;
+    }
     if constexpr (FLAGS == MDB_SUM_SINC && IMG && BOXC) {
         if (p.sinc_f32) {          // uniform over the launch
             process_tile_sinc_f32<MASKED>(p, ring, full0, empty0, stages, stage_bytes, tid, vmask, nl, s_acc);
@@ -898,7 +992,13 @@ int launch_typed(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st)
         case R2: return launch_flags<CT, IMG, R2>(p, plan, st);
         case SC: return launch_flags<CT, IMG, SC>(p, plan, st);
         case R2 | R4: return launch_flags<CT, IMG, R2 | R4>(p, plan, st);
-        case H: return launch_flags<CT, IMG, H>(p, plan, st);
+        case H:
+            if constexpr (sizeof(CT) == 4 && IMG) {
+                if (p.hist_f32 && plan.bulk && p.box == nullptr)      // candidate instantiation, off by default
+                    return launch_kernel(corr_bulk_kernel<true, H | kVariantF32, true>, p, plan, kBulkThreads, st,
+                                         plan.stages);
+            }
+            return launch_flags<CT, IMG, H>(p, plan, st);
         case R2 | R4 | H: return launch_flags<CT, IMG, R2 | R4 | H>(p, plan, st);
         case MDB_SUM_LEGENDRE:
             if constexpr (!IMG) return launch_flags<CT, false, MDB_SUM_LEGENDRE>(p, plan, st);
@@ -968,6 +1068,9 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     // ISF alone with one float32-representable box (what trajectory formats store): float32 displacements
     p.sinc_f32 = a->flags == MDB_SUM_SINC && a->images && !a->box && getenv("MDB_SINC_F64") == nullptr;
     for (int d = 0; d < 3; ++d) p.sinc_f32 = p.sinc_f32 && (double)(float)a->box_const[d] == a->box_const[d];
+    p.hist_f32 = a->flags == MDB_HIST && a->bin_mode == MDB_BINS_UNIFORM && a->images && !a->box &&
+                 getenv("MDB_HIST_F32") != nullptr;
+    for (int d = 0; d < 3; ++d) p.hist_f32 = p.hist_f32 && (double)(float)a->box_const[d] == a->box_const[d];
     p.q2f = (float)p.q2;
     {
         const float nb[3] = {-(float)a->box_const[0], -(float)a->box_const[1], -(float)a->box_const[2]};

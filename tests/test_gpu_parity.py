@@ -833,3 +833,32 @@ def test_candidate_dense_warp_staging(md, monkeypatch, n_atoms, n_frames, segmen
             _, got = c.shifted_correlation(fn, frames, segments=segments, window=0.5, average=True, index_distribution=dense)
             monkeypatch.delenv('MDB_DENSE_STAGE')
             np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('MDB_TEST_CANDIDATES'),
+                    reason='unmeasured round-2 candidates run only with MDB_TEST_CANDIDATES=1')
+def test_candidate_van_hove_float32_estimate(small, md, monkeypatch):
+    """MDB_HIST_F32=1 (csrc/corr_kernels.cu::process_tile_hist_f32): float32 displacements for the bin estimate,
+    the reference's float64 arithmetic for samples near an edge -- the counts must stay EXACT."""
+    from mdevaluate_b200.synthetic import random_walk
+    g, coords = small
+    c = md.correlation
+    monkeypatch.setenv('MDB_HIST_F32', '1')
+    t, r = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords.nojump, segments=12, window=0.4)
+    np.testing.assert_array_equal(r, g['vh_nojump'])
+    sel = c.subensemble_correlation(lambda f: np.where(np.asarray(f)[:, 2] % 1.5 < 0.6)[0])
+    _, masked = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords.nojump, segments=9, window=0.4,
+                                      correlation=sel)
+    monkeypatch.delenv('MDB_HIST_F32')
+    _, masked_ref = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords.nojump, segments=9, window=0.4,
+                                          correlation=sel)
+    np.testing.assert_array_equal(masked, masked_ref)
+    # a box of config-2 size, 500 bins, enough samples to land within 1e-6 of bin edges
+    pos, box, times = random_walk(20000, 300, seed=3, sigma=0.05, box=14.4)
+    big = md.Coordinates.from_arrays(pos, box, times)
+    bins = np.linspace(0, 3.0, 501)
+    _, ref = c.shifted_correlation(partial(c.van_hove_self, bins=bins), big.nojump, segments=20)
+    monkeypatch.setenv('MDB_HIST_F32', '1')
+    _, got = c.shifted_correlation(partial(c.van_hove_self, bins=bins), big.nojump, segments=20)
+    monkeypatch.delenv('MDB_HIST_F32')
+    np.testing.assert_array_equal(got, ref)
