@@ -132,7 +132,7 @@ def test_c_abi_struct_layout_matches_header():
     # field order/count of the ctypes mirrors vs the header structs
     header = open(os.path.join(ROOT, 'include', 'mdevaluate_b200.h')).read()
     for cname, ctype in (('mdb_corr_args', L.CorrArgs), ('mdb_nojump_args', L.NojumpArgs),
-                         ('mdb_dense_args', L.DenseArgs)):
+                         ('mdb_dense_args', L.DenseArgs), ('mdb_jumpmat_args', L.JumpMatArgs)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), header, re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
         fields = [re.split(r'[\s\*]+', f.strip())[-1].split('[')[0] for f in body.split(';') if f.strip()]
@@ -148,6 +148,11 @@ def test_argument_errors_without_gpu():
     assert lib.mdb_nojump_scan(C.byref(nj), None) == 1
     assert lib.mdb_nojump_apply(None, None, None, 0, None, None) == 1
     assert lib.mdb_dense_corr(C.byref(L.DenseArgs()), None) == 1
+    assert lib.mdb_nojump_images_from_jumps(C.byref(L.JumpMatArgs()), None) == 1
+    assert lib.mdb_copy_rows_h2d(None, 0, None, 0, 0, 0, None) == 1
+    buf = (C.c_char * 64)()
+    assert lib.mdb_copy_rows_h2d(buf, 8, buf, 16, 32, 2, None) == 1     # width > pitch
+    assert lib.mdb_copy_rows_h2d(buf, 8, buf, 8, 0, 0, None) == 0       # nothing to copy: no CUDA call
 
 
 def test_no_cpu_fallback():
