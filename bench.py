@@ -169,9 +169,11 @@ def reference_arm(a):
     from oracle import md_oracle as orc
     starts, num = orc.schedule(a.frames, a.segments, a.window, a.skip or 0)
     S, L = len(starts), len(orc.log_indices(0, num))
-    # bounded sample: aim at ~120 s for the whole run at ~1.5e7 evals/s on one core
+    # bounded sample: aim at ~120 s for the whole run at the ~4e6 evals/s one core does on the whole step (jump
+    # detection and unwrapping included; the per-frame Python overhead of the 10 000-frame pass sets a floor of a few
+    # seconds per step whatever the sample)
     budget = 120.0 / max(1, a.steps + a.warmup)
-    n = int(min(a.cpu_atoms, max(1024, budget * 1.5e7 / (S * L))))
+    n = int(min(a.cpu_atoms, max(1024, budget * 4e6 / (S * L))))
     n = min(n, a.atoms)
     pos, box, times = random_walk(n, a.frames, seed=20240, box=box_length(a.atoms))
     evals = n * S * L
