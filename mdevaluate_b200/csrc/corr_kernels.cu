@@ -29,6 +29,9 @@
 // accumulator.  Histogram bins follow utils.histogram exactly (utils.py:328-338): a float32
 // estimate decides every sample that is not within rounding distance of a bin edge, the rest
 // take the exact float64 path (np.floor_divide semantics or np.histogram edge search).
+// Exception: launches that ask for the ISF alone on rows with one constant float32 box take their
+// displacements in float32 (process_tile_sinc_f32: the operand on the far side of the periodic boundary is
+// moved first, which keeps every component good to 2^-23 -- the accuracy of the float32 sinc it feeds).
 #include <stdlib.h>
 
 #include "common.cuh"
