@@ -15,7 +15,8 @@
  *     the call returns;
  *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream); all
  *     work is enqueued on it and the call does not synchronise unless stated;
- *   - no hidden global state: calls are re-entrant per stream.
+ *   - no hidden global state: calls are re-entrant per stream, nothing is read from the environment; every
+ *     switch is a field of an argument struct (`mdb_tuning`), 0 = the measured default.
  *
  * Reference lines are relative to /root/reference/mdevaluate/.
  */
@@ -29,18 +30,40 @@
 extern "C" {
 #endif
 
-#define MDB_ABI_VERSION 1
+#define MDB_ABI_VERSION 2
 
 typedef enum mdb_status {
     MDB_OK = 0,
     MDB_ERR_ARGUMENT = 1,     /* NULL / negative size / misaligned / inconsistent arguments */
     MDB_ERR_CUDA = 2,         /* a CUDA runtime call failed (text in mdb_last_error) */
     MDB_ERR_UNSUPPORTED = 3,  /* valid request this build has no kernel for */
-    MDB_ERR_WORKSPACE = 4     /* workspace missing or too small */
+    MDB_ERR_WORKSPACE = 4,    /* workspace missing or too small */
+    MDB_ERR_TIMEOUT = 5       /* a peer GPU did not deliver its partial sums in time (mdb_comm) */
 } mdb_status;
 
 /* image counts are stored as uint8 = count + MDB_IMAGE_BIAS */
 #define MDB_IMAGE_BIAS 128
+
+/* Image-count storage.  The jump scan writes MDB_IMAGE_BYTES (one excess-128 byte per component).  When no count
+ * leaves [-1, 1] -- the rule for liquids whose atoms travel less than a box length -- mdb_images_pack re-codes the
+ * rows as MDB_IMAGE_PACKED: one 32-bit word per group of 4 atoms, byte a of the word = atom a of the group,
+ * bits 0-1 / 2-3 / 4-5 = n_x+1, n_y+1, n_z+1, bits 6-7 zero (1 byte instead of 3 per atom and frame: the
+ * correlation kernels then move 13 instead of 15 bytes per evaluation).  Counts beyond +-127 are kept as int16
+ * (MDB_IMAGE_I16, direct-load kernel). */
+#define MDB_IMAGE_BYTES  1
+#define MDB_IMAGE_PACKED 2
+#define MDB_IMAGE_I16    3
+
+/* Explicit switches of the kernels; 0 everywhere = the measured defaults. */
+typedef struct mdb_tuning {
+    int32_t ring_stages;     /* depth of the bulk-copy ring (3..8); 0 = what fits                             */
+    int32_t atom_blocks;     /* atom-block split of a correlation launch; 0 = wave model                      */
+    int32_t isf_float64;     /* 1: ISF displacements through the float64 chain (default float32, see DESIGN)  */
+    int32_t hist_float64;    /* 1: van Hove (and fused van Hove + alpha_2) displacements in float64           */
+    int32_t scan_direct;     /* 1: register-load variant of the jump scan instead of the bulk-copy ring       */
+    int32_t dense_stage_cta; /* 1: CTA-wide staging loop of the dense kernel instead of warp-per-row          */
+    int32_t reserved[2];
+} mdb_tuning;
 
 /* coordinate element type */
 #define MDB_F32 0
@@ -114,6 +137,12 @@ typedef struct mdb_corr_args {
     unsigned long long *hist;    /* DEVICE out [S*L*B] (zeroed by the call); NULL without HIST   */
     void *workspace;             /* DEVICE scratch of mdb_corr_workspace_bytes()                 */
     size_t workspace_bytes;
+    const uint32_t *packed;      /* DEVICE [n_rows][packed_pitch] MDB_IMAGE_PACKED rows, or NULL; preferred over
+                                    `images` when both are given                                   */
+    int64_t packed_pitch;        /* 32-bit words per packed row, >= ceil(n_atoms/4)              */
+    const int16_t *images16;     /* DEVICE [n_rows][img16_pitch] MDB_IMAGE_I16 rows, or NULL      */
+    int64_t img16_pitch;         /* int16 elements per row, >= 3*n_atoms                         */
+    mdb_tuning tuning;
 } mdb_corr_args;
 
 int mdb_corr_workspace_bytes(const mdb_corr_args *args, size_t *bytes);
@@ -125,6 +154,64 @@ int mdb_corr_last_launches(void);
  * the launch stream; mdb_corr_last_kernel_ms waits for that kernel and returns its duration. */
 int mdb_corr_profile(int enable);
 int mdb_corr_last_kernel_ms(float *ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Repeated calls: a PLAN owns everything one `shifted_correlation` call needs besides the frame rows --
+ * the atom-block workspace, the per-(origin, lag) sums and histogram on the device, and a page-locked
+ * host block the results land in -- so that one call is two kernel launches and no allocation:
+ *
+ *   corr kernel  ->  finish kernel: adds the atom-block partials in fixed order, (with a communicator)
+ *                    exchanges them with the peer GPUs and adds the shards in rank order, writes the sums
+ *                    to the device buffer and, through the mapped host block, straight into host memory,
+ *                    then raises a sequence flag the host is polling.
+ *
+ * The caller keeps ownership of coords / images / packed / box / rows / select / edges (DEVICE, they must
+ * stay valid while the plan is used; `sums`, `hist`, `workspace` of `args` are ignored).  What the reference
+ * does per call in Python -- the S x L loop and the per-frame function calls, correlation.py:147-149,190-199 --
+ * is mdb_corr_plan_run.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mdb_corr_plan mdb_corr_plan;
+typedef struct mdb_comm mdb_comm;
+
+int mdb_corr_plan_create(const mdb_corr_args *args, mdb_comm *comm /* or NULL */, mdb_corr_plan **plan);
+/* Enqueue both kernels on `stream` and wait for the results (spins on the host flag; no cudaStreamSynchronize on
+ * the fast path).  With `time_slot` >= 0 the correlation kernel is bracketed by the CUDA event pair of that slot
+ * (0..MDB_PLAN_TIME_SLOTS-1); mdb_corr_plan_kernel_ms reads a slot afterwards. */
+#define MDB_PLAN_TIME_SLOTS 1024
+int mdb_corr_plan_run(mdb_corr_plan *plan, void *stream, int32_t time_slot);
+/* The two halves of mdb_corr_plan_run for callers that overlap host work with the kernels. */
+int mdb_corr_plan_launch(mdb_corr_plan *plan, void *stream, int32_t time_slot);
+int mdb_corr_plan_wait(mdb_corr_plan *plan);
+int mdb_corr_plan_kernel_ms(mdb_corr_plan *plan, int32_t time_slot, float *ms);
+/* HOST pointers into the plan's page-locked result block, valid until mdb_corr_plan_destroy: sums [S*L*3]
+ * (summed over the shards of `comm`), hist [S*L*B] or NULL.  Overwritten by the next run. */
+const double *mdb_corr_plan_sums(const mdb_corr_plan *plan);
+const unsigned long long *mdb_corr_plan_hist(const mdb_corr_plan *plan);
+/* DEVICE copies of the same (e.g. to feed another kernel without a round trip). */
+const double *mdb_corr_plan_sums_device(const mdb_corr_plan *plan);
+int mdb_corr_plan_launches(const mdb_corr_plan *plan);      /* kernels one run enqueues */
+int mdb_corr_plan_destroy(mdb_corr_plan *plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU, atoms sharded by contiguous blocks).  The one
+ * collective of the path -- the sum of the small per-(origin, lag) partials over the shards -- is done by
+ * the finish kernel itself over NVLink peer memory: every rank owns an inbox (device memory exported with
+ * CUDA IPC), the finish kernel of rank r stores its partials into slot r of EVERY rank's inbox, raises the
+ * per-slot sequence flags, waits for the flags of its own inbox and adds the slots in rank order (every
+ * rank gets bit-identical results).  Inboxes are double-buffered by sequence parity.  A peer that does not
+ * deliver within `timeout_ms` makes the run fail with MDB_ERR_TIMEOUT instead of hanging.
+ *
+ *   mdb_comm_create(rank, world, capacity, &comm);  mdb_comm_handle(comm, my_handle);
+ *   -- exchange the MDB_COMM_HANDLE_BYTES of all ranks by any means (torch.distributed.all_gather) --
+ *   mdb_comm_connect(comm, all_handles);
+ * ------------------------------------------------------------------------------------------ */
+#define MDB_COMM_HANDLE_BYTES 64
+#define MDB_COMM_MAX_RANKS 16
+int mdb_comm_create(int32_t rank, int32_t world, size_t capacity_words /* 8-byte words per rank slot */,
+                    int32_t timeout_ms, mdb_comm **comm);
+int mdb_comm_handle(mdb_comm *comm, void *handle_out /* HOST MDB_COMM_HANDLE_BYTES */);
+int mdb_comm_connect(mdb_comm *comm, const void *handles /* HOST world * MDB_COMM_HANDLE_BYTES, by rank */);
+int mdb_comm_destroy(mdb_comm *comm);
 
 /* ------------------------------------------------------------------------------------------
  * nojump, producer side: periodic-jump detection + running image count.
@@ -153,6 +240,10 @@ typedef struct mdb_nojump_args {
     float *coords_out;           /* DEVICE out, copy of kept frames (compaction), or NULL        */
     int64_t pitch_out;           /* floats per row of coords_out                                 */
     int32_t *overflow;           /* DEVICE int, set to 1 if a running count left [-128, 127]     */
+    int16_t *images16;           /* DEVICE out, cumulative counts as int16 per kept frame (MDB_IMAGE_I16), or NULL;
+                                    the fallback when `overflow` was raised: counts up to +-32767 */
+    int64_t img16_pitch;         /* int16 elements per row of images16                           */
+    mdb_tuning tuning;
 } mdb_nojump_args;
 
 int mdb_nojump_scan(const mdb_nojump_args *args, void *stream);
@@ -175,13 +266,24 @@ typedef struct mdb_jumpmat_args {
     uint8_t *images;             /* DEVICE out [n_keep][img_pitch] excess-128                     */
     int64_t img_pitch;           /* bytes per row, >= 3*n_atoms                                   */
     int32_t *overflow;           /* DEVICE int, set to 1 if a count left [-128, 127]; or NULL     */
+    int16_t *images16;           /* DEVICE out [n_keep][img16_pitch] plain int16 counts instead of `images` (pass
+                                    images = NULL): the fallback when `overflow` was raised       */
+    int64_t img16_pitch;
 } mdb_jumpmat_args;
 
 int mdb_nojump_images_from_jumps(const mdb_jumpmat_args *args, void *stream);
 
+/* MDB_IMAGE_BYTES rows -> MDB_IMAGE_PACKED rows (see above).  `max_abs` (DEVICE int, zeroed by the caller) receives
+ * the largest |count| seen: the packed rows are valid iff it ends up <= 1. */
+int mdb_images_pack(const uint8_t *images, int64_t img_pitch, int64_t n_rows, int32_t n_atoms, uint32_t *packed,
+                    int64_t packed_pitch, int32_t *max_abs, void *stream);
+
 /* nojump, consumer side (pbc.py:235-247): out = x - n*box in float64 for one frame row. */
 int mdb_nojump_apply(const float *coords_row, const uint8_t *images_row, const double box[3],
                      int32_t n_atoms, double *out, void *stream);
+/* The same for a row in any image format (`image_format` = MDB_IMAGE_BYTES / _PACKED / _I16). */
+int mdb_nojump_apply_format(const float *coords_row, const void *images_row, int32_t image_format, const double box[3],
+                            int32_t n_atoms, double *out, void *stream);
 
 /* Trajectory ingestion (the reference pulls frames one by one through its reader, coordinates.py:257-271):
  * `n_rows` rows of `width_bytes` from page-locked host memory (row stride `src_pitch_bytes`) into device rows
@@ -218,6 +320,9 @@ typedef struct mdb_dense_args {
     double *sums;                /* DEVICE out [n_lags*2]                                        */
     void *workspace;             /* DEVICE scratch of mdb_dense_workspace_bytes()                */
     size_t workspace_bytes;
+    const uint32_t *packed;      /* DEVICE MDB_IMAGE_PACKED rows, or NULL; preferred over `images` */
+    int64_t packed_pitch;
+    mdb_tuning tuning;
 } mdb_dense_args;
 
 int mdb_dense_workspace_bytes(const mdb_dense_args *args, size_t *bytes);

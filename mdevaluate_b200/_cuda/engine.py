@@ -7,11 +7,15 @@ Layout in HBM:
   of 4 floats so that every row is 16-byte aligned (float4 streaming);
 * ``images``  uint8 ``(n_rows, img_pitch)``: cumulative periodic image counts per component stored
   excess-128 (``count + IMAGE_BIAS``), same element order as ``coords`` (only for nojump);
+* ``packed``  int32 ``(n_rows, packed_pitch)``: the same counts when none leaves [-1, 1], one word per group of
+  4 atoms (byte a = atom a, bits 0-1 / 2-3 / 4-5 = n_x+1, n_y+1, n_z+1): what the correlation kernels stream;
+* ``images16`` int16 ``(n_rows, pitch)``: plain counts, the fallback beyond +-127;
 * ``box``     float64 ``(n_rows, 3)``: box diagonal of the frame stored in each row.
 """
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -30,32 +34,97 @@ def row_pitch(n_atoms):
     return _round_up(3 * n_atoms, 32)
 
 
+class Tuning:
+    """Explicit kernel switches (``mdb_tuning`` of the C ABI); 0 = the measured default.  Process-wide, read at every
+    launch / plan creation.  ``engine.tuning.isf_float64 = 1`` e.g. sends the ISF through the float64 chain."""
+    FIELDS = ('ring_stages', 'atom_blocks', 'isf_float64', 'hist_float64', 'scan_direct', 'dense_stage_cta')
+
+    def __init__(self):
+        for f in self.FIELDS:
+            setattr(self, f, 0)
+        self.use_packed = True          # host-side: hand the packed image rows to the kernels when a store has them
+
+    def fill(self, struct):
+        for f in self.FIELDS:
+            setattr(struct, f, int(getattr(self, f)))
+
+    def key(self):
+        return tuple(int(getattr(self, f)) for f in self.FIELDS) + (bool(self.use_packed),)
+
+
+tuning = Tuning()
+
+
+def packed_pitch(n_atoms):
+    """Row length of packed image rows in 32-bit words: one word per 4 atoms, rounded up to 128 bytes."""
+    return _round_up((n_atoms + 3) // 4, 32)
+
+
 class DeviceStore:
     """Frame rows resident in HBM plus the map trajectory frame -> row."""
 
-    def __init__(self, coords, n_atoms, images=None, box=None, frame_to_row=None, n_frames=None, box_const=None):
+    def __init__(self, coords, n_atoms, images=None, box=None, frame_to_row=None, n_frames=None, box_const=None,
+                 packed=None, images16=None):
         self.coords = coords            # torch (n_rows, pitch) float32 / float64
         self.n_atoms = int(n_atoms)
         self.images = images            # torch uint8 (n_rows, img_pitch), excess-128, or None
+        self.packed = packed            # torch int32 (n_rows, packed_pitch) 2-bit counts, or None
+        self.images16 = images16        # torch int16 (n_rows, pitch) counts beyond +-127, or None
         self.box = box                  # torch float64 (n_rows, 3) or None
         self.box_const = box_const      # 3 floats when every row has the same box
         self.frame_to_row = frame_to_row  # np.int32 (T,) with -1 = absent, or None = identity
         self.n_frames = n_frames if n_frames is not None else coords.shape[0]
+        self.source = None              # what the image counts were derived from (Resident: jump matrices / scan)
         self._cache = {}
 
     @property
     def device(self):
         return self.coords.device
 
+    @property
+    def has_images(self):
+        return self.images is not None or self.packed is not None or self.images16 is not None
+
     def without_images(self):
         """The same rows read as raw (wrapped) coordinates: a view that shares all buffers."""
-        if self.images is None:
+        if not self.has_images:
             return self
         view = self._cache.get('raw_view')
         if view is None:
             view = DeviceStore(self.coords, self.n_atoms, frame_to_row=self.frame_to_row, n_frames=self.n_frames)
             self._cache['raw_view'] = view
         return view
+
+    def atom_block(self, a0, a1):
+        """The columns of atoms [a0, a1) as a store that shares all buffers (a0 a multiple of 16 keeps every row
+        16-byte aligned in all formats)."""
+        if a0 % 16:
+            raise ValueError('atom blocks must start at a multiple of 16 atoms')
+        return DeviceStore(self.coords[:, 3 * a0:], a1 - a0,
+                           images=None if self.images is None else self.images[:, 3 * a0:],
+                           packed=None if self.packed is None else self.packed[:, a0 // 4:],
+                           images16=None if self.images16 is None else self.images16[:, 3 * a0:],
+                           box=self.box, frame_to_row=self.frame_to_row, n_frames=self.n_frames,
+                           box_const=self.box_const)
+
+    def image_counts(self, rows=None):
+        """Host int64 ``(n_rows, n_atoms, 3)`` image counts of the given storage rows (all rows by default), from
+        whichever format the store holds -- for tests and diagnostics."""
+        n3 = 3 * self.n_atoms
+        sel = slice(None) if rows is None else np.asarray(rows, dtype=np.int64)
+        if self.images is not None:
+            arr = self.images[:, :n3].cpu().numpy()[sel].astype(np.int64) - IMAGE_BIAS
+        elif self.images16 is not None:
+            arr = self.images16[:, :n3].cpu().numpy()[sel].astype(np.int64)
+        elif self.packed is not None:
+            words = self.packed[:, :(self.n_atoms + 3) // 4].cpu().numpy()[sel].view(np.uint32)
+            c = np.arange(12)
+            shifts = (8 * (c // 3) + 2 * (c % 3)).astype(np.uint32)
+            arr = ((words[:, :, None] >> shifts[None, None, :]) & 3).astype(np.int64) - 1
+            arr = arr.reshape(arr.shape[0], -1)[:, :n3]
+        else:
+            raise ValueError('the store holds no image counts')
+        return arr.reshape(arr.shape[0], self.n_atoms, 3)
 
     def rows_for(self, frame_ids):
         frame_ids = np.asarray(frame_ids)
@@ -99,52 +168,40 @@ def _count(n):
     _launch_counter += n
 
 
+time_slot = -1            # >= 0: plans bracket their correlation kernel with the CUDA event pair of that slot
+last_plan = None          # weak reference to the plan that ran last (its kernel timings: CorrPlan.kernel_ms)
+
+
 def profile_kernels(enable):
-    """Bracket the correlation kernel of every following launch with CUDA events (bench.py)."""
-    _lib.check(_lib.load().mdb_corr_profile(1 if enable else 0), 'mdb_corr_profile')
+    """Bracket the correlation kernel of every following plan run with CUDA events (slot 0)."""
+    global time_slot
+    time_slot = 0 if enable else -1
 
 
 def last_kernel_ms():
-    ms = C.c_float(0.0)
-    _lib.check(_lib.load().mdb_corr_last_kernel_ms(C.byref(ms)), 'mdb_corr_last_kernel_ms')
-    return float(ms.value)
+    """Duration of the correlation kernel of the last plan run (after ``profile_kernels(True)``)."""
+    plan = last_plan() if last_plan is not None else None
+    if plan is None or time_slot < 0:
+        raise _lib.CudaPathError('no profiled launch (call profile_kernels(True) first)')
+    return plan.kernel_ms(time_slot)
 
 
-def correlate_device(store, rows, spec, stream=None, select=None):
-    """Launch the correlation kernels; returns device tensors ``(sums (S,L,3) f64, hist (S,L,B) i64|None)``.
-
-    ``rows`` is an int32 ``(S, L)`` array of storage rows (host NumPy, cached on the device per store).
-    """
+def _fill_corr_args(a, store, rows_dev, S, L, spec, select, edges_dev):
+    """The part of mdb_corr_args that describes the rows and the request (outputs are set by the caller)."""
     torch = _lib.require_cuda()
-    lib = _lib.load()
-    rows = np.ascontiguousarray(rows, dtype=np.int32)
-    S, L = rows.shape
-    dev = store.device
-    key = ('rows', rows.shape, rows.tobytes())       # the bytes themselves: no hash-collision risk
-    rows_dev = store._cache.get(key)
-    if rows_dev is None:
-        rows_dev = torch.from_numpy(rows).to(dev)
-        if len(store._cache) > 64:
-            store._cache.clear()
-        store._cache[key] = rows_dev
-    want_hist = bool(spec.flags & _lib.HIST)
-    sums = torch.empty((S, L, 3), dtype=torch.float64, device=dev)
-    hist = torch.empty((S, L, spec.n_bins), dtype=torch.int64, device=dev) if want_hist else None
-    edges_dev = None
-    if want_hist and spec.bin_mode == _lib.BINS_EDGES:
-        ekey = ('edges', spec.edges.tobytes())
-        edges_dev = store._cache.get(ekey)
-        if edges_dev is None:
-            edges_dev = torch.from_numpy(spec.edges).to(dev)
-            store._cache[ekey] = edges_dev
-
-    a = _lib.CorrArgs()
     a.coords = store.coords.data_ptr()
     a.pitch = store.coords.stride(0)
     a.coord_type = _lib.F32 if store.coords.dtype == torch.float32 else _lib.F64
-    if store.images is not None:
-        a.images = store.images.data_ptr()
-        a.img_pitch = store.images.stride(0)
+    if store.has_images:
+        if store.images is not None:
+            a.images = store.images.data_ptr()
+            a.img_pitch = store.images.stride(0)
+        if store.packed is not None and tuning.use_packed:
+            a.packed = store.packed.data_ptr()
+            a.packed_pitch = store.packed.stride(0)
+        if store.images16 is not None:
+            a.images16 = store.images16.data_ptr()
+            a.img16_pitch = store.images16.stride(0)
         if store.box_const is not None:
             a.box = None
             a.box_const[0], a.box_const[1], a.box_const[2] = store.box_const
@@ -166,19 +223,61 @@ def correlate_device(store, rows, spec, stream=None, select=None):
     a.bin_mode = spec.bin_mode
     a.dx = spec.dx
     a.edges = edges_dev.data_ptr() if edges_dev is not None else None
+    tuning.fill(a.tuning)
+
+
+def _rows_on_device(store, rows):
+    torch = _lib.require_cuda()
+    key = ('rows', rows.shape, rows.tobytes())       # the bytes themselves: no hash-collision risk
+    rows_dev = store._cache.get(key)
+    if rows_dev is None:
+        rows_dev = torch.from_numpy(rows).to(store.device)
+        if len(store._cache) > 64:
+            for k in [k for k in store._cache if isinstance(k, tuple) and k and k[0] in ('rows', 'plan')]:
+                plan = store._cache.pop(k)
+                if isinstance(plan, CorrPlan):
+                    plan.close()
+        store._cache[key] = rows_dev
+    return rows_dev, key
+
+
+def _edges_on_device(store, spec):
+    torch = _lib.require_cuda()
+    if not (spec.flags & _lib.HIST) or spec.bin_mode != _lib.BINS_EDGES:
+        return None
+    ekey = ('edges', spec.edges.tobytes())
+    edges_dev = store._cache.get(ekey)
+    if edges_dev is None:
+        edges_dev = store._cache[ekey] = torch.from_numpy(spec.edges).to(store.device)
+    return edges_dev
+
+
+def correlate_device(store, rows, spec, stream=None, select=None):
+    """Launch the correlation kernels; returns device tensors ``(sums (S,L,3) f64, hist (S,L,B) i64|None)``.
+
+    ``rows`` is an int32 ``(S, L)`` array of storage rows (host NumPy, cached on the device per store).  One-shot
+    form (fresh output tensors per call); repeated calls of the same request go through :class:`CorrPlan`.
+    """
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    S, L = rows.shape
+    dev = store.device
+    rows_dev, _ = _rows_on_device(store, rows)
+    want_hist = bool(spec.flags & _lib.HIST)
+    sums = torch.empty((S, L, 3), dtype=torch.float64, device=dev)
+    hist = torch.empty((S, L, spec.n_bins), dtype=torch.int64, device=dev) if want_hist else None
+    a = _lib.CorrArgs()
+    _fill_corr_args(a, store, rows_dev, S, L, spec, select, _edges_on_device(store, spec))
     a.sums = sums.data_ptr()
     a.hist = hist.data_ptr() if hist is not None else None
-    skey = ('ws_bytes', S, L, spec.flags, spec.n_bins, a.coord_type, store.images is not None)
-    need = store._cache.get(skey)
-    if need is None:
-        nbytes = C.c_size_t(0)
-        _lib.check(lib.mdb_corr_workspace_bytes(C.byref(a), C.byref(nbytes)), 'mdb_corr_workspace_bytes')
-        need = store._cache[skey] = nbytes.value
-    wkey = 'workspace'
-    ws = store._cache.get(wkey)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.mdb_corr_workspace_bytes(C.byref(a), C.byref(nbytes)), 'mdb_corr_workspace_bytes')
+    need = nbytes.value
+    ws = store._cache.get('workspace')
     if ws is None or ws.numel() < need:
         ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
-        store._cache[wkey] = ws
+        store._cache['workspace'] = ws
     a.workspace = ws.data_ptr()
     a.workspace_bytes = ws.numel()
     st = stream if stream is not None else torch.cuda.current_stream(dev)
@@ -186,6 +285,102 @@ def correlate_device(store, rows, spec, stream=None, select=None):
         _lib.check(lib.mdb_shifted_corr(C.byref(a), C.c_void_p(st.cuda_stream)), 'mdb_shifted_corr')
     _count(lib.mdb_corr_last_launches())
     return sums, hist
+
+
+class CorrPlan:
+    """One repeated correlation request on one store (``mdb_corr_plan``): the C side owns workspace, device sums /
+    histogram and a page-locked host block; :meth:`run` is two kernel launches and returns NumPy views of that host
+    block (valid until the next run).  With ``comm`` (a :class:`Comm`) the sums come back added over the GPUs."""
+
+    def __init__(self, store, rows, spec, select=None, comm=None):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self.shape = rows.shape
+        S, L = rows.shape
+        # no reference to the store itself: cached plans live IN store._cache, and a cycle would keep gigabytes of
+        # HBM waiting for the garbage collector; the tensors the C side points into are kept alive explicitly
+        self.comm = comm
+        self._keep = (_rows_on_device(store, rows)[0], _edges_on_device(store, spec), select, store.coords,
+                      store.images, store.packed, store.images16, store.box)
+        a = _lib.CorrArgs()
+        _fill_corr_args(a, store, self._keep[0], S, L, spec, select, self._keep[1])
+        handle = C.c_void_p()
+        with torch.cuda.device(store.device):
+            _lib.check(lib.mdb_corr_plan_create(C.byref(a), comm.handle if comm is not None else None,
+                                                C.byref(handle)), 'mdb_corr_plan_create')
+        self.handle = handle
+        self._lib = lib
+        self._stream_of = torch.cuda.current_stream
+        self._device = store.device
+        n = S * L * 3
+        ptr = lib.mdb_corr_plan_sums(handle)
+        self.sums = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)).reshape(S, L, 3)
+        self.hist = None
+        if spec.flags & _lib.HIST:
+            hp = lib.mdb_corr_plan_hist(handle)
+            self.hist = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_int64)),
+                                              shape=(S * L * spec.n_bins,)).reshape(S, L, spec.n_bins)
+        self.launches = lib.mdb_corr_plan_launches(handle) + (2 if spec.flags & _lib.HIST else 0)
+        self._weak = weakref.ref(self)
+
+    def run(self, slot=None):
+        """Launch on the current stream, wait, and return ``(sums, hist)`` -- views of the plan's host block."""
+        global last_plan
+        st = self._stream_of(self._device)
+        rc = self._lib.mdb_corr_plan_run(self.handle, C.c_void_p(st.cuda_stream), time_slot if slot is None else slot)
+        if rc:
+            _lib.check(rc, 'mdb_corr_plan_run')
+        _count(self.launches)
+        last_plan = self._weak
+        return self.sums, self.hist
+
+    def kernel_ms(self, time_slot):
+        ms = C.c_float(0.0)
+        _lib.check(self._lib.mdb_corr_plan_kernel_ms(self.handle, time_slot, C.byref(ms)), 'mdb_corr_plan_kernel_ms')
+        return float(ms.value)
+
+    def close(self):
+        if self.handle is not None:
+            self._lib.mdb_corr_plan_destroy(self.handle)
+            self.handle = None
+            self.sums = self.hist = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    """Peer-memory communicator (``mdb_comm``): every rank's inbox is mapped into every other rank with CUDA IPC;
+    the finish kernel of a plan adds the partial sums of all GPUs over NVLink.  ``exchange(handle_bytes) ->
+    [bytes of rank 0, ...]`` carries the 64-byte IPC handles once (``torch.distributed.all_gather_object``)."""
+
+    def __init__(self, rank, world, exchange, capacity_words=1 << 20, timeout_ms=20000):
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.rank, self.world = int(rank), int(world)
+        self.capacity_words = int(capacity_words)
+        handle = C.c_void_p()
+        _lib.check(lib.mdb_comm_create(self.rank, self.world, self.capacity_words, int(timeout_ms), C.byref(handle)),
+                   'mdb_comm_create')
+        self.handle = handle
+        self._lib = lib
+        if self.world > 1:
+            mine = C.create_string_buffer(_lib.COMM_HANDLE_BYTES)
+            _lib.check(lib.mdb_comm_handle(handle, mine), 'mdb_comm_handle')
+            everyone = exchange(bytes(mine.raw))
+            if len(everyone) != self.world or any(len(h) != _lib.COMM_HANDLE_BYTES for h in everyone):
+                raise ValueError('exchange() must return the %d-byte handle of every rank' % _lib.COMM_HANDLE_BYTES)
+            blob = C.create_string_buffer(b''.join(everyone), self.world * _lib.COMM_HANDLE_BYTES)
+            _lib.check(lib.mdb_comm_connect(handle, blob), 'mdb_comm_connect')
+
+    def close(self):
+        if self.handle is not None:
+            self._lib.mdb_comm_destroy(self.handle)
+            self.handle = None
 
 
 DENSE_MAX_ORIGIN_STEP = 4        # beyond that neighbouring origins share too few rows to pay off
@@ -222,6 +417,7 @@ def dense_device(store, first_origin, origin_step, n_origins, first_lag, n_lags,
     a.flags = int(flags)
     a.q = float(q)
     a.sums = sums.data_ptr()
+    tuning.fill(a.tuning)
     nbytes = C.c_size_t(0)
     _lib.check(lib.mdb_dense_workspace_bytes(C.byref(a), C.byref(nbytes)), 'mdb_dense_workspace_bytes')
     ws = store._cache.get('workspace')
@@ -237,7 +433,7 @@ def dense_device(store, first_origin, origin_step, n_origins, first_lag, n_lags,
 
 
 def nojump_scan(coords_seg, n_atoms, box0, box_is_f32, prev, cum, first_segment, images=None, jumps=None,
-                out_row=None, coords_out=None, overflow=None, whole0=None, stream=None):
+                out_row=None, coords_out=None, overflow=None, whole0=None, stream=None, images16=None):
     """One segment of the jump scan (mdb_nojump_scan).  All tensors are device tensors."""
     torch = _lib.require_cuda()
     lib = _lib.load()
@@ -262,6 +458,10 @@ def nojump_scan(coords_seg, n_atoms, box0, box_is_f32, prev, cum, first_segment,
     a.coords_out = coords_out.data_ptr() if coords_out is not None else None
     a.pitch_out = coords_out.stride(0) if coords_out is not None else 0
     a.overflow = overflow.data_ptr() if overflow is not None else None
+    if images16 is not None:
+        a.images16 = images16.data_ptr()
+        a.img16_pitch = images16.stride(0)
+    tuning.fill(a.tuning)
     dev = coords_seg.device
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
@@ -269,7 +469,7 @@ def nojump_scan(coords_seg, n_atoms, box0, box_is_f32, prev, cum, first_segment,
     _count(1)
 
 
-def images_from_jumps(indptr, frames, jumps, n_atoms, images, keep=None, overflow=None, stream=None):
+def images_from_jumps(indptr, frames, jumps, n_atoms, images, keep=None, overflow=None, stream=None, images16=None):
     """Image counts of the kept frames from jump matrices re-sorted by component column
     (mdb_nojump_images_from_jumps).  All tensors are device tensors; ``keep`` int32 ascending or None."""
     torch = _lib.require_cuda()
@@ -285,11 +485,16 @@ def images_from_jumps(indptr, frames, jumps, n_atoms, images, keep=None, overflo
     a.jumps = jumps.data_ptr() if a.nnz else None
     a.n_atoms = n_atoms
     a.keep = keep.data_ptr() if keep is not None else None
-    a.n_keep = keep.numel() if keep is not None else images.shape[0]
-    a.images = images.data_ptr()
-    a.img_pitch = images.stride(0)
+    out = images if images is not None else images16
+    a.n_keep = keep.numel() if keep is not None else out.shape[0]
+    if images is not None:
+        a.images = images.data_ptr()
+        a.img_pitch = images.stride(0)
+    else:
+        a.images16 = images16.data_ptr()
+        a.img16_pitch = images16.stride(0)
     a.overflow = overflow.data_ptr() if overflow is not None else None
-    dev = images.device
+    dev = out.device
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
         _lib.check(lib.mdb_nojump_images_from_jumps(C.byref(a), C.c_void_p(st.cuda_stream)),
@@ -308,8 +513,9 @@ def copy_rows_h2d(src_ptr, src_pitch_bytes, dst, width_bytes, n_rows, stream):
                                          C.c_void_p(stream.cuda_stream)), 'mdb_copy_rows_h2d')
 
 
-def nojump_apply(coords_row, images_row, box_diag, n_atoms):
-    """float64 unwrapped frame ``x - n*box`` of one stored row (device tensor (3N,))."""
+def nojump_apply(coords_row, images_row, box_diag, n_atoms, image_format=_lib.IMAGE_BYTES):
+    """float64 unwrapped frame ``x - n*box`` of one stored row (device tensor (3N,)); ``images_row`` in any of the
+    three image formats."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = coords_row.device
@@ -317,8 +523,25 @@ def nojump_apply(coords_row, images_row, box_diag, n_atoms):
     box = (C.c_double * 3)(*[float(b) for b in box_diag])
     st = torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.mdb_nojump_apply(C.c_void_p(coords_row.data_ptr()), C.c_void_p(images_row.data_ptr()),
-                                        box, n_atoms, C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream)),
-                   'mdb_nojump_apply')
+        _lib.check(lib.mdb_nojump_apply_format(C.c_void_p(coords_row.data_ptr()), C.c_void_p(images_row.data_ptr()),
+                                               int(image_format), box, n_atoms, C.c_void_p(out.data_ptr()),
+                                               C.c_void_p(st.cuda_stream)), 'mdb_nojump_apply_format')
     _count(1)
     return out
+
+
+def pack_images(images, n_atoms):
+    """Byte image rows -> packed rows (``mdb_images_pack``).  Returns ``(packed int32 (n_rows, packed_pitch),
+    max |count|)``; the packed rows are valid only if the maximum is <= 1."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = images.device
+    packed = torch.zeros((images.shape[0], packed_pitch(n_atoms)), dtype=torch.int32, device=dev)
+    worst = torch.zeros((1,), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mdb_images_pack(C.c_void_p(images.data_ptr()), images.stride(0), images.shape[0], n_atoms,
+                                       C.c_void_p(packed.data_ptr()), packed.stride(0), C.c_void_p(worst.data_ptr()),
+                                       C.c_void_p(st.cuda_stream)), 'mdb_images_pack')
+    _count(1)
+    return packed, int(worst.item())

@@ -16,7 +16,11 @@ LIB_PATH = os.path.join(HERE, 'libmdevaluate_b200.so')
 F32, F64 = 0, 1
 SUM_R2, SUM_R4, SUM_SINC, HIST, SUM_LEGENDRE = 1, 2, 4, 8, 16
 BINS_UNIFORM, BINS_EDGES = 0, 1
-ABI_VERSION = 1
+IMAGE_BYTES, IMAGE_PACKED, IMAGE_I16 = 1, 2, 3
+ERR_TIMEOUT = 5
+COMM_HANDLE_BYTES = 64
+PLAN_TIME_SLOTS = 1024
+ABI_VERSION = 2
 
 EXPORTS = (
     'mdb_last_error', 'mdb_abi_version', 'mdb_device_info',
@@ -24,11 +28,23 @@ EXPORTS = (
     'mdb_corr_profile', 'mdb_corr_last_kernel_ms',
     'mdb_nojump_scan', 'mdb_nojump_apply', 'mdb_nojump_images_from_jumps',
     'mdb_dense_workspace_bytes', 'mdb_dense_corr', 'mdb_copy_rows_h2d',
+    'mdb_corr_plan_create', 'mdb_corr_plan_run', 'mdb_corr_plan_launch', 'mdb_corr_plan_wait',
+    'mdb_corr_plan_kernel_ms', 'mdb_corr_plan_sums', 'mdb_corr_plan_hist', 'mdb_corr_plan_sums_device',
+    'mdb_corr_plan_launches', 'mdb_corr_plan_destroy',
+    'mdb_comm_create', 'mdb_comm_handle', 'mdb_comm_connect', 'mdb_comm_destroy',
+    'mdb_images_pack', 'mdb_nojump_apply_format',
 )
 
 
 class CudaPathError(RuntimeError):
     """The CUDA path is unavailable or a C-ABI call failed."""
+
+
+class Tuning(C.Structure):
+    """mdb_tuning: explicit kernel switches, 0 = the measured default."""
+    _fields_ = [('ring_stages', C.c_int32), ('atom_blocks', C.c_int32), ('isf_float64', C.c_int32),
+                ('hist_float64', C.c_int32), ('scan_direct', C.c_int32), ('dense_stage_cta', C.c_int32),
+                ('reserved', C.c_int32 * 2)]
 
 
 class CorrArgs(C.Structure):
@@ -41,6 +57,8 @@ class CorrArgs(C.Structure):
         ('n_bins', C.c_int32), ('bin_mode', C.c_int32), ('dx', C.c_double), ('edges', C.c_void_p),
         ('sums', C.c_void_p), ('hist', C.c_void_p),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+        ('packed', C.c_void_p), ('packed_pitch', C.c_int64), ('images16', C.c_void_p), ('img16_pitch', C.c_int64),
+        ('tuning', Tuning),
     ]
 
 
@@ -51,6 +69,7 @@ class NojumpArgs(C.Structure):
         ('whole0', C.c_void_p), ('prev', C.c_void_p), ('cum', C.c_void_p), ('out_row', C.c_void_p),
         ('images', C.c_void_p), ('img_pitch', C.c_int64), ('jumps', C.c_void_p),
         ('coords_out', C.c_void_p), ('pitch_out', C.c_int64), ('overflow', C.c_void_p),
+        ('images16', C.c_void_p), ('img16_pitch', C.c_int64), ('tuning', Tuning),
     ]
 
 
@@ -59,6 +78,7 @@ class JumpMatArgs(C.Structure):
         ('indptr', C.c_void_p), ('frames', C.c_void_p), ('jumps', C.c_void_p), ('nnz', C.c_int64),
         ('n_atoms', C.c_int32), ('keep', C.c_void_p), ('n_keep', C.c_int32),
         ('images', C.c_void_p), ('img_pitch', C.c_int64), ('overflow', C.c_void_p),
+        ('images16', C.c_void_p), ('img16_pitch', C.c_int64),
     ]
 
 
@@ -69,6 +89,7 @@ class DenseArgs(C.Structure):
         ('n_atoms', C.c_int32), ('first_origin', C.c_int32), ('origin_step', C.c_int32), ('n_origins', C.c_int32),
         ('first_lag', C.c_int32), ('n_lags', C.c_int32), ('flags', C.c_int32), ('q', C.c_double),
         ('sums', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+        ('packed', C.c_void_p), ('packed_pitch', C.c_int64), ('tuning', Tuning),
     ]
 
 
@@ -93,8 +114,28 @@ def _declare(lib):
     lib.mdb_dense_corr.argtypes = [C.POINTER(DenseArgs), C.c_void_p]
     lib.mdb_nojump_apply.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_void_p,
                                      C.c_void_p]
+    lib.mdb_corr_plan_create.argtypes = [C.POINTER(CorrArgs), C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mdb_corr_plan_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.mdb_corr_plan_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.mdb_corr_plan_wait.argtypes = [C.c_void_p]
+    lib.mdb_corr_plan_kernel_ms.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]
+    for name in ('mdb_corr_plan_sums', 'mdb_corr_plan_hist', 'mdb_corr_plan_sums_device'):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.mdb_corr_plan_launches.argtypes = [C.c_void_p]
+    lib.mdb_corr_plan_destroy.argtypes = [C.c_void_p]
+    lib.mdb_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.mdb_comm_handle.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mdb_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mdb_comm_destroy.argtypes = [C.c_void_p]
+    lib.mdb_images_pack.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p]
+    lib.mdb_nojump_apply_format.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32,
+                                            C.c_void_p, C.c_void_p]
+    pointers = ('mdb_last_error', 'mdb_corr_plan_sums', 'mdb_corr_plan_hist', 'mdb_corr_plan_sums_device')
+    for name in pointers[1:]:
+        getattr(lib, name).restype = C.c_void_p
     for name in EXPORTS:
-        if name != 'mdb_last_error':
+        if name not in pointers:
             getattr(lib, name).restype = C.c_int        # every other entry point returns an int status / count
 
 

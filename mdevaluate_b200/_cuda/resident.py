@@ -75,6 +75,7 @@ class Resident:
         self._dense_images = False
         self._compact = {}              # (mode, hash of frame ids) -> DeviceStore
         self.force_compact = False
+        self.pack_images = True         # re-code byte image rows as packed rows when no count leaves [-1, 1]
 
     @property
     def reader(self):
@@ -273,8 +274,9 @@ class Resident:
         self._dense = engine.DeviceStore(coords, self.n_atoms, n_frames=self.n_frames)
         return self._dense
 
-    def _scan_all(self, images=None, jumps=None, out_row=None, coords_out=None):
-        """Run the jump scan over the whole trajectory (segment by segment, carrying state)."""
+    def _scan_all(self, images=None, jumps=None, out_row=None, coords_out=None, images16=None):
+        """Run the jump scan over the whole trajectory (segment by segment, carrying state).  Returns True when a
+        running count left the range of the requested image rows (one byte: +-127, int16: +-32767)."""
         torch = _lib.require_cuda()
         n3 = 3 * self.n_atoms
         prev = torch.zeros((n3,), dtype=torch.float32, device=self.device)
@@ -298,15 +300,29 @@ class Resident:
             rows = None
             if out_row is not None:
                 rows = out_row[t0:t1]
-                img_seg, jmp_seg = images, jumps
+                img_seg, jmp_seg, i16_seg = images, jumps, images16
             else:
                 img_seg = images[t0:t1] if images is not None else None
                 jmp_seg = jumps[t0:t1] if jumps is not None else None
+                i16_seg = images16[t0:t1] if images16 is not None else None
             engine.nojump_scan(seg, self.n_atoms, box0, box_is_f32, prev, cum, first_segment=(t0 == 0),
                                images=img_seg, jumps=jmp_seg, out_row=rows, coords_out=coords_out,
-                               overflow=overflow, whole0=whole0)
-        if int(overflow.item()):
-            raise _lib.CudaPathError('an atom crossed more than 127 periodic images; the one-byte image counts overflow')
+                               overflow=overflow, whole0=whole0, images16=i16_seg)
+        return bool(int(overflow.item()))
+
+    @staticmethod
+    def _too_far():
+        return _lib.CudaPathError('an atom crossed more than 32767 periodic images; the image counts overflow')
+
+    def _compress_images(self, store):
+        """Byte image rows -> the packed rows the correlation kernels prefer (when no count leaves [-1, 1])."""
+        if store.images is None or not self.pack_images:
+            return
+        packed, worst = engine.pack_images(store.images, self.n_atoms)
+        if worst <= 1:
+            store.packed = packed
+        else:
+            logger.debug('image counts reach %d: keeping one byte per component', worst)
 
     # -- stored jump matrices (the reference's nojump cache) ----------------------------------------
     def _matrices(self):
@@ -329,8 +345,9 @@ class Resident:
                                  % (m.shape, self.n_frames, self.n_atoms_all))
         return mats
 
-    def _images_from_matrices(self, mats, images, keep=None):
-        """Fill ``images`` (rows = ``keep`` ascending, or every frame) from the jump matrices."""
+    def _images_from_matrices(self, mats, n_rows, keep=None):
+        """Image rows (rows = ``keep`` ascending, or every frame) from the jump matrices: ``(images uint8 | None,
+        images16 | None)`` -- int16 rows only when a count leaves one byte."""
         torch = _lib.require_cuda()
         from ..reader import jump_columns
         lists = self._jump_lists
@@ -342,25 +359,47 @@ class Resident:
         keep_dev = None
         if keep is not None:
             keep_dev = torch.from_numpy(np.ascontiguousarray(keep, dtype=np.int32)).to(self.device)
+        images = torch.empty((n_rows, self.pitch), dtype=torch.uint8, device=self.device)
         engine.images_from_jumps(lists[1], lists[2], lists[3], self.n_atoms, images, keep=keep_dev, overflow=overflow)
+        if not int(overflow.item()):
+            return images, None
+        del images
+        images16 = torch.empty((n_rows, self.pitch), dtype=torch.int16, device=self.device)
+        engine.images_from_jumps(lists[1], lists[2], lists[3], self.n_atoms, None, keep=keep_dev, overflow=overflow,
+                                 images16=images16)
         if int(overflow.item()):
-            raise _lib.CudaPathError('an atom crossed more than 127 periodic images; the one-byte image counts overflow')
+            raise self._too_far()
+        return None, images16
 
     def _ensure_dense_images(self):
         torch = _lib.require_cuda()
         store = self._ensure_dense()
-        if store.images is None:
+        mats = self._matrices()
+        if store.has_images and store.source is not mats:
+            # the reader's jump matrices were replaced (generate / load / correct_nojump_matrixes_for_whole):
+            # they are authoritative (pbc.py:233-237), the stored counts are stale
+            store.images = store.packed = store.images16 = None
+            store._cache.clear()
+        if not store.has_images:
             if store.coords.dtype != torch.float32:
                 raise _lib.CudaPathError('nojump needs float32 wrapped positions')
-            images = torch.empty((self.n_frames, self.pitch), dtype=torch.uint8, device=self.device)
-            mats = self._matrices()
             if mats is not None:
-                self._images_from_matrices(mats, images)
+                store.images, store.images16 = self._images_from_matrices(mats, self.n_frames)
             else:
-                self._scan_all(images=images)
-            store.images = images
+                images = torch.empty((self.n_frames, self.pitch), dtype=torch.uint8, device=self.device)
+                if self._scan_all(images=images):
+                    # beyond +-127 images: int16 rows from the general scan kernel (the reference has no limit,
+                    # pbc.py:235-237 sums int8 jumps into int64)
+                    del images
+                    store.images16 = torch.empty((self.n_frames, self.pitch), dtype=torch.int16, device=self.device)
+                    if self._scan_all(images16=store.images16):
+                        raise self._too_far()
+                else:
+                    store.images = images
+            store.source = mats
             store.box = self._box_rows(range(self.n_frames))
             store.box_const = self._box_const()
+            self._compress_images(store)
         return store
 
     def dense_jumps(self):
@@ -368,7 +407,7 @@ class Resident:
         torch = _lib.require_cuda()
         n3 = 3 * self.n_atoms
         jumps = torch.empty((self.n_frames, self.pitch), dtype=torch.int8, device=self.device)
-        self._scan_all(jumps=jumps)
+        self._scan_all(jumps=jumps)            # per-step jumps only: the running counts are not stored
         return jumps[:, :n3].cpu().numpy().reshape(self.n_frames, self.n_atoms, 3)
 
     # -- compact residency -------------------------------------------------------------------------
@@ -385,9 +424,18 @@ class Resident:
             coords = torch.empty((n_rows, self.pitch), dtype=torch.float32, device=self.device)
             images = torch.empty((n_rows, self.pitch), dtype=torch.uint8, device=self.device)
             out_row = torch.from_numpy(f2r).to(self.device)
-            self._scan_all(images=images, out_row=out_row, coords_out=coords)
-            return engine.DeviceStore(coords, self.n_atoms, images=images, box=self._box_rows(frame_ids),
-                                      frame_to_row=f2r, n_frames=self.n_frames, box_const=self._box_const())
+            images16 = None
+            if self._scan_all(images=images, out_row=out_row, coords_out=coords):
+                images = None
+                images16 = torch.empty((n_rows, self.pitch), dtype=torch.int16, device=self.device)
+                if self._scan_all(images16=images16, out_row=out_row):
+                    raise self._too_far()
+            store = engine.DeviceStore(coords, self.n_atoms, images=images, images16=images16,
+                                       box=self._box_rows(frame_ids), frame_to_row=f2r, n_frames=self.n_frames,
+                                       box_const=self._box_const())
+            store.source = None
+            self._compress_images(store)
+            return store
         tdt = torch.float32 if self.dtype == np.float32 else torch.float64
         if nojump and tdt != torch.float32:
             raise _lib.CudaPathError('nojump needs float32 wrapped positions (got %s)' % self.dtype)
@@ -411,10 +459,12 @@ class Resident:
                 torch.cuda.current_stream(self.device).synchronize()
         if not nojump:
             return engine.DeviceStore(coords, self.n_atoms, frame_to_row=f2r, n_frames=self.n_frames)
-        images = torch.empty((n_rows, self.pitch), dtype=torch.uint8, device=self.device)
-        self._images_from_matrices(mats, images, keep=frame_ids)
-        store = engine.DeviceStore(coords, self.n_atoms, images=images, box=self._box_rows(frame_ids),
-                                   frame_to_row=f2r, n_frames=self.n_frames, box_const=self._box_const())
+        images, images16 = self._images_from_matrices(mats, n_rows, keep=frame_ids)
+        store = engine.DeviceStore(coords, self.n_atoms, images=images, images16=images16,
+                                   box=self._box_rows(frame_ids), frame_to_row=f2r, n_frames=self.n_frames,
+                                   box_const=self._box_const())
+        store.source = mats
+        self._compress_images(store)
         return store
 
     # -- public ---------------------------------------------------------------------------------
@@ -435,7 +485,7 @@ class Resident:
     def store_for(self, frame_ids, nojump):
         """A DeviceStore holding (at least) ``frame_ids``; with image counts if ``nojump``."""
         if (self._dense is not None and not self.force_compact
-                and (not nojump or self._dense.images is not None)):
+                and (not nojump or (self._dense.has_images and self._dense.source is self._matrices()))):
             return self._dense                      # hot path: everything is resident already
         torch = _lib.require_cuda()
         frame_ids = np.unique(np.asarray(frame_ids, dtype=np.int64))
@@ -448,7 +498,7 @@ class Resident:
                      and getattr(self.reader, 'host_block', None) is None and self._matrices() is not None)
         if not self.force_compact and not sparse_io:
             on_device = self._dense is not None or (block is not None and self.atom_filter is None)
-            have_images = self._dense is not None and self._dense.images is not None
+            have_images = self._dense is not None and self._dense.has_images
             extra = 0 if on_device else self._dense_bytes(False)
             if nojump and not have_images:
                 extra += self.pitch * self.n_frames
@@ -456,6 +506,12 @@ class Resident:
                 return self._ensure_dense_images() if nojump else self._ensure_dense()
         mode = 'nojump' if nojump else 'raw'
         key = (mode, frame_ids.tobytes())
+        if nojump:
+            # stored jump matrices are authoritative: stores whose counts came from other matrices (or from the
+            # scan, before matrices were loaded) are stale
+            mats = self._matrices()
+            for k in [k for k, st in self._compact.items() if k[0] == 'nojump' and st.source is not mats]:
+                del self._compact[k]
         store = self._compact.get(key)
         if store is None:
             for (have_mode, _), have in self._compact.items():       # e.g. single frames of a schedule's store
@@ -473,7 +529,13 @@ class Resident:
         store = self.store_for([i], nojump=True)
         row = int(store.rows_for([i])[0])
         n3 = 3 * self.n_atoms
-        out = engine.nojump_apply(store.coords[row], store.images[row], store.box[row].cpu().numpy(), self.n_atoms)
+        if store.images is not None:
+            img, fmt = store.images[row], _lib.IMAGE_BYTES
+        elif store.images16 is not None:
+            img, fmt = store.images16[row], _lib.IMAGE_I16
+        else:
+            img, fmt = store.packed[row], _lib.IMAGE_PACKED
+        out = engine.nojump_apply(store.coords[row], img, store.box[row].cpu().numpy(), self.n_atoms, fmt)
         return out.cpu().numpy().reshape(self.n_atoms, 3)
 
     def raw_frame(self, i):

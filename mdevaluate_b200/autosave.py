@@ -62,19 +62,37 @@ class disabled:
         return False
 
 
+trust_pickle = False
+"""Result files written by the REFERENCE hold their checksum (a 160-bit Python integer) and ragged results only as
+pickled object entries.  Unpickling runs code from the file, so such files are read only after an explicit
+``autosave.trust_pickle = True``; files written by this package carry pickle-free twins of every entry
+(``checksum_str``, ``item_<k>``) and are always read with ``allow_pickle=False``."""
+
+
 class ResultFile:
-    """One ``.npz`` result file: ``checksum`` (a 160-bit Python integer, which NumPy can only store as a
-    pickled object entry -- hence ``allow_pickle`` on the read side) and ``data``."""
+    """One ``.npz`` result file.  Layout of the reference (autosave.py:85-100): ``checksum`` and ``data``; next to
+    them this package writes ``checksum_str`` (the checksum in decimal) and, for a ragged result, ``n_items`` and
+    ``item_<k>`` -- the entries it reads back, none of which needs pickle."""
 
     def __init__(self, path):
         self.path = path
 
     def stored_checksum(self):
-        """The checksum inside the file; 0 when the file is absent or carries none."""
+        """The checksum inside the file; 0 when the file is absent, carries none, or carries only a pickled one
+        and ``trust_pickle`` is off."""
         if not os.path.exists(self.path):
             return 0
+        with np.load(self.path, allow_pickle=False) as archive:
+            if 'checksum_str' in archive:
+                return int(str(archive['checksum_str'][()]))
+            if 'checksum' not in archive:
+                return 0
+        if not trust_pickle:
+            logger.info('ignoring %s: written without checksum_str (set autosave.trust_pickle = True to read files '
+                        'of the reference)', self.path)
+            return 0
         with np.load(self.path, allow_pickle=True) as archive:
-            return archive['checksum'][()] if 'checksum' in archive else 0
+            return archive['checksum'][()]
 
     def holds(self, *checksums):
         stored = self.stored_checksum()
@@ -83,20 +101,36 @@ class ResultFile:
     def write(self, csum, result):
         """A tuple of equally shaped arrays becomes one array; anything ragged -- ``(times (L,), result
         (S, L))``, the ``(times, result, count)`` of multi-sub-ensemble runs -- an object array, one
-        entry per item."""
+        entry per item (the reference's layout), plus the pickle-free ``item_<k>`` entries."""
         notify('Saving result to file: {}'.format(self.path))
+        extra = {'checksum_str': np.array(str(int(csum)))}
         try:
             packed = np.array(result)
+            if packed.dtype == object:
+                raise ValueError
         except ValueError:
             packed = np.empty((len(result),), dtype=object)
             for slot, item in enumerate(result):
                 packed[slot] = item
-        np.savez(self.path, checksum=csum, data=packed)
+                extra['item_{}'.format(slot)] = np.asarray(item)
+            extra['n_items'] = np.array(len(result))
+        np.savez(self.path, checksum=csum, data=packed, **extra)
 
     def read(self):
         """The stored result.  Files from before the ``data`` entry existed hold positional ``arr_*``
         entries instead; they are returned as a tuple and rewritten in today's layout."""
         notify('Loading result from file: {}'.format(self.path))
+        with np.load(self.path, allow_pickle=False) as archive:
+            if 'n_items' in archive:
+                items = np.empty((int(archive['n_items']),), dtype=object)
+                for slot in range(len(items)):
+                    items[slot] = archive['item_{}'.format(slot)]
+                return items
+            if 'checksum_str' in archive and 'data' in archive:
+                return archive['data']
+        if not trust_pickle:
+            raise ValueError('{} holds pickled entries only; set autosave.trust_pickle = True to read result files '
+                             'written by the reference'.format(self.path))
         with np.load(self.path, allow_pickle=True) as archive:
             if 'data' in archive:
                 return archive['data']

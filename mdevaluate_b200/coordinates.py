@@ -164,7 +164,13 @@ class Coordinates:
             return res
         from ._cuda.resident import Resident
         cache = self.frames.__dict__.setdefault('_mdb_resident', {}) if hasattr(self.frames, '__dict__') else {}
-        key = np.asarray(self.atom_filter).tobytes() if self.atom_filter is not None else None
+        key = None
+        if self.atom_filter is not None:
+            # the atoms themselves, not the bytes of whatever array selects them: a bool mask and an index array
+            # (or arrays of different shape) with identical bytes must not share a store
+            af = np.asarray(self.atom_filter)
+            index = np.nonzero(af)[0] if af.dtype == bool else af.astype(np.int64).ravel()
+            key = ('atoms', len(index), index.tobytes())
         res = cache.get(key)
         if res is None:
             res = Resident(self.frames, self.atom_filter)

@@ -371,6 +371,8 @@ def _dense_sums(res, nojump, spec, first_frame, last_frame, first_origin, step, 
     store = res.store_for(np.arange(first_frame, last_frame + 1), nojump=nojump)
     if not nojump:
         store = store.without_images()
+    if store.has_images and store.images is None:
+        return None                                   # int16 image counts: the streaming kernel reads them
     if store.coords.stride(0) % 4 or store.coords.data_ptr() % 16 or (
             store.images is not None and (store.images.stride(0) % 4 or store.images.data_ptr() % 4)):
         return None                                   # unaligned rows: the streaming kernel has a scalar path
@@ -460,9 +462,8 @@ def _frame_ids(start_frames, idx, n_frames):
     return frame_ids
 
 
-def _run(frames, frame_ids, specs, select=None):
-    """Kernel launch + shard reduction; returns host ``(sums, hist, n_atoms_global, float32)``.
-    ``select`` is an optional host uint8 ``(S, N)`` per-origin atom mask."""
+def _merged_spec(specs):
+    """One kernel request for all functions of a call."""
     flags = 0
     hist_spec = None
     q = 0.0
@@ -482,6 +483,38 @@ def _run(frames, frame_ids, specs, select=None):
     if hist_spec is not None:
         corr.n_bins, corr.bin_mode, corr.dx, corr.edges = (hist_spec.n_bins, hist_spec.bin_mode, hist_spec.dx,
                                                            hist_spec.edges)
+    return corr
+
+
+def _spec_key(corr):
+    return (corr.flags, corr.q, corr.order, corr.n_bins, corr.bin_mode, corr.dx,
+            None if corr.edges is None else corr.edges.tobytes())
+
+
+MAX_PLANS_PER_STORE = 16
+
+
+def _plan_for(store, rows, corr, select_dev, p2p):
+    """The cached :class:`engine.CorrPlan` of this request on this store (plans own their device / host buffers,
+    so a repeated call allocates nothing)."""
+    if select_dev is not None:
+        return engine.CorrPlan(store, rows, corr, select=select_dev, comm=p2p)       # masks differ per call
+    key = ('plan', rows.shape, rows.tobytes(), _spec_key(corr), id(p2p), engine.tuning.key())
+    plan = store._cache.get(key)
+    if plan is None:
+        plans = [k for k in store._cache if isinstance(k, tuple) and k and k[0] == 'plan']
+        if len(plans) >= MAX_PLANS_PER_STORE:
+            for k in plans:
+                store._cache.pop(k).close()
+        plan = store._cache[key] = engine.CorrPlan(store, rows, corr, comm=p2p)
+    return plan
+
+
+def _run(frames, frame_ids, specs, select=None):
+    """Kernel launch + shard reduction; returns host ``(sums, hist, n_atoms_global, float32)``.
+    ``select`` is an optional host uint8 ``(S, N)`` per-origin atom mask.  ``sums`` / ``hist`` are views of the
+    plan's page-locked result block: read them before the next call."""
+    corr = _merged_spec(specs)
     store, rows, n_atoms, float32, comm = _provider(frames, frame_ids)
     select_dev = None
     if select is not None:
@@ -489,12 +522,24 @@ def _run(frames, frame_ids, specs, select=None):
         padded = np.zeros((select.shape[0], (select.shape[1] + 3) // 4 * 4), dtype=np.uint8)
         padded[:, :select.shape[1]] = select
         select_dev = torch.from_numpy(padded).to(store.device)
-    sums, hist = engine.correlate_device(store, rows, corr, select=select_dev)
+    p2p = getattr(comm, 'p2p', None) if comm is not None else None
+    plan = _plan_for(store, rows, corr, select_dev, p2p)
+    sums, hist = plan.run()
     if comm is not None:
-        from . import parallel
-        sums, hist, n_atoms = parallel.allreduce_partials(sums, hist, n_atoms, comm)
-    sums = sums.cpu().numpy()
-    hist = hist.cpu().numpy() if hist is not None else None
+        if p2p is None:      # no peer memory (gloo / IPC refused): the torch.distributed all-reduce
+            from . import parallel
+            torch = _lib.require_cuda()
+            dev = store.device if parallel.backend_of(comm) == 'nccl' else 'cpu'
+            s_t = torch.from_numpy(np.array(sums)).to(dev)
+            h_t = torch.from_numpy(np.array(hist)).to(dev) if hist is not None else None
+            s_t, h_t, _ = parallel.allreduce_partials(s_t, h_t, n_atoms, comm)
+            sums = s_t.cpu().numpy()
+            hist = h_t.cpu().numpy() if h_t is not None else None
+        n_atoms = comm[1]
+    if select_dev is not None:
+        sums = np.array(sums)
+        hist = np.array(hist) if hist is not None else None
+        plan.close()
     return sums, hist, n_atoms, float32
 
 

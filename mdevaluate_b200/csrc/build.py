@@ -14,8 +14,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT_DIR = os.path.join(PKG, '_cuda')
 LIB = os.path.join(OUT_DIR, 'libmdevaluate_b200.so')
-SOURCES = ['abi.cu', 'corr_kernels.cu', 'nojump_kernels.cu', 'dense_kernels.cu']
-HEADERS = ['common.cuh', os.path.join('..', '..', 'include', 'mdevaluate_b200.h')]
+# (source, object name, extra defines): corr_kernels.cu is compiled once per part so that its instantiations build
+# in parallel (0 direct-load kernels, 1-3 bulk kernels without / with byte / with packed image counts)
+UNITS = [('abi.cu', 'abi.o', []), ('corr_host.cu', 'corr_host.o', []), ('comm.cu', 'comm.o', []),
+         ('nojump_kernels.cu', 'nojump_kernels.o', []), ('dense_kernels.cu', 'dense_kernels.o', [])] + [
+    ('corr_kernels.cu', 'corr_kernels_%d.o' % part, ['-DMDB_CORR_PART=%d' % part]) for part in range(4)]
+SOURCES = sorted({u[0] for u in UNITS})
+HEADERS = ['common.cuh', 'corr_core.cuh', os.path.join('..', '..', 'include', 'mdevaluate_b200.h')]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 
@@ -49,11 +54,11 @@ def build(force=False, verbose=False):
         common += ['-Xptxas', '-v']
     procs = []
     objs = []
-    for src in SOURCES:
-        obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
+    for src, obj_name, defines in UNITS:
+        obj = os.path.join(obj_dir, obj_name)
         objs.append(obj)
-        cmd = common + ['-c', os.path.join(HERE, src), '-o', obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        cmd = common + defines + ['-c', os.path.join(HERE, src), '-o', obj]
+        procs.append((obj_name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, proc in procs:
         out, _ = proc.communicate()

@@ -95,6 +95,12 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
 __device__ __forceinline__ float image_float(uint32_t w, int j) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j));
 }
+// The same with the constant 0x4B000000 handed in as a run-time REGISTER value (a kernel parameter): PRMT takes one
+// immediate, and with the constant in a register it is the selector -- otherwise ptxas materialises twelve selectors
+// in registers per row (measured in the SASS: 12 extra moves per 4 evaluations).
+__device__ __forceinline__ float image_float(uint32_t w, int j, uint32_t magic) {
+    return __uint_as_float(__byte_perm(w, magic, 0x7650u | (uint32_t)j));
+}
 __device__ __forceinline__ float rsqrt_approx(float y) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));   // bare MUFU.RSQ
@@ -136,6 +142,32 @@ __device__ __forceinline__ void sinc_of_square_x2(float y0, float y1, float &r0,
     sn0 = __uint_as_float(__float_as_uint(sn0) + (__float_as_uint(kb0) << 31));
     sn1 = __uint_as_float(__float_as_uint(sn1) + (__float_as_uint(kb1) << 31));
     unpack2(mul2(pack2(sn0, sn1), rs), r0, r1);
+}
+
+// ---- image-count formats ------------------------------------------------------------------------------
+// IMG_BYTES:  one byte per component, excess-128 (the scan's native output);
+// IMG_PACKED: one 32-bit word per group of 4 atoms, byte a = atom a of the group, bits 0-1 / 2-3 / 4-5 =
+//             n_x + 1, n_y + 1, n_z + 1 (|n| <= 1, checked by the pack kernel); 1 B instead of 3 B per atom;
+// IMG_I16:    int16 per component (|n| > 127; correctness fallback, direct-load kernel only).
+enum { IMG_NONE = 0, IMG_BYTES = 1, IMG_PACKED = 2, IMG_I16 = 3 };
+
+// Masking a packed word with 0x03030303 << 2d leaves the fields of dimension d of the four atoms in separate
+// bytes, scaled by 4^d.  The scale is a power of two, so it is folded into the box (box_d / 4^d): products and
+// FMA results are bit-identical to the unscaled ones.
+__device__ __forceinline__ uint32_t packed_dim(uint32_t w, int d) { return w & (0x03030303u << (2 * d)); }
+// byte a of a masked word as the double 4^d * n (n = field - 1)
+__device__ __forceinline__ double packed_count(uint32_t masked, int a, int d) {
+    const uint32_t b = __byte_perm(masked, 0u, 0x4440u | (uint32_t)a);
+    return __hiloint2double(0x43300000, (int)b) - (4503599627370496.0 + (double)(1 << (2 * d)));
+}
+
+// predicated shared-memory increment (no return value): red.shared stays a single predicated instruction
+// Unconditional shared-memory add without return value.  ptxas wraps a PREDICATED red/atom in a branch with its own
+// convergence region (BSSY / BRA / BSYNC per update, seen in the SASS), so the histogram kernels instead redirect the
+// samples that must not count to a scratch word; `value` comes from a register (a kernel parameter): an immediate 1
+// turns the instruction into the warp-aggregating ATOMS.POPC.INC, which again needs the convergence region.
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t value) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(value) : "memory");
 }
 
 // ---- mbarrier + bulk-copy (TMA engine) primitives shared by the streaming kernels ------------------

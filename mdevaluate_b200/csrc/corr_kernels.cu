@@ -3,99 +3,76 @@
 // Work decomposition (one CTA = one (origin s, lag chunk c, atom block ab)):
 //   * a thread owns groups of 4 consecutive atoms = 12 interleaved xyz values = 48 bytes per frame
 //     row (three 128-bit accesses, a warp covers 1536 contiguous bytes);
-//   * the unwrapped origin positions of the group are kept in registers (12 doubles) and reused
-//     for the up to kLagChunk lag frames of the chunk;
+//   * the origin positions of the group are kept in registers and reused for the up to kLagChunk lag
+//     frames of the chunk;
 //   * CTAs of the same (s, ab) and different chunks are adjacent in launch order, so the origin
 //     row is fetched from HBM once and re-read from L2 by the other chunks;
-//   * per-lag accumulators live in registers for the whole atom loop; there is ONE block
-//     reduction per CTA at the end, written as a partial; a second tiny kernel adds the
-//     partials of the atom blocks in fixed order (bit-reproducible, no float atomics);
-//   * histograms are accumulated in shared memory (u32, one table per lag of the chunk) and
+//   * per-lag accumulators live in shared memory (one private column per thread) for the whole atom loop;
+//     there is ONE block reduction per CTA at the end, written as a partial; the finish kernel
+//     (corr_host.cu) adds the partials of the atom blocks in fixed order (bit-reproducible, no float atomics);
+//   * histograms are accumulated in shared memory (u32, one table per lag of the chunk) with
+//     red.shared (measured on B200: one warp-wide update per clock and SM, scripts/ubench_atoms.cu) and
 //     flushed with integer atomics.
 //
 // Two data paths feed the same arithmetic:
 //   corr_bulk_kernel  (the product path for float32 rows with 16-byte aligned pitch): a producer
-//       warp streams row tiles (1024 atoms = 12 KiB coordinates + 3 KiB image counts) from HBM
-//       into a ring of shared-memory stages with cp.async.bulk (the TMA engine, SASS UBLKCP),
-//       completion on mbarriers; 8 consumer warps read their 48+12 bytes per stage with
-//       conflict-free LDS and release the stage as soon as the values are in registers.  Memory
-//       parallelism is the ring depth, not the register file.
-//   corr_ldg_kernel   (fallback: float64 rows, unaligned pitch): the same loop with direct
+//       warp streams row tiles (1024 atoms = 12 KiB coordinates + 1 KiB packed / 3 KiB byte image counts)
+//       from HBM into a ring of shared-memory stages with cp.async.bulk (the TMA engine, SASS UBLKCP),
+//       completion on mbarriers; 8 consumer warps read their bytes per stage with conflict-free LDS and
+//       release the stage as soon as the values are in registers.
+//   corr_ldg_kernel   (fallback: float64 rows, unaligned pitch, int16 counts): the same loop with direct
 //       128-bit / scalar global loads.
 //
-// Arithmetic: positions are widened to float64, unwrapped as fma(-n, box, x) (bit-identical to
-// pbc.nojump's float64 frame, pbc.py:235-247), the displacement and r^2 are float64.  sinc is
-// evaluated in float32 from float32(q^2 r^2) and summed per group before it joins the float64
-// accumulator.  Histogram bins follow utils.histogram exactly (utils.py:328-338): a float32
-// estimate decides every sample that is not within rounding distance of a bin edge, the rest
-// take the exact float64 path (np.floor_divide semantics or np.histogram edge search).
-// Exception: launches that ask for the ISF alone on rows with one constant float32 box take their
-// displacements in float32 (process_tile_sinc_f32: the operand on the far side of the periodic boundary is
-// moved first, which keeps every component good to 2^-23 -- the accuracy of the float32 sinc it feeds).
-#include <stdlib.h>
+// Arithmetic, float64 chain: positions are widened to float64, unwrapped as fma(-n, box, x) (bit-identical to
+// pbc.nojump's float64 frame, pbc.py:235-247), the displacement and r^2 are float64; sinc is evaluated in
+// float32 from float32(q^2 r^2).  Float32 displacements (process_tile_f32d; ISF alone, van Hove alone and
+// van Hove + alpha_2 on rows with one constant float32 box): d = x0 - xt - k L with k = n0 - nt, where the
+// operand on the far side of the periodic boundary is moved first, which keeps every component good to 2^-23.
+// Histogram bins follow utils.histogram exactly (utils.py:328-338): a branch-free float32 estimate decides
+// every sample that is not within rounding distance of a bin edge, the rest are recomputed with the
+// reference's float64 arithmetic (np.floor_divide semantics or np.histogram edge search).
+//
+// This file is compiled once per MDB_CORR_PART (see corr_core.cuh).
+#include "corr_core.cuh"
 
-#include "common.cuh"
+#ifndef MDB_CORR_PART
+#error "compile with -DMDB_CORR_PART=0..3"
+#endif
 
 namespace mdb {
 namespace {
 
-constexpr int kThreads = 256;           // compute threads per CTA (both kernels)
-constexpr int kLagChunk = 8;
-constexpr int kWarps = kThreads / 32;
-constexpr int kTileAtoms = 4 * kThreads;          // atoms per bulk tile
-constexpr int kCoordTileBytes = kTileAtoms * 12;  // 12288
-constexpr int kImgTileBytes = kTileAtoms * 3;     // 3072
-constexpr int kBulkThreads = kThreads + 32;       // + one producer warp
-#ifndef MDB_BULK_CTAS_PER_SM
-#define MDB_BULK_CTAS_PER_SM 2
-#endif
+// ---- image counts of one group of 4 atoms (12 components) -----------------------------------------------
+// raw words: IMG_BYTES 3 words (byte c), IMG_PACKED 1 word (byte a, bits 2d), IMG_I16 6 words (int16 c)
+template <int IMG>
+__device__ __forceinline__ int image_count_int(const uint32_t (&w)[6], int c) {
+    if (IMG == IMG_BYTES) return (int)((w[c >> 2] >> (8 * (c & 3))) & 0xffu) - MDB_IMAGE_BIAS;
+    if (IMG == IMG_PACKED) return (int)((w[0] >> (8 * (c / 3) + 2 * (c % 3))) & 3u) - 1;
+    if (IMG == IMG_I16) return (int)(short)(w[c >> 1] >> (16 * (c & 1)));
+    return 0;
+}
 
-struct CorrDev {
-    const void *coords;
-    long long pitch;
-    const uint8_t *images;
-    long long img_pitch;
-    const double *box;
-    double box_const[3];  // used when box == nullptr: the same box for every row (kernel-parameter constants)
-    int n_atoms;
-    int n_groups;        // ceil(n_atoms / 4)
-    int groups_per_block;
-    int S, L;
-    const int *rows;
-    const uint8_t *select;   // [S][sel_pitch] 1 = atom takes part for origin s (sub-ensembles), or nullptr
-    long long sel_pitch;
-    int n_chunks, n_ablocks;
-    double q2;
-    int sinc_f32;        // ISF alone, constant float32 box: displacements in float32 (process_tile_sinc_f32)
-    float q2f;           // float(q^2) and the negated box as the packed pairs (x,y) (z,x) (y,z) of that path:
-    alignas(8) float neg_box2[6];   // kernel parameters = constant bank, read as 64-bit operands
-    int leg_order;
-    int n_bins;
-    int bin_mode;
-    double dx, inv_dx;
-    float inv_dx_f;
-    int hist_f32;        // candidate (MDB_HIST_F32=1): van Hove alone, float32 displacements for the bin estimate
-                         // (sits in what was padding: the parameter offsets of the measured kernels do not move)
-    const double *edges;
-    double *partial;     // [S*L][n_ablocks][3]
-    unsigned long long *hist;
-};
-
-// ---- unwrap: 12 raw float32 components (+ packed int8 image counts) -> 12 float64 -------------
-template <bool IMG>
-__device__ __forceinline__ void unwrap12(const float (&raw)[12], const uint32_t (&w)[3], const double *bx,
+// ---- unwrap: 12 raw float32 components (+ image counts) -> 12 float64 ------------------------------------
+// bx: the box of the row; for IMG_PACKED it is already divided by 4^d (the packed fields come scaled).
+template <int IMG>
+__device__ __forceinline__ void unwrap12(const float (&raw)[12], const uint32_t (&w)[6], const double *bx,
                                          double (&u)[12]) {
-    if (IMG) {
-        const double b0 = bx[0], b1 = bx[1], b2 = bx[2];
-#pragma unroll
-        for (int c = 0; c < 12; ++c) {
-            const double n = image_count(w[c >> 2], c & 3);
-            const double b = (c % 3 == 0) ? b0 : ((c % 3 == 1) ? b1 : b2);
-            u[c] = fma(-n, b, (double)raw[c]);
-        }
-    } else {
+    if (IMG == IMG_NONE) {
 #pragma unroll
         for (int c = 0; c < 12; ++c) u[c] = (double)raw[c];
+        return;
+    }
+    const double b[3] = {bx[0], bx[1], bx[2]};
+    if (IMG == IMG_PACKED) {
+        const uint32_t m[3] = {packed_dim(w[0], 0), packed_dim(w[0], 1), packed_dim(w[0], 2)};
+#pragma unroll
+        for (int c = 0; c < 12; ++c) u[c] = fma(-packed_count(m[c % 3], c / 3, c % 3), b[c % 3], (double)raw[c]);
+    } else if (IMG == IMG_BYTES) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) u[c] = fma(-image_count(w[c >> 2], c & 3), b[c % 3], (double)raw[c]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) u[c] = fma(-(double)image_count_int<IMG_I16>(w, c), b[c % 3], (double)raw[c]);
     }
 }
 
@@ -126,6 +103,79 @@ __device__ __forceinline__ double r2_unfused(double ddx, double ddy, double ddz)
     return __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
 }
 
+// Exact bin of one float64 displacement (the rare / general path, kept out of line so that the streaming
+// loop stays small): float64 sqrt of the unfused r^2, then utils.histogram's rule; counts it.
+__device__ __noinline__ void exact_count(double ddx, double ddy, double ddz, int bin_mode, double dx, double inv_dx,
+                                         int n_bins, const double *s_edges, unsigned int *s_hist_k) {
+    const double r = sqrt(r2_unfused(ddx, ddy, ddz));
+    int bin;
+    if (bin_mode == MDB_BINS_UNIFORM) {
+        const long long kk = exact_floor_div(r, dx, inv_dx);
+        bin = (kk < n_bins) ? (int)kk : -1;
+    } else {
+        bin = edge_bin(r, s_edges, n_bins);
+    }
+    if (bin >= 0) atomicAdd(&s_hist_k[bin], 1u);
+}
+
+// The same from the raw values of one atom (float32 position + integer image counts of the two frames, one
+// constant box): the reference's float64 arithmetic (pbc.py:235-247, correlation.py:246-247, utils.py:334),
+// for the samples the float32-displacement path cannot decide.  Uniform bins only.
+__device__ __noinline__ void exact_count_raw(double bx, double by, double bz, double dx, double inv_dx, int n_bins,
+                                             float x0, float y0, float z0, int n0x, int n0y, int n0z, float xt,
+                                             float yt, float zt, int ntx, int nty, int ntz, unsigned int *s_hist_k) {
+    const double ddx = fma(-(double)n0x, bx, (double)x0) - fma(-(double)ntx, bx, (double)xt);
+    const double ddy = fma(-(double)n0y, by, (double)y0) - fma(-(double)nty, by, (double)yt);
+    const double ddz = fma(-(double)n0z, bz, (double)z0) - fma(-(double)ntz, bz, (double)zt);
+    const long long kk = exact_floor_div(sqrt(r2_unfused(ddx, ddy, ddz)), dx, inv_dx);
+    if (kk < n_bins) atomicAdd(&s_hist_k[(int)kk], 1u);
+}
+
+// Branch-free bin estimate of 4 samples from float32 r^2 (uniform bins).  th = r/dx - 1/2, so that the
+// nearest integer of th (the 1.5*2^23 trick: no conversion instructions) is floor(r/dx) for every sample that is
+// not next to a bin edge, and dd = th - rint(th) = frac(r/dx) - 1/2.  A sample is decided here when
+// |dd| < 1/2 - margin(t), margin = twice the float32 error bound of t (p.hist_c1, p.hist_lim0); the others
+// come back in the returned mask and are recomputed exactly.  r = 0 gives NaN (0 * inf): not decided.  The bin
+// of a decided sample is (bits of tb) - 0x4B400000 >= 0; the subtraction is folded into the table address
+// (`table` = shared address of the lag's table - 4 * 0x4B400000) and t >= 2^22 (dropped like every r >= n_bins dx)
+// fails the range test.  The update itself is unconditional (see red_shared_add).
+template <bool MASKED>
+__device__ __forceinline__ uint32_t hist_fast4(const CorrDev &p, const float (&r2)[4], uint32_t vmask, uint32_t table,
+                                               uint32_t trash) {
+    const f32x2 inv_dx = bcast2(p.inv_dx_f), mhalf = bcast2(-0.5f), big = bcast2(12582912.0f),
+                nbig = bcast2(-12582912.0f), c1 = bcast2(p.hist_c1), lim0 = bcast2(p.hist_lim0);
+    const uint32_t one = p.one;
+    float tb[4], dd[4], lim[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const f32x2 r = mul2(pack2(r2[2 * h], r2[2 * h + 1]), pack2(rsqrt_approx(r2[2 * h]), rsqrt_approx(r2[2 * h + 1])));
+        const f32x2 th = fma2(r, inv_dx, mhalf);
+        const f32x2 b = add2(th, big);
+        unpack2(b, tb[2 * h], tb[2 * h + 1]);
+        unpack2(sub2(th, add2(b, nbig)), dd[2 * h], dd[2 * h + 1]);
+        unpack2(fma2(th, c1, lim0), lim[2 * h], lim[2 * h + 1]);
+    }
+    uint32_t slow = 0u;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const bool live = !MASKED || ((vmask >> a) & 1u);
+        const bool fast = fabsf(dd[a]) < lim[a];
+        const uint32_t ib = __float_as_uint(tb[a]);
+        // samples that are undecided, out of range or masked go to the scratch word `trash`
+#ifdef MDB_DBG_FAST_ATOMIC
+        if (live && fast && ib < p.ib_limit) {
+            unsigned int *ptr;
+            asm("cvta.shared.u64 %0, %1;" : "=l"(ptr) : "l"((unsigned long long)(table + 4u * ib)));
+            atomicAdd(ptr, 1u);
+        }
+#else
+        red_shared_add((live && fast && ib < p.ib_limit) ? table + 4u * ib : trash, one);
+#endif
+        slow |= (live && !fast) ? (1u << a) : 0u;
+    }
+    return slow;
+}
+
 // Accumulators of one thread for the lags of its chunk.
 template <int FLAGS>
 struct Accum {
@@ -145,19 +195,7 @@ struct Accum {
     }
 };
 
-// Exact bin of one displacement (the rare / general path, kept out of line so that the streaming
-// loop stays small): float64 sqrt of the unfused r^2, then utils.histogram's rule.
-__device__ __noinline__ int exact_bin(double ddx, double ddy, double ddz, int bin_mode, double dx, double inv_dx,
-                                      int n_bins, const double *s_edges) {
-    const double r = sqrt(r2_unfused(ddx, ddy, ddz));
-    if (bin_mode == MDB_BINS_UNIFORM) {
-        const long long kk = exact_floor_div(r, dx, inv_dx);
-        return (kk < n_bins) ? (int)kk : -1;
-    }
-    return edge_bin(r, s_edges, n_bins);
-}
-
-// One group of 4 atoms against one lag frame: partial sums of r^2, r^4 (float64) and sinc (float32)
+// One group of 4 atoms against one lag frame in float64: partial sums of r^2, r^4 (float64) and sinc (float32)
 // over the group, histogram counts straight into shared memory.  MASKED is instantiated for the
 // last tile of a shard and for sub-ensemble launches: bit a of `vmask` says whether atom a of the
 // group takes part (it exists, and the origin's selector picked it); the others are computed and
@@ -166,7 +204,7 @@ template <int FLAGS, bool HIST_F32, bool MASKED>
 __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[12], const float (&raw0)[12],
                                            const double (&ut)[12], const float (&rawt)[12], uint32_t vmask,
                                            double &sum2, double &sum4, float &sums, unsigned int *s_hist_k,
-                                           const double *s_edges) {
+                                           const double *s_edges, uint32_t trash) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
@@ -175,8 +213,7 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
     sum4 = 0.0;
     sums = 0.0f;
     float yq[4];
-    double dd[4][3];
-    double r2v[4];
+    float r2f[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const double ddx = u0[3 * a] - ut[3 * a];
@@ -198,10 +235,7 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
         if constexpr (kR2) sum2 += on ? r2 : 0.0;
         if constexpr (kR4) sum4 = MASKED ? sum4 + (on ? r2 * r2 : 0.0) : fma(r2, r2, sum4);
         if constexpr (kSinc) yq[a] = (float)(r2 * p.q2);
-        if constexpr (kHist) {
-            dd[a][0] = ddx; dd[a][1] = ddy; dd[a][2] = ddz;
-            r2v[a] = r2;
-        }
+        if constexpr (kHist) r2f[a] = (float)r2;
     }
     if constexpr (kSinc) {
         float v0, v1, v2, v3;
@@ -238,42 +272,17 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
                 }
             }
         } else {
-            // Uniform bins: a branch-free float32 estimate t = r/dx (MUFU.RSQ, no conversions: the
-            // nearest integer and the distance to it come from the 1.5*2^23 trick).  A sample is
-            // decided here when it lies farther from every bin edge than the float32 error bound;
-            // everything else (and non-uniform bins) goes through exact_bin().
-            bool slow[4];
-            bool any_slow = false;
+            // uniform bins: the float32 estimate decides what is clear of the bin edges; everything else (and
+            // every sample of non-uniform bins) is counted by exact_count()
+            uint32_t slow = MASKED ? (vmask & 0xfu) : 0xfu;
+            if (p.bin_mode == MDB_BINS_UNIFORM)
+                slow = hist_fast4<MASKED>(p, r2f, vmask, smem_u32(s_hist_k) - 4u * 0x4B400000u, trash);
+            if (slow) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const bool live = !MASKED || ((vmask >> a) & 1u);
-                bool fast = false;
-                int bin = 0;
-                if (p.bin_mode == MDB_BINS_UNIFORM) {
-                    const float r2f = (float)r2v[a];
-                    const float t = (r2f * rsqrt_approx(r2f)) * p.inv_dx_f;       // NaN for r2f == 0 -> slow
-                    const float tb = t + 12582912.0f;
-                    const float tr = tb - 12582912.0f;                            // rint(t) for t < 2^22
-                    const float dist = t - tr;
-                    const float margin = fmaf(t, 8.0e-7f, 1.0e-6f);   // 2x the float32 error bound (3.9e-7 t)
-                    bin = (__float_as_int(tb) - 0x4B400000) - (dist < 0.0f ? 1 : 0);
-                    // t >= 2^22 needs no test: the trick then yields some bin >= 2^22 - 1 > n_bins (dropped,
-                    // as the true bin would be); NaN (r = 0) fails the comparison and goes the exact way
-                    fast = fabsf(dist) > margin;
-                }
-                slow[a] = live && !fast;
-                any_slow |= slow[a];
-                if (live && fast && bin < p.n_bins) atomicAdd(&s_hist_k[bin], 1u);
-            }
-            if (any_slow) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    if (slow[a]) {
-                        const int bin = exact_bin(dd[a][0], dd[a][1], dd[a][2], p.bin_mode, p.dx, p.inv_dx, p.n_bins,
-                                                  s_edges);
-                        if (bin >= 0) atomicAdd(&s_hist_k[bin], 1u);
-                    }
-                }
+                for (int a = 0; a < 4; ++a)
+                    if (slow & (1u << a))
+                        exact_count(u0[3 * a] - ut[3 * a], u0[3 * a + 1] - ut[3 * a + 1], u0[3 * a + 2] - ut[3 * a + 2],
+                                    p.bin_mode, p.dx, p.inv_dx, p.n_bins, s_edges, s_hist_k);
             }
         }
     }
@@ -290,6 +299,16 @@ __device__ __forceinline__ uint32_t group_mask(const CorrDev &p, int s, int g) {
              ((w & 0xff000000u) ? 8u : 0u);
     }
     return m;
+}
+
+// Scratch words for the histogram updates that must not count (hist_fast4): one word per lane in a 128-byte line of
+// its own at the end of the dynamic shared memory (kHistTailBytes, reserved by make_plan) -- no two lanes of a warp
+// share a word, and the line holds nothing else.  (A single scratch word placed next to the mbarriers of the ring
+// made samples read overwritten stages -- found with scripts/debug_hist.py; the barriers share no line with anything
+// the kernels update with shared-memory atomics any more.)
+__device__ __forceinline__ uint32_t trash_slot(const CorrDev &p, const double *s_edges, int tid) {
+    const uint32_t tail = smem_u32(s_edges) + (p.bin_mode == MDB_BINS_EDGES ? 8u * (uint32_t)(p.n_bins + 1) : 0u);
+    return ((tail + 127u) & ~127u) + 4u * (uint32_t)(tid & 31);
 }
 
 // CTA prologue shared by both kernels: which (origin, chunk, atom block) am I, rows and boxes.
@@ -309,7 +328,7 @@ __device__ __forceinline__ CtaWork cta_work(const CorrDev &p) {
     return w;
 }
 
-template <bool IMG>
+template <int IMG>
 __device__ __forceinline__ void load_rows(const CorrDev &p, const CtaWork &w, int tid, int *s_row,
                                           double (*s_box)[3]) {
     if (tid <= kLagChunk) {
@@ -317,10 +336,12 @@ __device__ __forceinline__ void load_rows(const CorrDev &p, const CtaWork &w, in
         const int l = (tid == 0) ? 0 : w.l0 + tid - 1;
         const int row = (tid == 0 || tid - 1 < w.nl) ? p.rows[(long long)w.s * p.L + l] : 0;
         s_row[tid] = row;
-        if (IMG) {
+        if (IMG != IMG_NONE) {
+            // packed counts come scaled by 4^d: the box is divided accordingly (exact)
+            const double sy = IMG == IMG_PACKED ? 0.25 : 1.0, sz = IMG == IMG_PACKED ? 0.0625 : 1.0;
             s_box[tid][0] = p.box ? p.box[3ll * row] : p.box_const[0];
-            s_box[tid][1] = p.box ? p.box[3ll * row + 1] : p.box_const[1];
-            s_box[tid][2] = p.box ? p.box[3ll * row + 2] : p.box_const[2];
+            s_box[tid][1] = p.box ? p.box[3ll * row + 1] * sy : p.box_const[1];
+            s_box[tid][2] = p.box ? p.box[3ll * row + 2] * sz : p.box_const[2];
         }
     }
 }
@@ -368,18 +389,20 @@ __device__ __forceinline__ void cta_epilogue(const CorrDev &p, const CtaWork &w,
     }
 }
 
+#if MDB_CORR_PART == 0
 // =================================================================================================
-// fallback path: direct global loads (float64 rows, unaligned pitch)
+// fallback path: direct global loads (float64 rows, unaligned pitch, int16 image counts)
 // =================================================================================================
-template <typename CT, bool IMG, bool VEC, bool STREAM>
+template <typename CT, int IMG, bool VEC, bool STREAM>
 struct GroupLoader;
 
-template <bool IMG, bool VEC, bool STREAM>
+template <int IMG, bool VEC, bool STREAM>
 struct GroupLoader<float, IMG, VEC, STREAM> {
     __device__ static __forceinline__ void load(const CorrDev &p, int row, int g, int nv, const double *bx,
                                                 double (&u)[12], float (&raw)[12]) {
         const float *base = static_cast<const float *>(p.coords) + (long long)row * p.pitch + 12ll * g;
-        uint32_t w[3] = {0x80808080u, 0x80808080u, 0x80808080u};   // n = 0 in excess-128
+        uint32_t w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        if (IMG == IMG_BYTES) w[0] = w[1] = w[2] = 0x80808080u;   // n = 0 in excess-128
         if (VEC && nv == 4) {
             const float4 *b4 = reinterpret_cast<const float4 *>(base);
             float4 a, b, c;
@@ -392,8 +415,8 @@ struct GroupLoader<float, IMG, VEC, STREAM> {
 #pragma unroll
             for (int c = 0; c < 12; ++c) raw[c] = (c < 3 * nv) ? __ldg(base + c) : 0.0f;
         }
-        if (IMG) {
-            const uint8_t *ib = p.images + (long long)row * p.img_pitch + 12ll * g;
+        if (IMG == IMG_BYTES) {
+            const uint8_t *ib = static_cast<const uint8_t *>(p.images) + (long long)row * p.img_pitch + 12ll * g;
             if (VEC && nv == 4) {
                 const uint32_t *iw = reinterpret_cast<const uint32_t *>(ib);
                 if (STREAM) { w[0] = ld_stream(iw); w[1] = ld_stream(iw + 1); w[2] = ld_stream(iw + 2); }
@@ -405,12 +428,18 @@ struct GroupLoader<float, IMG, VEC, STREAM> {
                         w[c >> 2] = (w[c >> 2] & ~(0xffu << (8 * (c & 3)))) | ((uint32_t)ib[c] << (8 * (c & 3)));
             }
         }
+        if (IMG == IMG_I16) {
+            const uint16_t *ib = reinterpret_cast<const uint16_t *>(p.images) + (long long)row * p.img_pitch + 12ll * g;
+#pragma unroll
+            for (int c = 0; c < 12; ++c)
+                if (c < 3 * nv) w[c >> 1] |= (uint32_t)__ldg(ib + c) << (16 * (c & 1));
+        }
         unwrap12<IMG>(raw, w, bx, u);
     }
 };
 
 template <bool VEC, bool STREAM>
-struct GroupLoader<double, false, VEC, STREAM> {
+struct GroupLoader<double, IMG_NONE, VEC, STREAM> {
     __device__ static __forceinline__ void load(const CorrDev &p, int row, int g, int nv, const double *,
                                                 double (&u)[12], float (&)[12]) {
         const double *base = static_cast<const double *>(p.coords) + (long long)row * p.pitch + 12ll * g;
@@ -429,10 +458,10 @@ struct GroupLoader<double, false, VEC, STREAM> {
     }
 };
 
-template <typename CT, bool IMG, int FLAGS, bool VEC>
+template <typename CT, int IMG, int FLAGS, bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) {
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
-    constexpr bool kHistF32 = kHist && sizeof(CT) == 4 && !IMG;
+    constexpr bool kHistF32 = kHist && sizeof(CT) == 4 && IMG == IMG_NONE;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_row[kLagChunk + 1];
@@ -443,6 +472,7 @@ __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) 
     const int tid = threadIdx.x;
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem_raw);
     double *s_edges = reinterpret_cast<double *>(smem_raw + (size_t)kLagChunk * p.n_bins * sizeof(unsigned int));
+    const uint32_t trash = trash_slot(p, s_edges, tid);
 
     load_rows<IMG>(p, w, tid, s_row, s_box);
     if (kHist) {
@@ -471,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) 
                 double s2, s4;
                 float ss;
                 eval_group<FLAGS, kHistF32, true>(p, u0, raw0, ut, rawt, vmask, s2, s4, ss, s_hist + k * p.n_bins,
-                                                  s_edges);
+                                                  s_edges, trash);
                 if constexpr (Accum<FLAGS>::kR2) acc.r2[k] += s2;
                 if constexpr (Accum<FLAGS>::kR4) acc.r4[k] += s4;
                 if constexpr (Accum<FLAGS>::kSinc) acc.sc[k] += (double)ss;
@@ -480,15 +510,15 @@ __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) 
     }
     cta_epilogue<FLAGS>(p, w, tid, acc, s_red, s_hist, [] { __syncthreads(); });
 }
+#endif  // MDB_CORR_PART == 0
 
+#if MDB_CORR_PART != 0
 // =================================================================================================
 // product path: cp.async.bulk (TMA) -> shared-memory ring -> compute warps
 // =================================================================================================
 __device__ __forceinline__ void compute_barrier() {  // named barrier 1: the kThreads compute threads
     asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
 }
-
-constexpr int kMaxStages = 8;
 
 // Ring position of a compute thread / the producer.
 struct Ring {
@@ -499,18 +529,19 @@ struct Ring {
 };
 
 // Take the calling thread's 4 atoms out of the current stage and release the stage.
-template <bool IMG>
+template <int IMG>
 __device__ __forceinline__ void fetch_raw(Ring &ring, uint32_t full0, uint32_t empty0, const unsigned char *stages,
-                                          int stage_bytes, int tid, float (&raw)[12], uint32_t (&wds)[3]) {
+                                          int stage_bytes, int tid, float (&raw)[12], uint32_t (&wds)[6]) {
     mbar_wait(full0 + 8 * ring.stage, ring.phase);
     const unsigned char *src = stages + (size_t)ring.stage * stage_bytes;
     const float4 *c4 = reinterpret_cast<const float4 *>(src) + 3 * tid;
     const float4 a = c4[0], b = c4[1], c = c4[2];
-    wds[0] = wds[1] = wds[2] = 0x80808080u;
-    if (IMG) {
+    wds[0] = wds[1] = wds[2] = wds[3] = wds[4] = wds[5] = 0u;
+    if (IMG == IMG_BYTES) {
         const uint32_t *iw = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes) + 3 * tid;
         wds[0] = iw[0]; wds[1] = iw[1]; wds[2] = iw[2];
     }
+    if (IMG == IMG_PACKED) wds[0] = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes)[tid];
     raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
     raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
     raw[8] = c.x; raw[9] = c.y; raw[10] = c.z; raw[11] = c.w;
@@ -523,191 +554,165 @@ __device__ __forceinline__ void fetch_raw(Ring &ring, uint32_t full0, uint32_t e
 }
 
 // ... and unwrap to float64.
-template <bool IMG, bool BOXC>
+template <int IMG, bool BOXC>
 __device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
                                             const unsigned char *stages, int stage_bytes, int tid,
                                             const double *bx, double (&u)[12], float (&raw)[12]) {
-    uint32_t wds[3];
+    uint32_t wds[6];
     fetch_raw<IMG>(ring, full0, empty0, stages, stage_bytes, tid, raw, wds);
     // a box that is the same for every row comes from the kernel parameters (constant bank operands)
     unwrap12<IMG>(raw, wds, BOXC ? p.box_const : bx, u);
 }
 
-// ISF alone on unwrapped float32 rows with one constant box: the displacement in FLOAT32, without
-// conversions and without the float64 pipe.  d = (x0 - n0 L) - (xt - nt L) = x0 - xt - k L with k = n0 - nt.
-// k = 0 (the common case): fl(x0 - xt) is the exact difference rounded once (relative 2^-24).  k != 0: the
-// operand on the far side of the boundary is moved first -- k > 0: (x0 - kL) - xt, k < 0: x0 - (xt + kL) --
-// one FMA each, so the moved operand is the exact value rounded once and, being within |d| of the boundary
-// (Sterbenz: exact when it lies in [L/2, L]), carries an error of at most ulp(d)/2; moving the OTHER
-// operand would cost ulp(L)/2.  Every component of d is thus good to ~2^-23 relative, the same order as
-// the float32 sinc that follows (sinc_of_square_x2), which is why this path exists for the ISF only:
-// MSD / alpha_2 / van Hove keep the float64 arithmetic of the reference.  Image counts become floats by
-// one byte-permute (image_float); all adds / fmas are packed pairs (components 2j, 2j+1 of the 12).
-template <bool MASKED>
-__device__ __forceinline__ void process_tile_sinc_f32(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
-                                                      const unsigned char *stages, int stage_bytes, int tid,
-                                                      uint32_t vmask, int nl, double *s_acc) {
+// Float32 displacements on rows with one constant float32 box, without conversions and without the float64
+// pipe.  d = (x0 - n0 L) - (xt - nt L) = x0 - xt - k L with k = n0 - nt.  k = 0 (the common case): fl(x0 - xt) is
+// the exact difference rounded once (relative 2^-24).  k != 0: the operand on the far side of the boundary is moved
+// first -- k > 0: (x0 - kL) - xt, k < 0: x0 - (xt + kL) -- one FMA each, so the moved operand is the exact value
+// rounded once and, being within |d| of the boundary (Sterbenz: exact when it lies in [L/2, L]), carries an error
+// of at most ulp(d)/2; moving the OTHER operand would cost ulp(L)/2.  Every component of d is thus good to ~2^-23
+// relative -- the accuracy of the float32 sinc (ISF), far inside the margin of the bin estimate (van Hove; the
+// undecided samples are recomputed in float64 from the raw values, so the counts stay exact), and 1e-7 relative
+// per atom on r^2, r^4 for alpha_2 when it rides along with the histogram (BASELINE config 3; alone, MSD and
+// alpha_2 keep the float64 chain).  Image counts become floats by one byte-permute (image_float); all adds / fmas
+// are packed pairs (components 2j, 2j+1 of the 12).  Packed counts: the three masked words (one per dimension, see
+// packed_dim) of the lag row are subtracted from the biased ones of the origin as integers, the four bytes of each
+// difference are 64 + 4^d k.
+template <int IMG, int FLAGS, bool MASKED>
+__device__ __forceinline__ void process_tile_f32d(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
+                                                  const unsigned char *stages, int stage_bytes, int tid,
+                                                  uint32_t vmask, int nl, double *s_acc, unsigned int *s_hist,
+                                                  uint32_t trash) {
+    constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;          // with R4: alpha_2 next to the histogram
+    constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
+    constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
+    constexpr int NV = (kR2 ? 2 : 0) + (kSinc ? 1 : 0);
+    static_assert(IMG == IMG_BYTES || IMG == IMG_PACKED, "float32 displacements need image counts");
     const f32x2 *neg_box = reinterpret_cast<const f32x2 *>(p.neg_box2);      // dims of pair j: j % 3
     const f32x2 q2 = bcast2(p.q2f);
+    const uint32_t magic = p.magic23;
+    float raw0[12];
+    uint32_t w0[6];
+    fetch_raw<IMG>(ring, full0, empty0, stages, stage_bytes, tid, raw0, w0);
     f32x2 x0[6], f0[6];
-    {
-        float raw0[12];
-        uint32_t w0[3];
-        fetch_raw<true>(ring, full0, empty0, stages, stage_bytes, tid, raw0, w0);
+    uint32_t o[3];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            x0[j] = pack2(raw0[2 * j], raw0[2 * j + 1]);
-            f0[j] = pack2(image_float(w0[(2 * j) >> 2], (2 * j) & 3), image_float(w0[(2 * j + 1) >> 2], (2 * j + 1) & 3));
-        }
+    for (int j = 0; j < 6; ++j) {
+        x0[j] = pack2(raw0[2 * j], raw0[2 * j + 1]);
+        if (IMG == IMG_BYTES)
+            f0[j] = pack2(image_float(w0[(2 * j) >> 2], (2 * j) & 3, magic),
+                          image_float(w0[(2 * j + 1) >> 2], (2 * j + 1) & 3, magic));
     }
+    if (IMG == IMG_PACKED) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) o[d] = packed_dim(w0[0], d) + 0x40404040u;
+    }
+    const uint32_t table0 = smem_u32(s_hist) - 4u * 0x4B400000u;
 #pragma unroll 1
     for (int k = 0; k < nl; ++k) {
         float rawt[12];
-        uint32_t wt[3];
-        fetch_raw<true>(ring, full0, empty0, stages, stage_bytes, tid, rawt, wt);
-        float d[12];
+        uint32_t wt[6];
+        fetch_raw<IMG>(ring, full0, empty0, stages, stage_bytes, tid, rawt, wt);
+        uint32_t kd[3];
+        if (IMG == IMG_PACKED) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) kd[d] = o[d] - packed_dim(wt[0], d);     // bytes: 64 + 4^d (n0 - nt)
+        }
+        float dv[12];
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const f32x2 ft = pack2(image_float(wt[(2 * j) >> 2], (2 * j) & 3),
-                                   image_float(wt[(2 * j + 1) >> 2], (2 * j + 1) & 3));
-            const f32x2 dn = sub2(f0[j], ft);                    // n0 - nt, exact
+            f32x2 dn;                                                            // (scaled) n0 - nt, exact
+            if (IMG == IMG_BYTES) {
+                const f32x2 ft = pack2(image_float(wt[(2 * j) >> 2], (2 * j) & 3, magic),
+                                       image_float(wt[(2 * j + 1) >> 2], (2 * j + 1) & 3, magic));
+                dn = sub2(f0[j], ft);
+            } else {
+                const int c0 = 2 * j, c1 = 2 * j + 1;
+                dn = add2(pack2(image_float(kd[c0 % 3], c0 / 3, magic), image_float(kd[c1 % 3], c1 / 3, magic)),
+                          bcast2(-8388672.0f));
+            }
             float dn0, dn1;
             unpack2(dn, dn0, dn1);
             const f32x2 up = pack2(fmaxf(dn0, 0.0f), fmaxf(dn1, 0.0f));     // images the origin is moved by
             const f32x2 dw = sub2(up, dn);                                   // images the lag frame is moved by
-            const f32x2 o = fma2(up, neg_box[j % 3], x0[j]);
-            const f32x2 t = fma2(dw, neg_box[j % 3], pack2(rawt[2 * j], rawt[2 * j + 1]));
-            unpack2(sub2(o, t), d[2 * j], d[2 * j + 1]);
+            const f32x2 om = fma2(up, neg_box[j % 3], x0[j]);
+            const f32x2 tm = fma2(dw, neg_box[j % 3], pack2(rawt[2 * j], rawt[2 * j + 1]));
+            unpack2(sub2(om, tm), dv[2 * j], dv[2 * j + 1]);
         }
         float r2[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
-            r2[a] = fmaf(d[3 * a + 2], d[3 * a + 2], fmaf(d[3 * a + 1], d[3 * a + 1], d[3 * a] * d[3 * a]));
-        float y0, y1, y2, y3, v0, v1, v2, v3;
-        unpack2(mul2(pack2(r2[0], r2[1]), q2), y0, y1);
-        unpack2(mul2(pack2(r2[2], r2[3]), q2), y2, y3);
-        sinc_of_square_x2(y0, y1, v0, v1);
-        sinc_of_square_x2(y2, y3, v2, v3);
-        if (MASKED) {
-            v0 = (vmask & 1u) ? v0 : 0.0f;
-            v1 = (vmask & 2u) ? v1 : 0.0f;
-            v2 = (vmask & 4u) ? v2 : 0.0f;
-            v3 = (vmask & 8u) ? v3 : 0.0f;
+            r2[a] = fmaf(dv[3 * a + 2], dv[3 * a + 2], fmaf(dv[3 * a + 1], dv[3 * a + 1], dv[3 * a] * dv[3 * a]));
+        double *col = s_acc + (size_t)k * NV * kThreads + tid;
+        if constexpr (kR2) {
+            float m0 = r2[0], m1 = r2[1], m2 = r2[2], m3 = r2[3];
+            if (MASKED) {
+                m0 = (vmask & 1u) ? m0 : 0.0f;
+                m1 = (vmask & 2u) ? m1 : 0.0f;
+                m2 = (vmask & 4u) ? m2 : 0.0f;
+                m3 = (vmask & 8u) ? m3 : 0.0f;
+            }
+            col[0] += (double)((m0 + m1) + (m2 + m3));
+            col[kThreads] += (double)fmaf(m0, m0, fmaf(m1, m1, fmaf(m2, m2, m3 * m3)));
         }
-        s_acc[(size_t)k * kThreads + tid] += (double)((v0 + v1) + (v2 + v3));
-    }
-}
-
-// ---- CANDIDATE, not the default (MDB_HIST_F32=1; written after the round-1 GPU budget was spent, unmeasured) ------
-// van Hove alone, uniform bins, one constant float32 box: the same float32 displacements as the ISF path feed the
-// branch-free bin ESTIMATE; a sample within the (wider) margin of a bin edge is recomputed from the raw values with the
-// reference's float64 arithmetic and utils.histogram's rule, so the counts stay exact.  The margin 1.6e-6 t + 1e-6
-// covers the estimate's error with float32 displacements (tests/test_histogram_estimate.py replays it on the CPU).
-constexpr int kVariantF32 = 64;      // pseudo flag bit that selects this instantiation
-
-__device__ __noinline__ void exact_hist_from_raw(double bx, double by, double bz, double dx, double inv_dx, int n_bins,
-                                                 float x0, float y0, float z0, uint32_t n0, float xt, float yt, float zt,
-                                                 uint32_t nt, unsigned int *s_hist_k) {
-    // n0 / nt: the three excess-128 image bytes of the atom in bytes 0..2; scalars, not the parameter struct,
-    // cross the call (a reference to it would force a local copy)
-    const double ddx = fma(-image_count(n0, 0), bx, (double)x0) - fma(-image_count(nt, 0), bx, (double)xt);
-    const double ddy = fma(-image_count(n0, 1), by, (double)y0) - fma(-image_count(nt, 1), by, (double)yt);
-    const double ddz = fma(-image_count(n0, 2), bz, (double)z0) - fma(-image_count(nt, 2), bz, (double)zt);
-    // exact_bin()'s uniform-bin rule, spelled out here so that exact_bin keeps exactly the callers it was measured with
-    const long long kk = exact_floor_div(sqrt(r2_unfused(ddx, ddy, ddz)), dx, inv_dx);
-    if (kk < n_bins) atomicAdd(&s_hist_k[(int)kk], 1u);
-}
-
-// bytes of components 3a, 3a+1, 3a+2 of the group's 12 (three packed words) in bytes 0..2 of one word
-__device__ __forceinline__ uint32_t atom_image_bytes(const uint32_t (&w)[3], int a) {
-    const int c = 3 * a;
-    const uint32_t lo = w[c >> 2], hi = w[(c + 2) >> 2];
-    return __byte_perm(lo, hi, (uint32_t)((c & 3) | ((((c + 1) >> 2) == (c >> 2) ? ((c + 1) & 3) : (4 + ((c + 1) & 3))) << 4) |
-                                          ((((c + 2) >> 2) == (c >> 2) ? ((c + 2) & 3) : (4 + ((c + 2) & 3))) << 8) | (0x4u << 12)));
-}
-
-template <bool MASKED>
-__device__ __forceinline__ void process_tile_hist_f32(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
-                                                      const unsigned char *stages, int stage_bytes, int tid,
-                                                      uint32_t vmask, int nl, unsigned int *s_hist) {
-    const f32x2 *neg_box = reinterpret_cast<const f32x2 *>(p.neg_box2);
-    float raw0[12];
-    uint32_t w0[3];
-    fetch_raw<true>(ring, full0, empty0, stages, stage_bytes, tid, raw0, w0);
-    f32x2 x0[6], f0[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        x0[j] = pack2(raw0[2 * j], raw0[2 * j + 1]);
-        f0[j] = pack2(image_float(w0[(2 * j) >> 2], (2 * j) & 3), image_float(w0[(2 * j + 1) >> 2], (2 * j + 1) & 3));
-    }
-#pragma unroll 1
-    for (int k = 0; k < nl; ++k) {
-        float rawt[12];
-        uint32_t wt[3];
-        fetch_raw<true>(ring, full0, empty0, stages, stage_bytes, tid, rawt, wt);
-        float d[12];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const f32x2 ft = pack2(image_float(wt[(2 * j) >> 2], (2 * j) & 3),
-                                   image_float(wt[(2 * j + 1) >> 2], (2 * j + 1) & 3));
-            const f32x2 dn = sub2(f0[j], ft);
-            float dn0, dn1;
-            unpack2(dn, dn0, dn1);
-            const f32x2 up = pack2(fmaxf(dn0, 0.0f), fmaxf(dn1, 0.0f));
-            const f32x2 dw = sub2(up, dn);
-            const f32x2 o = fma2(up, neg_box[j % 3], x0[j]);
-            const f32x2 t = fma2(dw, neg_box[j % 3], pack2(rawt[2 * j], rawt[2 * j + 1]));
-            unpack2(sub2(o, t), d[2 * j], d[2 * j + 1]);
+        if constexpr (kSinc) {
+            float y0, y1, y2, y3, v0, v1, v2, v3;
+            unpack2(mul2(pack2(r2[0], r2[1]), q2), y0, y1);
+            unpack2(mul2(pack2(r2[2], r2[3]), q2), y2, y3);
+            sinc_of_square_x2(y0, y1, v0, v1);
+            sinc_of_square_x2(y2, y3, v2, v3);
+            if (MASKED) {
+                v0 = (vmask & 1u) ? v0 : 0.0f;
+                v1 = (vmask & 2u) ? v1 : 0.0f;
+                v2 = (vmask & 4u) ? v2 : 0.0f;
+                v3 = (vmask & 8u) ? v3 : 0.0f;
+            }
+            col[(kR2 ? 2 : 0) * kThreads] += (double)((v0 + v1) + (v2 + v3));
         }
-        unsigned int *s_hist_k = s_hist + k * p.n_bins;
-        uint32_t slow = 0u;
+        if constexpr (kHist) {
+            const uint32_t slow = hist_fast4<MASKED>(p, r2, vmask, table0 + 4u * (uint32_t)(k * p.n_bins), trash);
+            if (slow) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const float r2f = fmaf(d[3 * a + 2], d[3 * a + 2], fmaf(d[3 * a + 1], d[3 * a + 1], d[3 * a] * d[3 * a]));
-            const bool live = !MASKED || ((vmask >> a) & 1u);
-            const float t = (r2f * rsqrt_approx(r2f)) * p.inv_dx_f;               // NaN for r = 0 -> exact path
-            const float tb = t + 12582912.0f;
-            const float tr = tb - 12582912.0f;                                    // rint(t) for t < 2^22
-            const float dist = t - tr;
-            const float margin = fmaf(t, 1.6e-6f, 1.0e-6f);
-            const int bin = (__float_as_int(tb) - 0x4B400000) - (dist < 0.0f ? 1 : 0);
-            const bool fast = fabsf(dist) > margin;
-            if (live && fast && bin < p.n_bins) atomicAdd(&s_hist_k[bin], 1u);
-            slow |= (live && !fast) ? (1u << a) : 0u;
-        }
-        if (slow) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-                if (slow & (1u << a))
-                    exact_hist_from_raw(p.box_const[0], p.box_const[1], p.box_const[2], p.dx, p.inv_dx, p.n_bins, raw0[3 * a],
-                                        raw0[3 * a + 1], raw0[3 * a + 2], atom_image_bytes(w0, a), rawt[3 * a],
-                                        rawt[3 * a + 1], rawt[3 * a + 2], atom_image_bytes(wt, a), s_hist_k);
+                for (int a = 0; a < 4; ++a)
+                    if (slow & (1u << a))
+                        exact_count_raw(p.box_const[0], p.box_const[1] * (IMG == IMG_PACKED ? 4.0 : 1.0),
+                                        p.box_const[2] * (IMG == IMG_PACKED ? 16.0 : 1.0), p.dx, p.inv_dx, p.n_bins,
+                                        raw0[3 * a], raw0[3 * a + 1], raw0[3 * a + 2], image_count_int<IMG>(w0, 3 * a),
+                                        image_count_int<IMG>(w0, 3 * a + 1), image_count_int<IMG>(w0, 3 * a + 2),
+                                        rawt[3 * a], rawt[3 * a + 1], rawt[3 * a + 2], image_count_int<IMG>(wt, 3 * a),
+                                        image_count_int<IMG>(wt, 3 * a + 1), image_count_int<IMG>(wt, 3 * a + 2),
+                                        s_hist + k * p.n_bins);
+            }
         }
     }
 }
+
+// Does this instantiation have a float32-displacement variant?  (selected per launch by p.f32d)
+template <int IMG, int FLAGS, bool BOXC>
+struct HasF32d {
+    static constexpr bool value = (IMG == IMG_BYTES || IMG == IMG_PACKED) && BOXC &&
+                                  (FLAGS == MDB_SUM_SINC || FLAGS == MDB_HIST ||
+                                   FLAGS == (MDB_SUM_R2 | MDB_SUM_R4 | MDB_HIST));
+};
 
 // One tile of 1024 atoms: origin group into registers, then the lag rows of the chunk one by one.
 // The loop over lags is NOT unrolled (the body is 4 evaluations, ~1 KiB of code, and stays in the
 // instruction cache); per-lag accumulators live in shared memory, one private column per thread.
-template <bool IMG, int FLAGS, bool MASKED, bool BOXC>
+template <int IMG, int FLAGS, bool MASKED, bool BOXC>
 __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
                                              const unsigned char *stages, int stage_bytes, int tid, uint32_t vmask,
                                              int nl,
                                              const double (*s_box)[3], double *s_acc, unsigned int *s_hist,
-                                             const double *s_edges) {
+                                             const double *s_edges, uint32_t trash) {
     constexpr bool kR2 = (FLAGS & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
-    constexpr bool kHistF32 = kHist && !IMG;
+    constexpr bool kHistF32 = kHist && IMG == IMG_NONE;
     constexpr int NV = (kR2 ? 1 : 0) + (kR4 ? 1 : 0) + (kSinc ? 1 : 0);
-    if constexpr (FLAGS == (MDB_HIST | kVariantF32) && IMG && BOXC) {
-        process_tile_hist_f32<MASKED>(p, ring, full0, empty0, stages, stage_bytes, tid, vmask, nl, s_hist);
-        return;
-    }
-    if constexpr (FLAGS == MDB_SUM_SINC && IMG && BOXC) {
-        if (p.sinc_f32) {          // uniform over the launch
-            process_tile_sinc_f32<MASKED>(p, ring, full0, empty0, stages, stage_bytes, tid, vmask, nl, s_acc);
+    if constexpr (HasF32d<IMG, FLAGS, BOXC>::value) {
+        if (p.f32d) {          // uniform over the launch
+            process_tile_f32d<IMG, FLAGS, MASKED>(p, ring, full0, empty0, stages, stage_bytes, tid, vmask, nl, s_acc,
+                                                  s_hist, trash);
             return;
         }
     }
@@ -721,7 +726,8 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
         fetch_group<IMG, BOXC>(p, ring, full0, empty0, stages, stage_bytes, tid, s_box[k + 1], ut, rawt);
         double s2, s4;
         float ss;
-        eval_group<FLAGS, kHistF32, MASKED>(p, u0, raw0, ut, rawt, vmask, s2, s4, ss, s_hist + k * p.n_bins, s_edges);
+        eval_group<FLAGS, kHistF32, MASKED>(p, u0, raw0, ut, rawt, vmask, s2, s4, ss, s_hist + k * p.n_bins, s_edges,
+                                            trash);
         double *col = s_acc + (size_t)k * NV * kThreads + tid;
         int v = 0;
         if constexpr (kR2) { col[v * kThreads] += s2; ++v; }
@@ -730,14 +736,16 @@ __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint3
     }
 }
 
-template <bool IMG, int FLAGS, bool BOXC>
+template <int IMG, int FLAGS, bool BOXC>
 __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_kernel(const CorrDev p, const int n_stages) {
     constexpr bool kR2 = (FLAGS & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
     constexpr bool kHist = (FLAGS & MDB_HIST) != 0;
     constexpr int NV = (kR2 ? 1 : 0) + (kR4 ? 1 : 0) + (kSinc ? 1 : 0);
-    constexpr int kStageBytes = kCoordTileBytes + (IMG ? kImgTileBytes : 0);
+    constexpr int kImgBytes = img_tile_bytes(IMG);
+    constexpr int kStageBytes = kCoordTileBytes + kImgBytes;
+    constexpr int kImgElem = IMG == IMG_PACKED ? 4 : 1;          // bytes per element of an image row
 
     // dynamic shared memory: [n_stages stages][accumulators NV*kLagChunk*kThreads doubles][hist][edges]
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -752,6 +760,7 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
     double *s_acc = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * kStageBytes);
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_acc + (size_t)NV * kLagChunk * kThreads);
     double *s_edges = reinterpret_cast<double *>(s_hist + (size_t)kLagChunk * p.n_bins);
+    const uint32_t trash = trash_slot(p, s_edges, tid);
 
     load_rows<IMG>(p, w, tid, s_row, s_box);
     if (tid == kThreads) {
@@ -784,12 +793,16 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
             const long long row_floats = p.pitch;
             const uint32_t stages0 = smem_u32(smem_raw);
             for (int t = 0; t < n_tiles; ++t) {
-                const long long first_float = 12ll * (g_begin + (long long)t * kThreads);
+                const long long first_group = g_begin + (long long)t * kThreads;
+                const long long first_float = 12ll * first_group;
                 // copy what the shard's atoms need, rounded up to the 16-byte granule of the bulk copy (rows
                 // are readable that far: pitch % 4 == 0 floats, image pitch % 16 == 0 bytes)
                 const long long left = 3ll * p.n_atoms - first_float;          // components still to come
                 const uint32_t cbytes = (uint32_t)min((long long)kCoordTileBytes, ((left + 3) / 4) * 16);
-                const uint32_t ibytes = IMG ? (uint32_t)min((long long)kImgTileBytes, ((left + 15) / 16) * 16) : 0u;
+                uint32_t ibytes = 0u;
+                if (IMG == IMG_BYTES) ibytes = (uint32_t)min((long long)kImgBytes, ((left + 15) / 16) * 16);
+                if (IMG == IMG_PACKED) ibytes = (uint32_t)min((long long)kImgBytes, ((left + 47) / 48) * 16);
+                const long long img_first = IMG == IMG_PACKED ? first_group : first_float;   // elements into the row
                 for (int u = 0; u < n_units; ++u) {
                     const int row = s_row[u];
                     mbar_wait(empty0 + 8 * ring.stage, ring.phase ^ 1);
@@ -798,9 +811,11 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
                     mbar_expect_tx(bar, cbytes + ibytes);
                     bulk_g2s(dst, static_cast<const float *>(p.coords) + (long long)row * row_floats + first_float,
                              cbytes, bar);
-                    if (IMG)
-                        bulk_g2s(dst + kCoordTileBytes, p.images + (long long)row * p.img_pitch + first_float, ibytes,
-                                 bar);
+                    if (IMG != IMG_NONE)
+                        bulk_g2s(dst + kCoordTileBytes,
+                                 static_cast<const unsigned char *>(p.images) +
+                                     ((long long)row * p.img_pitch + img_first) * kImgElem,
+                                 ibytes, bar);
                     ring.advance();
                 }
             }
@@ -813,11 +828,11 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
         const int g_last = g_begin + t * kThreads + kThreads - 1;          // last group of this tile
         if (4 * g_last + 3 < p.n_atoms && p.select == nullptr) {
             process_tile<IMG, FLAGS, false, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, 0xfu, w.nl, s_box,
-                                                  s_acc, s_hist, s_edges);
+                                                  s_acc, s_hist, s_edges, trash);
         } else {
             const uint32_t vmask = group_mask(p, w.s, g_begin + t * kThreads + tid);
             process_tile<IMG, FLAGS, true, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, vmask, w.nl, s_box,
-                                                 s_acc, s_hist, s_edges);
+                                                 s_acc, s_hist, s_edges, trash);
         }
     }
 
@@ -832,301 +847,98 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
     }
     cta_epilogue<FLAGS>(p, w, tid, acc, s_red, s_hist, [] { compute_barrier(); });
 }
-
-__global__ void reduce_partials_kernel(const double *__restrict__ partial, double *__restrict__ sums,
-                                       long long n_out, int n_ablocks) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over S*L*3
-    if (i >= n_out) return;
-    const long long sl = i / 3;
-    const int comp = (int)(i - 3 * sl);
-    double v = 0.0;
-    for (int ab = 0; ab < n_ablocks; ++ab) v += partial[(sl * n_ablocks + ab) * 3 + comp];
-    sums[i] = v;
-}
+#endif  // MDB_CORR_PART != 0
 
 // =================================================================================================
-// host side
+// launchers of this translation unit
 // =================================================================================================
-struct Plan {
-    int n_groups, n_chunks, n_ablocks, groups_per_block;
-    bool bulk;           // cp.async.bulk path
-    bool vec;            // 128-bit loads in the fallback path
-    int stages;
-    size_t smem;
-};
-
-constexpr size_t kSmemBudgetPerCta = (MDB_BULK_CTAS_PER_SM == 3 ? 72 : 110) * 1024;   // CTAs per SM share 227 KiB
-
-// The kernel instantiation that serves a request: the four single-purpose kernels, van Hove +
-// non-Gaussian in one pass (BASELINE config 3), or the all-sums kernel (optionally with the histogram) for any other mix.
-int kernel_flags(int flags) {
-    constexpr int R2 = MDB_SUM_R2, R4 = MDB_SUM_R4, SC = MDB_SUM_SINC, H = MDB_HIST;
-    if (flags == R2 || flags == SC || flags == (R2 | R4) || flags == H || flags == (R2 | R4 | H) ||
-        flags == MDB_SUM_LEGENDRE)
-        return flags;
-    return (flags & H) ? (R2 | R4 | SC | H) : (R2 | R4 | SC);
-}
-
-int make_plan(const mdb_corr_args *a, Plan *plan) {
-    if (!a) return fail(MDB_ERR_ARGUMENT, "args is NULL");
-    if (a->n_atoms <= 0 || a->n_origins <= 0 || a->n_lags <= 0)
-        return fail(MDB_ERR_ARGUMENT, "n_atoms, n_origins and n_lags must be positive");
-    if (!(a->flags & (MDB_SUM_R2 | MDB_SUM_R4 | MDB_SUM_SINC | MDB_HIST | MDB_SUM_LEGENDRE)))
-        return fail(MDB_ERR_ARGUMENT, "flags selects nothing to compute");
-    if ((a->flags & MDB_SUM_LEGENDRE) && (a->flags != MDB_SUM_LEGENDRE || a->images || a->legendre_order < 0 ||
-                                          a->legendre_order > 32))
-        return fail(MDB_ERR_ARGUMENT, "MDB_SUM_LEGENDRE stands alone, on raw vector rows, with 0 <= order <= 32");
-    if (a->pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "pitch < 3*n_atoms");
-    plan->n_groups = (a->n_atoms + 3) / 4;
-    plan->n_chunks = (a->n_lags + kLagChunk - 1) / kLagChunk;
-
-    const size_t esz = a->coord_type == MDB_F32 ? 4 : 8;
-    plan->vec = (reinterpret_cast<uintptr_t>(a->coords) % 16 == 0) && ((a->pitch * esz) % 16 == 0);
-    if (a->images)
-        plan->vec = plan->vec && (reinterpret_cast<uintptr_t>(a->images) % 4 == 0) && (a->img_pitch % 4 == 0);
-    // bulk copies need 16-byte aligned sources and sizes: float32 rows with pitch % 4 == 0 and, for the
-    // image rows, pitch % 16 == 0 (engine.row_pitch pads rows to 128 bytes, so stores built by the
-    // package always qualify)
-    plan->bulk = a->coord_type == MDB_F32 && plan->vec;
-    if (a->images)
-        plan->bulk = plan->bulk && (reinterpret_cast<uintptr_t>(a->images) % 16 == 0) && (a->img_pitch % 16 == 0);
-
-    size_t hist_smem = 0;
-    if (a->flags & MDB_HIST) {
-        if (a->n_bins <= 0) return fail(MDB_ERR_ARGUMENT, "n_bins must be positive with MDB_HIST");
-        hist_smem = (size_t)kLagChunk * a->n_bins * sizeof(unsigned int);
-        if (a->bin_mode == MDB_BINS_EDGES) hist_smem += (size_t)(a->n_bins + 1) * sizeof(double);
-    }
-    const size_t stage_bytes = kCoordTileBytes + (a->images ? kImgTileBytes : 0);
-    const int kf = kernel_flags(a->flags);
-    const int nv_kernel = ((kf & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) ? 1 : 0) + ((kf & MDB_SUM_R4) ? 1 : 0) +
-                          ((kf & MDB_SUM_SINC) ? 1 : 0);
-    const size_t acc_smem = (size_t)nv_kernel * kLagChunk * kThreads * sizeof(double);
-    // ring depth: what fits next to the accumulators / histogram with two CTAs per SM, 3..8 stages
-    plan->stages = 0;
-    if (acc_smem + hist_smem + 3 * stage_bytes <= kSmemBudgetPerCta)
-        plan->stages = (int)((kSmemBudgetPerCta - acc_smem - hist_smem) / stage_bytes);
-    else if (acc_smem + hist_smem + 3 * stage_bytes <= 220 * 1024)
-        plan->stages = (int)((220 * 1024 - acc_smem - hist_smem) / stage_bytes);   // one CTA per SM
-    if (plan->stages > kMaxStages) plan->stages = kMaxStages;
-    if (const char *env = getenv("MDB_STAGES"))
-        if (atoi(env) >= 2 && atoi(env) <= plan->stages) plan->stages = atoi(env);              // tuning aid
-    if (plan->stages < 3) plan->bulk = false;                      // huge histograms: fall back
-    const size_t bulk_smem = plan->stages * stage_bytes + acc_smem + hist_smem;
-    plan->smem = plan->bulk ? bulk_smem : hist_smem;
-    if (plan->smem > 220 * 1024)
-        return fail(MDB_ERR_UNSUPPORTED, "n_bins=%d needs %zu bytes of shared memory (limit 220 KiB)", a->n_bins,
-                    plan->smem);
-
-    int sms = 148;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // Atom blocks: every CTA gets a whole number of 1024-atom tiles.  All CTAs cost about the same, so
-    // the launch runs in ceil(CTAs / resident slots) waves of (tiles per CTA + fixed overhead): pick
-    // the split with the smallest estimate (wave quantisation is the main loss for small launches).
-    const long long base = (long long)a->n_origins * plan->n_chunks;
-    const long long n_tiles = (plan->n_groups + kThreads - 1) / kThreads;
-    const long long slots = (long long)MDB_BULK_CTAS_PER_SM * sms;
-    long long best_tpb = n_tiles;
-    double best_cost = 1e300;
-    for (long long blocks = 1; blocks <= n_tiles && blocks <= 4096; ++blocks) {
-        const long long tpb = (n_tiles + blocks - 1) / blocks;
-        if ((n_tiles + tpb - 1) / tpb != blocks) continue;          // same split as a smaller block count
-        const long long ctas = base * blocks;
-        const long long waves = (ctas + slots - 1) / slots;
-        const double cost = (double)waves * ((double)tpb + 1.0);     // ~1 tile of prologue/epilogue per CTA
-        if (cost < best_cost * 0.999) {
-            best_cost = cost;
-            best_tpb = tpb;
-        }
-    }
-    if (const char *env = getenv("MDB_ABLOCKS"))                     // tuning aid
-        if (atoll(env) > 0) best_tpb = (n_tiles + atoll(env) - 1) / atoll(env);
-    const long long tiles_per_block = best_tpb;
-    plan->groups_per_block = (int)(tiles_per_block * kThreads);
-    plan->n_ablocks = (int)((n_tiles + tiles_per_block - 1) / tiles_per_block);
-    return MDB_OK;
-}
-
-struct Profile {
-    bool enabled = false;
-    bool valid = false;
-    cudaEvent_t start = nullptr, stop = nullptr;
-};
-Profile &profile() {
-    static thread_local Profile pr;
-    return pr;
-}
-
 template <typename Kernel, typename... Extra>
-int launch_kernel(Kernel kern, const CorrDev &p, const Plan &plan, int threads, cudaStream_t st, Extra... extra) {
+int launch_kernel(Kernel kern, const CorrDev &p, const Plan &plan, int threads, cudaStream_t st, LaunchTiming tm,
+                  Extra... extra) {
     const long long blocks = (long long)p.S * p.n_chunks * p.n_ablocks;
     if (blocks > 2147483647ll) return fail(MDB_ERR_UNSUPPORTED, "grid too large");
     if (plan.smem > 40 * 1024)
         MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    Profile &pr = profile();
-    if (pr.enabled) MDB_CUDA_CHECK(cudaEventRecord(pr.start, st));
+    if (tm.start) MDB_CUDA_CHECK(cudaEventRecord(tm.start, st));
     kern<<<(unsigned)blocks, threads, plan.smem, st>>>(p, extra...);
     MDB_CUDA_CHECK(cudaGetLastError());
-    if (pr.enabled) {
-        MDB_CUDA_CHECK(cudaEventRecord(pr.stop, st));
-        pr.valid = true;
-    }
+    if (tm.stop) MDB_CUDA_CHECK(cudaEventRecord(tm.stop, st));
     return MDB_OK;
 }
 
-template <typename CT, bool IMG, int FLAGS>
-int launch_flags(const CorrDev &p, const Plan &plan, cudaStream_t st) {
-    if constexpr (sizeof(CT) == 4) {
-        if (plan.bulk) {
-            if (IMG && p.box == nullptr)
-                return launch_kernel(corr_bulk_kernel<IMG, FLAGS, true>, p, plan, kBulkThreads, st, plan.stages);
-            return launch_kernel(corr_bulk_kernel<IMG, FLAGS, false>, p, plan, kBulkThreads, st, plan.stages);
-        }
-    }
-    if (plan.vec) return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, true>, p, plan, kThreads, st);
-    return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, false>, p, plan, kThreads, st);
+#if MDB_CORR_PART == 0
+template <typename CT, int IMG, int FLAGS>
+int launch_ldg_flags(const CorrDev &p, const Plan &plan, cudaStream_t st, LaunchTiming tm) {
+    if (plan.vec) return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, true>, p, plan, kThreads, st, tm);
+    return launch_kernel(corr_ldg_kernel<CT, IMG, FLAGS, false>, p, plan, kThreads, st, tm);
 }
 
-template <typename CT, bool IMG>
-int launch_typed(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st) {
+template <typename CT, int IMG>
+int launch_ldg_typed(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st, LaunchTiming tm) {
     constexpr int R2 = MDB_SUM_R2, R4 = MDB_SUM_R4, SC = MDB_SUM_SINC, H = MDB_HIST;
     switch (kernel_flags(flags)) {
-        case R2: return launch_flags<CT, IMG, R2>(p, plan, st);
-        case SC: return launch_flags<CT, IMG, SC>(p, plan, st);
-        case R2 | R4: return launch_flags<CT, IMG, R2 | R4>(p, plan, st);
-        case H:
-            if constexpr (sizeof(CT) == 4 && IMG) {
-                if (p.hist_f32 && plan.bulk && p.box == nullptr)      // candidate instantiation, off by default
-                    return launch_kernel(corr_bulk_kernel<true, H | kVariantF32, true>, p, plan, kBulkThreads, st,
-                                         plan.stages);
-            }
-            return launch_flags<CT, IMG, H>(p, plan, st);
-        case R2 | R4 | H: return launch_flags<CT, IMG, R2 | R4 | H>(p, plan, st);
+        case R2: return launch_ldg_flags<CT, IMG, R2>(p, plan, st, tm);
+        case SC: return launch_ldg_flags<CT, IMG, SC>(p, plan, st, tm);
+        case R2 | R4: return launch_ldg_flags<CT, IMG, R2 | R4>(p, plan, st, tm);
+        case H: return launch_ldg_flags<CT, IMG, H>(p, plan, st, tm);
+        case R2 | R4 | H: return launch_ldg_flags<CT, IMG, R2 | R4 | H>(p, plan, st, tm);
         case MDB_SUM_LEGENDRE:
-            if constexpr (!IMG) return launch_flags<CT, false, MDB_SUM_LEGENDRE>(p, plan, st);
+            if constexpr (IMG == IMG_NONE) return launch_ldg_flags<CT, IMG_NONE, MDB_SUM_LEGENDRE>(p, plan, st, tm);
             return fail(MDB_ERR_ARGUMENT, "MDB_SUM_LEGENDRE needs raw rows");
-        case R2 | R4 | SC | H: return launch_flags<CT, IMG, R2 | R4 | SC | H>(p, plan, st);
-        default: return launch_flags<CT, IMG, R2 | R4 | SC>(p, plan, st);
+        case R2 | R4 | SC | H: return launch_ldg_flags<CT, IMG, R2 | R4 | SC | H>(p, plan, st, tm);
+        default: return launch_ldg_flags<CT, IMG, R2 | R4 | SC>(p, plan, st, tm);
     }
 }
+#else
+template <int IMG, int FLAGS>
+int launch_bulk_flags(const CorrDev &p, const Plan &plan, cudaStream_t st, LaunchTiming tm) {
+    if (IMG != IMG_NONE && p.box == nullptr)
+        return launch_kernel(corr_bulk_kernel<IMG, FLAGS, IMG != IMG_NONE>, p, plan, kBulkThreads, st, tm, plan.stages);
+    return launch_kernel(corr_bulk_kernel<IMG, FLAGS, false>, p, plan, kBulkThreads, st, tm, plan.stages);
+}
+
+template <int IMG>
+int launch_bulk(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st, LaunchTiming tm) {
+    constexpr int R2 = MDB_SUM_R2, R4 = MDB_SUM_R4, SC = MDB_SUM_SINC, H = MDB_HIST;
+    switch (kernel_flags(flags)) {
+        case R2: return launch_bulk_flags<IMG, R2>(p, plan, st, tm);
+        case SC: return launch_bulk_flags<IMG, SC>(p, plan, st, tm);
+        case R2 | R4: return launch_bulk_flags<IMG, R2 | R4>(p, plan, st, tm);
+        case H: return launch_bulk_flags<IMG, H>(p, plan, st, tm);
+        case R2 | R4 | H: return launch_bulk_flags<IMG, R2 | R4 | H>(p, plan, st, tm);
+        case MDB_SUM_LEGENDRE:
+            if constexpr (IMG == IMG_NONE) return launch_bulk_flags<IMG_NONE, MDB_SUM_LEGENDRE>(p, plan, st, tm);
+            return fail(MDB_ERR_ARGUMENT, "MDB_SUM_LEGENDRE needs raw rows");
+        case R2 | R4 | SC | H: return launch_bulk_flags<IMG, R2 | R4 | SC | H>(p, plan, st, tm);
+        default: return launch_bulk_flags<IMG, R2 | R4 | SC>(p, plan, st, tm);
+    }
+}
+#endif
 
 }  // namespace
+
+#if MDB_CORR_PART == 0
+int corr_launch_ldg(const CorrDev &p, const Plan &plan, int flags, int coord_type, cudaStream_t st, LaunchTiming tm) {
+    if (coord_type == MDB_F64) return launch_ldg_typed<double, IMG_NONE>(p, plan, flags, st, tm);
+    switch (plan.img) {
+        case IMG_NONE: return launch_ldg_typed<float, IMG_NONE>(p, plan, flags, st, tm);
+        case IMG_BYTES: return launch_ldg_typed<float, IMG_BYTES>(p, plan, flags, st, tm);
+        case IMG_I16: return launch_ldg_typed<float, IMG_I16>(p, plan, flags, st, tm);
+        default: return fail(MDB_ERR_UNSUPPORTED, "the direct-load kernel reads byte or int16 image counts");
+    }
+}
+#elif MDB_CORR_PART == 1
+int corr_launch_bulk_none(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st, LaunchTiming tm) {
+    return launch_bulk<IMG_NONE>(p, plan, flags, st, tm);
+}
+#elif MDB_CORR_PART == 2
+int corr_launch_bulk_bytes(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st, LaunchTiming tm) {
+    return launch_bulk<IMG_BYTES>(p, plan, flags, st, tm);
+}
+#elif MDB_CORR_PART == 3
+int corr_launch_bulk_packed(const CorrDev &p, const Plan &plan, int flags, cudaStream_t st, LaunchTiming tm) {
+    return launch_bulk<IMG_PACKED>(p, plan, flags, st, tm);
+}
+#endif
+
 }  // namespace mdb
-
-using namespace mdb;
-
-extern "C" int mdb_corr_workspace_bytes(const mdb_corr_args *a, size_t *bytes) {
-    Plan plan;
-    if (int rc = make_plan(a, &plan)) return rc;
-    if (!bytes) return fail(MDB_ERR_ARGUMENT, "bytes is NULL");
-    *bytes = (size_t)a->n_origins * a->n_lags * plan.n_ablocks * 3 * sizeof(double);
-    return MDB_OK;
-}
-
-extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
-    Plan plan;
-    if (int rc = make_plan(a, &plan)) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!a->coords || !a->rows || !a->sums) return fail(MDB_ERR_ARGUMENT, "coords, rows and sums are required");
-    if (a->coord_type != MDB_F32 && a->coord_type != MDB_F64) return fail(MDB_ERR_ARGUMENT, "bad coord_type");
-    if (a->images && a->coord_type != MDB_F32)
-        return fail(MDB_ERR_ARGUMENT, "image counts go with float32 (wrapped) coordinates");
-    if (a->images && !a->box && !(a->box_const[0] > 0.0 && a->box_const[1] > 0.0 && a->box_const[2] > 0.0))
-        return fail(MDB_ERR_ARGUMENT, "images need box (per row) or a positive box_const");
-    if (a->images && a->img_pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "img_pitch < 3*n_atoms");
-    if (a->select && (a->sel_pitch < a->n_atoms || a->sel_pitch % 4 != 0 ||
-                      reinterpret_cast<uintptr_t>(a->select) % 4 != 0))
-        return fail(MDB_ERR_ARGUMENT, "select needs sel_pitch >= n_atoms, a multiple of 4, and a 4-byte aligned base");
-    const bool hist = (a->flags & MDB_HIST) != 0;
-    if (hist) {
-        if (!a->hist) return fail(MDB_ERR_ARGUMENT, "hist is required with MDB_HIST");
-        if (a->bin_mode == MDB_BINS_UNIFORM && !(a->dx > 0.0)) return fail(MDB_ERR_ARGUMENT, "dx must be > 0");
-        if (a->bin_mode == MDB_BINS_EDGES && !a->edges) return fail(MDB_ERR_ARGUMENT, "edges is required");
-        if (a->bin_mode != MDB_BINS_UNIFORM && a->bin_mode != MDB_BINS_EDGES)
-            return fail(MDB_ERR_ARGUMENT, "bad bin_mode");
-    }
-    const size_t need = (size_t)a->n_origins * a->n_lags * plan.n_ablocks * 3 * sizeof(double);
-    if (!a->workspace || a->workspace_bytes < need)
-        return fail(MDB_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, a->workspace_bytes);
-
-    CorrDev p;
-    p.coords = a->coords;
-    p.pitch = a->pitch;
-    p.images = a->images;
-    p.img_pitch = a->img_pitch;
-    p.box = a->box;
-    for (int d = 0; d < 3; ++d) p.box_const[d] = a->box_const[d];
-    p.n_atoms = a->n_atoms;
-    p.n_groups = plan.n_groups;
-    p.groups_per_block = plan.groups_per_block;
-    p.S = a->n_origins;
-    p.L = a->n_lags;
-    p.rows = a->rows;
-    p.select = a->select;
-    p.sel_pitch = a->sel_pitch;
-    p.n_chunks = plan.n_chunks;
-    p.n_ablocks = plan.n_ablocks;
-    p.q2 = a->q * a->q;
-    // ISF alone with one float32-representable box (what trajectory formats store): float32 displacements
-    p.sinc_f32 = a->flags == MDB_SUM_SINC && a->images && !a->box && getenv("MDB_SINC_F64") == nullptr;
-    for (int d = 0; d < 3; ++d) p.sinc_f32 = p.sinc_f32 && (double)(float)a->box_const[d] == a->box_const[d];
-    p.hist_f32 = a->flags == MDB_HIST && a->bin_mode == MDB_BINS_UNIFORM && a->images && !a->box &&
-                 getenv("MDB_HIST_F32") != nullptr;
-    for (int d = 0; d < 3; ++d) p.hist_f32 = p.hist_f32 && (double)(float)a->box_const[d] == a->box_const[d];
-    p.q2f = (float)p.q2;
-    {
-        const float nb[3] = {-(float)a->box_const[0], -(float)a->box_const[1], -(float)a->box_const[2]};
-        const int dims[6] = {0, 1, 2, 0, 1, 2};
-        for (int i = 0; i < 6; ++i) p.neg_box2[i] = nb[dims[i]];
-    }
-    p.leg_order = a->legendre_order;
-    p.n_bins = hist ? a->n_bins : 0;
-    p.bin_mode = a->bin_mode;
-    p.dx = a->dx;
-    p.inv_dx = hist && a->dx > 0 ? 1.0 / a->dx : 0.0;
-    p.inv_dx_f = (float)p.inv_dx;
-    p.edges = a->edges;
-    p.partial = static_cast<double *>(a->workspace);
-    p.hist = a->hist;
-
-    int launches = 0;
-    if (hist) {
-        MDB_CUDA_CHECK(cudaMemsetAsync(a->hist, 0,
-                                       (size_t)a->n_origins * a->n_lags * a->n_bins * sizeof(unsigned long long), st));
-    }
-    int rc;
-    if (a->coord_type == MDB_F64) rc = launch_typed<double, false>(p, plan, a->flags, st);
-    else if (a->images) rc = launch_typed<float, true>(p, plan, a->flags, st);
-    else rc = launch_typed<float, false>(p, plan, a->flags, st);
-    if (rc) return rc;
-    ++launches;
-    const long long n_out = (long long)a->n_origins * a->n_lags * 3;
-    reduce_partials_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(p.partial, a->sums, n_out, plan.n_ablocks);
-    MDB_CUDA_CHECK(cudaGetLastError());
-    ++launches;
-    last_launch_count() = launches;
-    return MDB_OK;
-}
-
-extern "C" int mdb_corr_last_launches(void) { return last_launch_count(); }
-
-extern "C" int mdb_corr_profile(int enable) {
-    Profile &pr = profile();
-    if (enable && !pr.start) {
-        MDB_CUDA_CHECK(cudaEventCreate(&pr.start));
-        MDB_CUDA_CHECK(cudaEventCreate(&pr.stop));
-    }
-    pr.enabled = enable != 0;
-    pr.valid = false;
-    return MDB_OK;
-}
-
-extern "C" int mdb_corr_last_kernel_ms(float *ms) {
-    Profile &pr = profile();
-    if (!ms) return fail(MDB_ERR_ARGUMENT, "ms is NULL");
-    if (!pr.valid) return fail(MDB_ERR_ARGUMENT, "no profiled launch (call mdb_corr_profile(1) first)");
-    MDB_CUDA_CHECK(cudaEventSynchronize(pr.stop));
-    MDB_CUDA_CHECK(cudaEventElapsedTime(ms, pr.start, pr.stop));
-    return MDB_OK;
-}

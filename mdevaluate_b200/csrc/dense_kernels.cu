@@ -419,8 +419,9 @@ extern "C" int mdb_dense_corr(const mdb_dense_args *a, void *stream) {
     };
     int rc;
     const bool img = a->images != nullptr;
-    const char *stage = getenv("MDB_DENSE_STAGE");
-    const bool warp_stage = stage && strcmp(stage, "warp") == 0 && kDenseThreads == 256 && !(img && a->box);   // candidate, off by default; constant box only
+    // warp-per-row staging (measured: MSD 7.0e11 -> 8.0e11, ISF 5.2e11 -> 6.4e11 evals/s, profiles/r2_call1.log) is
+    // the default where it applies (constant box); tuning.dense_stage_cta = 1 selects the CTA-wide staging loop
+    const bool warp_stage = !a->tuning.dense_stage_cta && kDenseThreads == 256 && !(img && a->box);
     auto pick = [&](auto flags_c) -> int {
         constexpr int F = decltype(flags_c)::value;
         if (warp_stage) return img ? launch(dense_corr_kernel<true, F, true>) : launch(dense_corr_kernel<false, F, true>);

@@ -10,8 +10,6 @@
 // in the dtype NumPy uses: float32 subtract, IEEE float32 divide (float64 divide when the box is
 // float64), round-half-even.  A division-free test decides the common case: |curr - prev| <
 // 0.49 * box implies |quotient| < 0.5 after rounding, i.e. a jump of 0.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace mdb {
@@ -38,6 +36,8 @@ struct NojumpDev {
     float *coords_out;
     long long pitch_out;
     int *overflow;
+    int16_t *images16;   // plain int16 counts (the fallback beyond +-127), general kernel only
+    long long img16_pitch;
 };
 
 template <bool BOXF32>
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) nojump_scan_kernel(const NojumpDev p
             for (int j = 0; j < 4; ++j) {
                 if (j >= nv) jmp[j] = 0;
                 cum[j] += jmp[j];
-                overflow |= (cum[j] > 127 || cum[j] < -128);
+                overflow |= (p.images != nullptr) && (cum[j] > 127 || cum[j] < -128);
             }
             packed = pack4(cum[0] + MDB_IMAGE_BIAS, cum[1] + MDB_IMAGE_BIAS, cum[2] + MDB_IMAGE_BIAS,
                            cum[3] + MDB_IMAGE_BIAS);
@@ -158,6 +158,12 @@ __global__ void __launch_bounds__(kThreads) nojump_scan_kernel(const NojumpDev p
             if (VEC) *reinterpret_cast<uint32_t *>(dst) = packed;
             else
                 for (int j = 0; j < nv; ++j) dst[j] = (uint8_t)(cum[j] + MDB_IMAGE_BIAS);
+        }
+        if (p.images16) {
+            int16_t *dst = p.images16 + (long long)orow * p.img16_pitch + e0;
+            for (int j = 0; j < nv; ++j) dst[j] = (int16_t)cum[j];
+            overflow |= (cum[0] > 32767 || cum[0] < -32768 || cum[1] > 32767 || cum[1] < -32768 || cum[2] > 32767 ||
+                         cum[2] < -32768 || cum[3] > 32767 || cum[3] < -32768);
         }
         if (p.jumps) {
             int8_t *dst = p.jumps + (long long)orow * p.img_pitch + e0;
@@ -349,6 +355,8 @@ struct JumpMatDev {
     long long img_pitch;
     int *overflow;
     int vec;
+    int16_t *images16;
+    long long img16_pitch;
 };
 
 __global__ void __launch_bounds__(kThreads) nojump_images_from_jumps_kernel(const JumpMatDev p) {
@@ -368,7 +376,14 @@ __global__ void __launch_bounds__(kThreads) nojump_images_from_jumps_kernel(cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             while (pos[j] < end[j] && p.frames[pos[j]] <= frame) cum[j] += (int)p.jumps[pos[j]++];
-            overflow |= (cum[j] < -128) | (cum[j] > 127);
+            overflow |= p.images16 ? ((cum[j] < -32768) | (cum[j] > 32767)) : ((cum[j] < -128) | (cum[j] > 127));
+        }
+        if (p.images16) {
+            int16_t *row16 = p.images16 + (long long)r * p.img16_pitch + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < p.n_vals) row16[j] = (int16_t)cum[j];
+            continue;
         }
         uint8_t *row = p.images + (long long)r * p.img_pitch + c0;
         if (p.vec) {
@@ -391,6 +406,52 @@ __global__ void nojump_apply_kernel(const float *__restrict__ x, const uint8_t *
     const double b = d == 0 ? b0 : (d == 1 ? b1 : b2);
     // pbc.py:235-247: frame - counts * box, float64 (the product is exact, so fma == mul then sub)
     out[i] = fma(-(double)((int)n[i] - MDB_IMAGE_BIAS), b, (double)x[i]);
+}
+
+
+// MDB_IMAGE_BYTES rows -> MDB_IMAGE_PACKED rows: one thread per group of 4 atoms reads its 12 excess-128 bytes
+// (three words) and writes one word, byte a = atom a, bits 2d = n + 1.  Reads 3 B, writes 1 B per atom and frame.
+__global__ void __launch_bounds__(256) images_pack_kernel(const uint8_t *__restrict__ images, long long img_pitch,
+                                                           long long n_rows, int n_atoms, int n_groups,
+                                                           uint32_t *__restrict__ packed, long long packed_pitch,
+                                                           int *__restrict__ max_abs, int vec) {
+    const long long row = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int worst = 0;
+    if (g < n_groups && row < n_rows) {
+        const uint8_t *src = images + row * img_pitch + 12ll * g;
+        const int nc = min(12, 3 * n_atoms - 12 * g);
+        uint32_t w[3] = {0x80808080u, 0x80808080u, 0x80808080u};
+        if (vec && nc == 12) {
+            const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
+            w[0] = __ldg(s4); w[1] = __ldg(s4 + 1); w[2] = __ldg(s4 + 2);
+        } else {
+            for (int c = 0; c < nc; ++c) w[c >> 2] = (w[c >> 2] & ~(0xffu << (8 * (c & 3)))) | ((uint32_t)src[c] << (8 * (c & 3)));
+        }
+        uint32_t out = 0u;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            const int n = (int)((w[c >> 2] >> (8 * (c & 3))) & 0xffu) - MDB_IMAGE_BIAS;
+            worst = max(worst, abs(n));
+            out |= (uint32_t)(min(max(n, -1), 1) + 1) << (8 * (c / 3) + 2 * (c % 3));
+        }
+        packed[row * packed_pitch + g] = out;
+    }
+    worst = __reduce_max_sync(0xffffffffu, worst);
+    if ((threadIdx.x & 31) == 0 && worst > 1) atomicMax(max_abs, worst);
+}
+
+__global__ void nojump_apply_format_kernel(const float *__restrict__ x, const void *__restrict__ images, int format,
+                                           double b0, double b1, double b2, int n_vals, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vals) return;
+    const int d = i % 3;
+    const double b = d == 0 ? b0 : (d == 1 ? b1 : b2);
+    int n;
+    if (format == MDB_IMAGE_BYTES) n = (int)static_cast<const uint8_t *>(images)[i] - MDB_IMAGE_BIAS;
+    else if (format == MDB_IMAGE_I16) n = (int)static_cast<const int16_t *>(images)[i];
+    else n = (int)((static_cast<const uint32_t *>(images)[i / 12] >> (8 * ((i % 12) / 3) + 2 * d)) & 3u) - 1;
+    out[i] = fma(-(double)n, b, (double)x[i]);     // pbc.py:235-247
 }
 
 }  // namespace
@@ -431,6 +492,9 @@ extern "C" int mdb_nojump_scan(const mdb_nojump_args *a, void *stream) {
     p.coords_out = a->coords_out;
     p.pitch_out = a->pitch_out;
     p.overflow = a->overflow;
+    p.images16 = a->images16;
+    p.img16_pitch = a->img16_pitch;
+    if (a->images16 && a->img16_pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "img16_pitch < 3*n_atoms");
 
     bool vec = (reinterpret_cast<uintptr_t>(a->coords) % 16 == 0) && (a->pitch % 4 == 0);
     if (a->images) vec = vec && (reinterpret_cast<uintptr_t>(a->images) % 4 == 0) && (a->img_pitch % 4 == 0);
@@ -439,9 +503,9 @@ extern "C" int mdb_nojump_scan(const mdb_nojump_args *a, void *stream) {
 
     const int n_threads = (p.n_vals + 3) / 4;
     const unsigned blocks = (unsigned)((n_threads + kThreads - 1) / kThreads);
-    const bool plain = vec && a->images && !a->out_row && !a->jumps && !a->coords_out;
+    const bool plain = vec && a->images && !a->out_row && !a->jumps && !a->coords_out && !a->images16;
     // the bulk-copy variant needs enough frames to fill its ring and is the default for the dense case
-    const bool bulk = plain && a->n_frames >= 64 && getenv("MDB_SCAN_LDG") == nullptr;
+    const bool bulk = plain && a->n_frames >= 64 && !a->tuning.scan_direct;
     if (bulk) {
         const unsigned bblocks = (unsigned)((p.n_vals + kThreads * 4 - 1) / (kThreads * 4));
         const size_t smem = (size_t)kScanStages * kRowsPerStage * kSlabBytes;
@@ -484,12 +548,15 @@ extern "C" int mdb_nojump_apply(const float *coords_row, const uint8_t *images_r
 extern "C" int mdb_nojump_images_from_jumps(const mdb_jumpmat_args *a, void *stream) {
     if (!a) return fail(MDB_ERR_ARGUMENT, "args is NULL");
     if (a->n_atoms <= 0 || a->n_keep < 0) return fail(MDB_ERR_ARGUMENT, "bad n_atoms / n_keep");
-    if (!a->indptr || !a->images) return fail(MDB_ERR_ARGUMENT, "indptr and images are required");
+    if (!a->indptr || (!a->images && !a->images16)) return fail(MDB_ERR_ARGUMENT, "indptr and images (or images16) are required");
     if (a->nnz < 0 || (a->nnz > 0 && (!a->frames || !a->jumps)))
         return fail(MDB_ERR_ARGUMENT, "frames and jumps are required when nnz > 0");
-    if (a->img_pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "img_pitch < 3*n_atoms");
+    if (a->images && a->img_pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "img_pitch < 3*n_atoms");
+    if (a->images16 && a->img16_pitch < 3ll * a->n_atoms) return fail(MDB_ERR_ARGUMENT, "img16_pitch < 3*n_atoms");
     if (a->n_keep == 0) return MDB_OK;
     JumpMatDev p;
+    p.images16 = a->images ? nullptr : a->images16;
+    p.img16_pitch = a->img16_pitch;
     p.indptr = reinterpret_cast<const long long *>(a->indptr);
     p.frames = a->frames;
     p.jumps = a->jumps;
@@ -505,6 +572,38 @@ extern "C" int mdb_nojump_images_from_jumps(const mdb_jumpmat_args *a, void *str
     const int n_threads = (p.n_vals + 3) / 4;
     nojump_images_from_jumps_kernel<<<(n_threads + kThreads - 1) / kThreads, kThreads, 0,
                                       static_cast<cudaStream_t>(stream)>>>(p);
+    MDB_CUDA_CHECK(cudaGetLastError());
+    return MDB_OK;
+}
+
+extern "C" int mdb_images_pack(const uint8_t *images, int64_t img_pitch, int64_t n_rows, int32_t n_atoms,
+                               uint32_t *packed, int64_t packed_pitch, int32_t *max_abs, void *stream) {
+    if (!images || !packed || !max_abs) return fail(MDB_ERR_ARGUMENT, "mdb_images_pack: NULL pointer");
+    if (n_atoms <= 0 || n_rows < 0) return fail(MDB_ERR_ARGUMENT, "mdb_images_pack: bad n_atoms / n_rows");
+    const int n_groups = (n_atoms + 3) / 4;
+    if (img_pitch < 3ll * n_atoms || packed_pitch < n_groups)
+        return fail(MDB_ERR_ARGUMENT, "mdb_images_pack: pitch too small");
+    if (n_rows == 0) return MDB_OK;
+    const int vec = (reinterpret_cast<uintptr_t>(images) % 4 == 0) && (img_pitch % 4 == 0);
+    for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {          // gridDim.y limit
+        const int64_t nr = n_rows - r0 < 65535 ? n_rows - r0 : 65535;
+        const dim3 grid((unsigned)((n_groups + 255) / 256), (unsigned)nr);
+        images_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            images + r0 * img_pitch, img_pitch, nr, n_atoms, n_groups, packed + r0 * packed_pitch, packed_pitch, max_abs, vec);
+        MDB_CUDA_CHECK(cudaGetLastError());
+    }
+    return MDB_OK;
+}
+
+extern "C" int mdb_nojump_apply_format(const float *coords_row, const void *images_row, int32_t image_format,
+                                       const double box[3], int32_t n_atoms, double *out, void *stream) {
+    if (!coords_row || !images_row || !box || !out || n_atoms <= 0)
+        return fail(MDB_ERR_ARGUMENT, "mdb_nojump_apply_format: NULL pointer or n_atoms <= 0");
+    if (image_format != MDB_IMAGE_BYTES && image_format != MDB_IMAGE_PACKED && image_format != MDB_IMAGE_I16)
+        return fail(MDB_ERR_ARGUMENT, "mdb_nojump_apply_format: unknown image format %d", image_format);
+    const int n_vals = 3 * n_atoms;
+    nojump_apply_format_kernel<<<(n_vals + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        coords_row, images_row, image_format, box[0], box[1], box[2], n_vals, out);
     MDB_CUDA_CHECK(cudaGetLastError());
     return MDB_OK;
 }

@@ -224,10 +224,12 @@ def _nojump_checksum(reader):
 
 def save_nojump_matrixes(reader, matrixes=None):
     """Write the jump matrices in the reference's format (reader.py:205-213): ``checksum``, ``shape`` and
-    ``data_d / indices_d / indptr_d`` of the three CSR matrices, uncompressed npz."""
+    ``data_d / indices_d / indptr_d`` of the three CSR matrices, uncompressed npz -- plus ``checksum_str``, the
+    checksum in decimal, which is what this package reads back (no pickle)."""
     if matrixes is None:
         matrixes = reader.nojump_matrixes
-    data = {'checksum': _nojump_checksum(reader)}
+    csum = _nojump_checksum(reader)
+    data = {'checksum': csum, 'checksum_str': np.array(str(int(csum)))}
     for d, mat in enumerate(matrixes):
         data['shape'] = mat.shape
         for attr in CSR_ATTRS:
@@ -235,30 +237,53 @@ def save_nojump_matrixes(reader, matrixes=None):
     np.savez(nojump_filename(reader), **data)
 
 
-def read_nojump_file(filename):
+class PickledChecksum(Exception):
+    """The cache file carries its checksum only as a pickled object (a file the reference wrote)."""
+
+
+def read_nojump_file(filename, trust_pickle=False):
     """``(checksum, (Jx, Jy, Jz))`` of a ``.nojump.npz`` file written by this package or by the reference.
-    The checksum is a 160-bit Python integer, which NumPy stores as a pickled object entry: the file is
-    opened with ``allow_pickle`` -- load only cache files you (or the reference) wrote."""
+
+    The checksum is a 160-bit Python integer.  This package stores it in decimal (``checksum_str``) and reads the
+    file with ``allow_pickle=False``.  The reference stores it as a pickled object entry only: unpickling runs code
+    from the file, so that happens solely with ``trust_pickle=True`` -- for cache files you (or the reference on
+    your behalf) wrote.  Without it such a file raises :class:`PickledChecksum`; the matrices themselves are plain
+    arrays and never need pickle."""
     from scipy import sparse
-    with np.load(filename, allow_pickle=True) as data:
-        stored = data['checksum'][()] if 'checksum' in data else None
+    with np.load(filename, allow_pickle=False) as data:
         shape = tuple(int(n) for n in data['shape'])
         mats = tuple(
             sparse.csr_matrix(tuple(data['{}_{}'.format(attr, d)] for attr in CSR_ATTRS), shape=shape)
             for d in range(3)
         )
-    return stored, mats
+        if 'checksum_str' in data:
+            return int(str(data['checksum_str'][()])), mats
+        if 'checksum' not in data:
+            return None, mats
+    if not trust_pickle:
+        raise PickledChecksum(filename)
+    with np.load(filename, allow_pickle=True) as data:
+        return data['checksum'][()], mats
 
 
-def load_nojump_matrixes(reader, filename=None, verify=True):
+def load_nojump_matrixes(reader, filename=None, verify=True, trust_pickle=False):
     """Attach the stored jump matrices to ``reader`` if the file belongs to it (reader.py:216-241): a
     file with another checksum is ignored, an unreadable one is removed.  ``filename`` reads a specific
     file; ``verify=False`` accepts a foreign checksum (a cache the reference wrote through its own file
-    reader hashes that reader's frame index, which only the reference can recompute).  Returns True when
-    the matrices were attached."""
+    reader hashes that reader's frame index, which only the reference can recompute) and does not look at the
+    stored checksum at all.  ``trust_pickle=True`` allows unpickling the checksum entry of a file the reference
+    wrote (see :func:`read_nojump_file`); the automatic pick-up in ``MemoryReader.__init__`` never does.  Returns
+    True when the matrices were attached."""
     zipname = nojump_filename(reader) if filename is None else filename
     try:
-        stored, mats = read_nojump_file(zipname)
+        try:
+            stored, mats = read_nojump_file(zipname, trust_pickle=trust_pickle)
+        except PickledChecksum:
+            if verify:
+                logger.info('Ignoring %s: its checksum is a pickled entry (pass trust_pickle=True to '
+                            'load_nojump_matrixes for cache files the reference wrote)', zipname)
+                return False
+            stored, mats = read_nojump_file_matrices(zipname)
     except (AttributeError, BadZipFile, OSError, KeyError, ValueError, EOFError, pickle.UnpicklingError):
         logger.info('Removing zip-File: %s', zipname)
         if filename is None:
@@ -270,6 +295,18 @@ def load_nojump_matrixes(reader, filename=None, verify=True):
     reader.nojump_matrixes = mats
     logger.info('Loaded Nojump Matrixes: {}'.format(zipname))
     return True
+
+
+def read_nojump_file_matrices(filename):
+    """``(None, matrices)``: the three CSR matrices of a cache file without touching its checksum entry."""
+    from scipy import sparse
+    with np.load(filename, allow_pickle=False) as data:
+        shape = tuple(int(n) for n in data['shape'])
+        mats = tuple(
+            sparse.csr_matrix(tuple(data['{}_{}'.format(attr, d)] for attr in CSR_ATTRS), shape=shape)
+            for d in range(3)
+        )
+    return None, mats
 
 
 def correct_nojump_matrixes_for_whole(trajectory):

@@ -37,15 +37,8 @@ timeit('frame_ids', lambda: (starts[:, None] + idx[None, :]).max())
 timeit('_times', lambda: c._times(coords, idx))
 timeit('_provider', lambda: c._provider(coords, ids))
 store, rows, n_atoms, f32, comm = c._provider(coords, ids)
-def launch():
-    s, h = engine.correlate_device(store, rows, spec.corr)
-    return s
-timeit('launch+sync', lambda: launch().cpu())
-def launch_nosync():
-    engine.correlate_device(store, rows, spec.corr)
-t0 = time.perf_counter()
-for _ in range(n): launch_nosync()
-t1 = time.perf_counter(); torch.cuda.synchronize()
-print('launch (async)  %.1f us' % ((t1 - t0) / n * 1e6))
-sums = launch().cpu().numpy()
+plan = c._plan_for(store, rows, spec.corr, None, None)
+timeit('plan lookup', lambda: c._plan_for(store, rows, spec.corr, None, None))
+timeit('plan.run', lambda: plan.run())
+sums = np.array(plan.run()[0])
 timeit('finalize', lambda: spec.finalize(sums, None, n_atoms, False))

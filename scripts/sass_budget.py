@@ -69,7 +69,7 @@ def loops(body):
 
 
 def main():
-    pattern = re.compile(sys.argv[1] if len(sys.argv) > 1 else r'corr_bulk_kernel<true, \(int\)(1|3|4|8|11), true>|dense_corr_kernel<true'
+    pattern = re.compile(sys.argv[1] if len(sys.argv) > 1 else r'corr_bulk_kernel<2, (1|3|4|8|11), true>|dense_corr_kernel<true'
                                                                 r'|nojump_scan_bulk_kernel<true>')
     all_kernels = list(kernels())
     names = demangle([n for n, _ in all_kernels])

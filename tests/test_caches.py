@@ -123,7 +123,7 @@ class PlainReader:
 
 def test_reference_nojump_file_is_read(golden):
     g = golden('walk_small')
-    stored, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'))
+    stored, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'), trust_pickle=True)
     assert stored == cs.checksum(rd.NOJUMP_MAGIC, cs.checksum(Named(987654321)))
     dense = np.stack([m.toarray() for m in mats], axis=-1)
     assert dense.dtype == np.int8
@@ -133,13 +133,15 @@ def test_reference_nojump_file_is_read(golden):
 def test_nojump_file_written_like_the_reference(golden, tmp_path):
     g = golden('walk_small')
     reader = PlainReader(g['pos'], g['box'], g['times'], str(tmp_path / 'walk_small.xtc'))
-    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'))
+    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'), trust_pickle=True)
     rd.save_nojump_matrixes(reader, mats)
     ours = tmp_path / '.walk_small.xtc.nojump.npz'
     assert rd.nojump_filename(reader) == str(ours) and ours.exists()
     with np.load(ours, allow_pickle=True) as a, np.load(os.path.join(GOLDEN, 'ref.nojump.npz'),
                                                         allow_pickle=True) as b:
-        assert sorted(a.files) == sorted(b.files)
+        # every entry of the reference's layout, plus the pickle-free twin of the checksum
+        assert sorted(a.files) == sorted(b.files + ['checksum_str'])
+        assert str(a['checksum_str'][()]) == str(a['checksum'][()])
         for key in b.files:
             assert a[key].dtype == b[key].dtype and a[key].shape == b[key].shape, key
             assert np.array_equal(a[key], b[key]), key
@@ -151,7 +153,7 @@ def test_nojump_file_load_rules(golden, tmp_path):
     reader = PlainReader(g['pos'], g['box'], g['times'], name)
     with pytest.raises(rd.NojumpError):
         reader.nojump_matrixes
-    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'))
+    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'), trust_pickle=True)
     rd.save_nojump_matrixes(reader, mats)
     fresh = PlainReader(g['pos'], g['box'], g['times'], name)
     assert rd.load_nojump_matrixes(fresh) is True
@@ -172,7 +174,7 @@ def test_memory_reader_picks_up_its_cache(golden, tmp_path):
     reader = MemoryReader(g['pos'], g['box'], g['times'], filename=name)
     with pytest.raises(rd.NojumpError):
         reader.nojump_matrixes
-    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'))
+    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'), trust_pickle=True)
     rd.save_nojump_matrixes(reader, mats)
     again = MemoryReader(g['pos'], g['box'], g['times'], filename=name)       # reader.py:283-285
     assert (again.nojump_matrixes[0] != mats[0]).nnz == 0
@@ -188,7 +190,7 @@ def test_jump_columns_reproduce_the_image_counts(golden, filtered):
     """The column lists the kernel walks, replayed in NumPy: running counts of any kept frames equal the
     prefix sums of the reference's jump matrices (pbc.py:235-237), also behind an atom selection."""
     g = golden('walk_small')
-    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'))
+    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'), trust_pickle=True)
     sel = np.nonzero(g['sel'])[0] if filtered else None
     indptr, frames, jumps = rd.jump_columns(mats, sel)
     jumps_ref = g['jumps'] if sel is None else g['jumps'][:, sel]
@@ -244,8 +246,9 @@ def test_autosave_file_like_the_reference(golden, tmp_path, autosave_on):
     assert os.listdir(tmp_path / 'autosave_dir') == [want['filename']]
     with np.load(path, allow_pickle=True) as a, np.load(os.path.join(GOLDEN, 'ref_autosave.npz'),
                                                         allow_pickle=True) as b:
-        assert sorted(a.files) == sorted(b.files) == ['checksum', 'data']
-        assert str(a['checksum'][()]) == str(b['checksum'][()]) == want['checksum']
+        assert sorted(b.files) == ['checksum', 'data']
+        assert sorted(a.files) == ['checksum', 'checksum_str', 'data', 'item_0', 'item_1', 'n_items']
+        assert str(a['checksum'][()]) == str(b['checksum'][()]) == want['checksum'] == str(a['checksum_str'][()])
         assert a['data'].dtype == b['data'].dtype and a['data'].shape == b['data'].shape
         assert all(np.array_equal(x, y) for x, y in zip(a['data'], b['data']))
     # second call: loaded, not recomputed; same values
@@ -260,11 +263,19 @@ def test_autosave_file_like_the_reference(golden, tmp_path, autosave_on):
         toy(Named('fn'), Frames(reader), scale=3.0, description='run1')
     assert calls[-1] == 3.0 and len(calls) == 5
     assert autosave.autosave_directory == 'autosave_dir'
-    # a file the reference wrote for the same call is accepted as it is
+    # a file the reference wrote for the same call holds pickled entries only: it is ignored (recomputed and
+    # replaced) unless the user opts in to unpickling; then it is accepted as it is
     import shutil
     shutil.copy(os.path.join(GOLDEN, 'ref_autosave.npz'), path)
-    loaded = toy(Named('fn'), Frames(reader), scale=2.0, description='run1')
-    assert len(calls) == 5 and all(np.array_equal(x, y) for x, y in zip(first, loaded))
+    toy(Named('fn'), Frames(reader), scale=2.0, description='run1')
+    assert len(calls) == 6
+    shutil.copy(os.path.join(GOLDEN, 'ref_autosave.npz'), path)
+    autosave.trust_pickle = True
+    try:
+        loaded = toy(Named('fn'), Frames(reader), scale=2.0, description='run1')
+    finally:
+        autosave.trust_pickle = False
+    assert len(calls) == 6 and all(np.array_equal(x, y) for x, y in zip(first, loaded))
     ragged = autosave.save_data(str(tmp_path / 'ragged.npz'), 7, (np.arange(3), np.arange(4), np.arange(5)))
     assert ragged is None
     back = autosave.load_data(str(tmp_path / 'ragged.npz'))
@@ -300,7 +311,7 @@ def test_correct_nojump_matrixes_for_whole(golden, tmp_path):
     g = golden('walk_small')
     name = str(tmp_path / 'traj.xtc')
     reader = MemoryReader(g['pos'], g['box'], g['times'], filename=name)
-    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'))
+    _, mats = rd.read_nojump_file(os.path.join(GOLDEN, 'ref.nojump.npz'), trust_pickle=True)
     from scipy import sparse
     seeded = sparse.lil_matrix(mats[1].shape, dtype=np.int8)
     seeded[0, 5] = -1
@@ -313,3 +324,41 @@ def test_correct_nojump_matrixes_for_whole(golden, tmp_path):
     assert (fixed[1][1:] != mats[1][1:]).nnz == 0                      # the other rows are untouched
     _, stored = rd.read_nojump_file(rd.nojump_filename(reader))
     assert all((a != b).nnz == 0 for a, b in zip(stored, fixed))
+
+
+class _Boom:
+    """Unpickling this object would run code (what ADVICE.md warns about)."""
+    fired = []
+
+    def __reduce__(self):
+        return (_Boom.fired.append, ('unpickled',))
+
+
+def test_cache_files_are_never_unpickled_by_default(golden, tmp_path, autosave_on):
+    """A cache file next to a trajectory is data from someone else's directory: neither the automatic pick-up of
+    ``.{traj}.nojump.npz`` nor an autosave lookup may unpickle its entries."""
+    from mdevaluate_b200 import MemoryReader
+    g = golden('walk_small')
+    name = str(tmp_path / 'traj.xtc')
+    _, mats = rd.read_nojump_file_matrices(os.path.join(GOLDEN, 'ref.nojump.npz'))
+    evil = {'checksum': np.array(_Boom(), dtype=object)}
+    for d, mat in enumerate(mats):
+        evil['shape'] = mat.shape
+        for attr in rd.CSR_ATTRS:
+            evil['{}_{}'.format(attr, d)] = getattr(mat, attr)
+    cache = tmp_path / '.traj.xtc.nojump.npz'
+    np.savez(cache, **evil)
+    reader = MemoryReader(g['pos'], g['box'], g['times'], filename=name)          # auto pick-up: ignored
+    with pytest.raises(rd.NojumpError):
+        reader.nojump_matrixes
+    assert rd.load_nojump_matrixes(reader) is False and cache.exists()
+    assert rd.load_nojump_matrixes(reader, verify=False) is True                  # matrices only, checksum untouched
+    assert _Boom.fired == []
+    with pytest.raises(rd.PickledChecksum):
+        rd.read_nojump_file(str(cache))
+    result = tmp_path / 'result.npz'
+    np.savez(result, checksum=np.array(_Boom(), dtype=object), data=np.arange(3.0))
+    assert autosave.verify_file(str(result), 1234) is False
+    with pytest.raises(ValueError):
+        autosave.load_data(str(result))
+    assert _Boom.fired == []

@@ -48,7 +48,7 @@ def test_sub_block_against_oracle(big):
     np.testing.assert_array_equal(images, unw.counts)
     assert np.abs(images).max() >= 1                     # atoms do cross the box
     c = md.correlation
-    sub_store = engine.DeviceStore(store.coords, n_sub, images=store.images, box=store.box, box_const=store.box_const)
+    sub_store = store.atom_block(0, n_sub)
     starts, idx = c._schedule(coords, c.log_indices, 10, 0.5, None)
     rows = (starts[:, None] + idx[None, :]).astype(np.int32)
     bins = np.linspace(0, 3.0, 501)
@@ -109,6 +109,15 @@ def test_shard_additivity_and_histogram_total(big):
     sa, ha = engine.correlate_device(a, rows, spec)
     sb, hb = engine.correlate_device(b, rows, spec)
     assert torch.equal(ha + hb, full_h)                                                    # integer counts: exact
+    torch.testing.assert_close(sa + sb, full_s, rtol=1e-12, atol=1e-9)
+    # the same through the packed image rows (atom blocks that start at a multiple of 16 atoms keep them aligned)
+    assert store.packed is not None
+    n1 = 50000 + 16 * 31
+    pa, pb = store.atom_block(0, n1), store.atom_block(n1, N)
+    assert pa.packed is not None and pb.packed is not None
+    sa, ha = engine.correlate_device(pa, rows, spec)
+    sb, hb = engine.correlate_device(pb, rows, spec)
+    assert torch.equal(ha + hb, full_h)
     torch.testing.assert_close(sa + sb, full_s, rtol=1e-12, atol=1e-9)
     # bit-reproducible run to run
     again_s, again_h = engine.correlate_device(store, rows, spec)
@@ -174,7 +183,7 @@ def test_config3_van_hove_and_alpha2_full_size():
     sub = block[:, :3 * n_sub].cpu().numpy().reshape(t_frames, n_sub, 3)
     unw = orc.UnwrappedTrajectory(sub, box, times)
     store = coords._resident().store_for(np.arange(t_frames), nojump=True)
-    sub_store = engine.DeviceStore(store.coords, n_sub, images=store.images, box=store.box, box_const=store.box_const)
+    sub_store = store.atom_block(0, n_sub)
     starts, idx = c._schedule(coords, c.log_indices, 10, 0.5, None)
     rows = (starts[:, None] + idx[None, :]).astype(np.int32)
     spec_vh = c._kernel_spec(partial(c.van_hove_self, bins=bins))

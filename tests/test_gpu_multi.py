@@ -70,6 +70,8 @@ if rank == 0:
                                   index_distribution=dense)
     assert np.allclose(out['dense'], rd, rtol=1e-9, atol=1e-12)
     print('MULTI_GPU_OK')
+assert shard.comm.p2p is not None, 'peer-memory communicator not in use'
+parallel.release_peer_comms()
 dist.destroy_process_group()
 '''
 

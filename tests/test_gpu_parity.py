@@ -629,7 +629,7 @@ def _golden_file(name):
 
 
 def _ref_matrices(md):
-    return md.reader.read_nojump_file(_golden_file('ref.nojump.npz'))[1]
+    return md.reader.read_nojump_file_matrices(_golden_file('ref.nojump.npz'))[1]
 
 
 def test_stored_jump_matrices_replace_the_scan(small, md):
@@ -769,11 +769,22 @@ def test_autosave_round_trip(small, md, tmp_path):
         md.autosave.disable()
 
 
-def test_isf_float32_displacement_path_against_float64_path(md, monkeypatch):
+@pytest.fixture
+def tuning():
+    """engine.tuning with every switch back at its default after the test."""
+    from mdevaluate_b200._cuda import engine
+    saved = {f: getattr(engine.tuning, f) for f in engine.Tuning.FIELDS + ('use_packed',)}
+    yield engine.tuning
+    for f, v in saved.items():
+        setattr(engine.tuning, f, v)
+
+
+def test_isf_float32_displacement_path_against_float64_path(md, tuning):
     """ISF alone with a constant float32 box computes displacements in float32 (operand on the far side of
-    the boundary moved first, csrc/corr_kernels.cu::process_tile_sinc_f32); MDB_SINC_F64=1 forces the float64
+    the boundary moved first, csrc/corr_kernels.cu::process_tile_f32d); tuning.isf_float64 forces the float64
     chain the other functions use.  Both against the oracle, and against each other, in a small box where
-    most atoms cross several images (|n0 - nt| up to 3 and more) and in a large one."""
+    most atoms cross several images (|n0 - nt| up to 3 and more: byte image counts) and in a large one (packed
+    counts)."""
     from mdevaluate_b200.synthetic import random_walk
     c = md.correlation
     for n_atoms, box, sigma in ((1500, 1.3, 0.12), (1100, 14.4, 0.05)):
@@ -784,9 +795,11 @@ def test_isf_float32_displacement_path_against_float64_path(md, monkeypatch):
         _, ref = orc.shifted_correlation(partial(orc.isf, q=22.7), unw, segments=9, window=0.5)
         coords = md.Coordinates.from_arrays(pos, bx, times)
         _, fast = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=9, window=0.5)
-        monkeypatch.setenv('MDB_SINC_F64', '1')
+        store = coords._resident().store_for(np.arange(160), nojump=True)
+        assert (store.packed is not None) == (np.abs(unw.counts).max() <= 1)
+        tuning.isf_float64 = 1
         _, slow = c.shifted_correlation(partial(c.isf, q=22.7), coords.nojump, segments=9, window=0.5)
-        monkeypatch.delenv('MDB_SINC_F64')
+        tuning.isf_float64 = 0
         assert not np.array_equal(fast, slow)             # really two code paths
         close(fast, ref)
         close(slow, ref)
@@ -798,6 +811,88 @@ def test_isf_float32_displacement_path_against_float64_path(md, monkeypatch):
                                            correlation=orc.subensemble_pairwise(
                                                lambda f: np.where(np.asarray(f)[:, 0] % box < 0.5 * box)[0]))
         close(fast_m, ref_m)
+
+
+def test_packed_image_counts_equal_the_byte_rows(md, tuning):
+    """Counts within [-1, 1] are re-coded as one word per 4 atoms (MDB_IMAGE_PACKED): the packed rows decode to the
+    scan's byte rows, and every kernel gives bit-identical results from either format (the scale 4^d of a packed
+    field is folded into the box: products and FMAs are exact)."""
+    from mdevaluate_b200.synthetic import random_walk
+    c = md.correlation
+    pos, bx, times = random_walk(2311, 200, seed=11, sigma=0.05, box=6.0)
+    coords = md.Coordinates.from_arrays(pos, bx, times)
+    store = coords._resident().store_for(np.arange(200), nojump=True)
+    assert store.packed is not None and store.images is not None
+    unw = orc.UnwrappedTrajectory(pos, bx, times)
+    assert np.abs(unw.counts).max() == 1
+    np.testing.assert_array_equal(store.image_counts(), unw.counts)
+    only_packed = type(store)(store.coords, store.n_atoms, packed=store.packed, box=store.box,
+                              box_const=store.box_const)
+    np.testing.assert_array_equal(only_packed.image_counts(), unw.counts)
+    bins = np.linspace(0, 2.0, 201)
+    fns = {'msd': c.msd, 'ng': c.non_gaussian, 'isf': partial(c.isf, q=22.7), 'vh': partial(c.van_hove_self, bins=bins)}
+    sel = c.subensemble_correlation(lambda f: np.where(np.asarray(f)[:, 1] % 6.0 < 2.5)[0])
+    for isf64, hist64 in ((0, 0), (1, 1)):
+        tuning.isf_float64, tuning.hist_float64 = isf64, hist64
+        got = {}
+        for use in (True, False):
+            tuning.use_packed = use
+            for name, fn in fns.items():
+                got[name, use] = c.shifted_correlation(fn, coords.nojump, segments=11, window=0.4)[1]
+                got[name + '_sel', use] = c.shifted_correlation(fn, coords.nojump, segments=11, window=0.4,
+                                                                correlation=sel)[1]
+            got['fused', use] = c.shifted_correlation_multi({'vh': fns['vh'], 'ng': fns['ng']}, coords.nojump,
+                                                            segments=11, window=0.4)[1]
+        for name in list(fns) + [n + '_sel' for n in fns]:
+            np.testing.assert_array_equal(got[name, True], got[name, False], err_msg=name)
+        np.testing.assert_array_equal(got['fused', True]['vh'], got['fused', False]['vh'])
+        np.testing.assert_array_equal(got['fused', True]['ng'], got['fused', False]['ng'])
+        # the unwrapped float64 frame from a packed row
+    tuning.use_packed = True
+    frame = coords.nojump[150]
+    np.testing.assert_array_equal(np.asarray(frame), unw[150])
+    import torch
+    from mdevaluate_b200._cuda import engine, lib
+    row = engine.nojump_apply(store.coords[150], store.packed[150], store.box[150].cpu().numpy(), store.n_atoms,
+                              lib.IMAGE_PACKED)
+    np.testing.assert_array_equal(row.cpu().numpy().reshape(-1, 3), unw[150])
+
+
+def test_image_counts_beyond_one_byte(md):
+    """An atom that crosses more than 127 images: the reference has no limit (pbc.py:235-237 sums int8 jumps into
+    int64); the scan falls back to int16 rows and the direct-load kernel."""
+    rng = np.random.default_rng(3)
+    n_atoms, n_frames, box = 40, 700, 1.0
+    x = rng.uniform(0, box, size=(n_atoms, 3))
+    drift = np.zeros((n_atoms, 3))
+    drift[:7, 0] = 0.3                     # 210 box lengths in 700 frames
+    drift[3:9, 2] = -0.27
+    walk = x[None] + np.cumsum(rng.normal(0, 0.02, size=(n_frames, n_atoms, 3)) + drift[None], axis=0)
+    pos = np.mod(walk, box).astype(np.float32)
+    pos[pos >= np.float32(box)] -= np.float32(box)
+    bx = np.array([box] * 3, dtype=np.float32)
+    times = np.arange(n_frames, dtype=np.float64)
+    unw = orc.UnwrappedTrajectory(pos, bx, times)
+    assert np.abs(unw.counts).max() > 127
+    c = md.correlation
+    for compact in (False, True):
+        coords = md.Coordinates.from_arrays(pos, bx, times)
+        coords._resident().force_compact = compact
+        _, r = c.shifted_correlation(c.msd, coords.nojump, segments=7, window=0.5)
+        _, ref = orc.shifted_correlation(orc.msd, unw, segments=7, window=0.5)
+        close(r, ref, scale=float(np.nanmax(ref)), rtol=1e-11, atol=1e-13)
+        _, f = c.shifted_correlation(partial(c.isf, q=7.0), coords.nojump, segments=7, window=0.5)
+        _, fref = orc.shifted_correlation(partial(orc.isf, q=7.0), unw, segments=7, window=0.5)
+        close(f, fref)
+    store = coords._resident().store_for(np.arange(n_frames), nojump=True)
+    assert store.images is None and store.packed is None and store.images16 is not None
+    np.testing.assert_array_equal(np.asarray(coords.nojump[650]), unw[650])
+    # per-step jumps stay int8 whatever the running counts do
+    jumps = md.reader.parse_jumps(md.Coordinates.from_arrays(pos, bx, times))
+    dense = np.zeros((n_frames, n_atoms, 3), dtype=np.int64)
+    for d, m in enumerate(jumps):
+        dense[m.row, m.col, d] = m.data
+    np.testing.assert_array_equal(np.cumsum(dense, axis=0), unw.counts)
 
 
 def test_generate_nojump_matrixes_from_a_subset_covers_all_atoms(small, md):
@@ -813,12 +908,11 @@ def test_generate_nojump_matrixes_from_a_subset_covers_all_atoms(small, md):
     close(r, g['msd_sel'], scale=float(np.nanmax(g['msd_sel'])), rtol=1e-11, atol=1e-13)
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('MDB_TEST_CANDIDATES'),
-                    reason='unmeasured round-2 candidates run only with MDB_TEST_CANDIDATES=1')
 @pytest.mark.parametrize('n_atoms,n_frames,segments', [(96, 240, 120), (131, 200, 50), (300, 150, 75), (1000, 130, 65)])
-def test_candidate_dense_warp_staging(md, monkeypatch, n_atoms, n_frames, segments):
-    """MDB_DENSE_STAGE=warp (csrc/dense_kernels.cu::stage_rows_warp): same sums as the default staging, bit for bit
-    (the staged rows are identical, the evaluation code is shared)."""
+def test_dense_staging_variants_agree(md, monkeypatch, tuning, n_atoms, n_frames, segments):
+    """Warp-per-row staging of the dense kernel (the default, csrc/dense_kernels.cu::stage_rows_warp) and the CTA-wide
+    staging loop (tuning.dense_stage_cta): same sums bit for bit (the staged rows are identical, the evaluation code
+    is shared)."""
     from mdevaluate_b200.synthetic import random_walk
     pos, box, times = random_walk(n_atoms, n_frames, seed=n_atoms, sigma=0.08, box=1.7)
     c = md.correlation
@@ -828,37 +922,77 @@ def test_candidate_dense_warp_staging(md, monkeypatch, n_atoms, n_frames, segmen
         for mode in ('nojump', 'raw'):
             coords = md.Coordinates.from_arrays(pos, box, times)
             frames = coords.nojump if mode == 'nojump' else coords
+            tuning.dense_stage_cta = 1
             _, ref = c.shifted_correlation(fn, frames, segments=segments, window=0.5, average=True, index_distribution=dense)
-            monkeypatch.setenv('MDB_DENSE_STAGE', 'warp')
+            tuning.dense_stage_cta = 0
             _, got = c.shifted_correlation(fn, frames, segments=segments, window=0.5, average=True, index_distribution=dense)
-            monkeypatch.delenv('MDB_DENSE_STAGE')
             np.testing.assert_array_equal(got, ref)
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('MDB_TEST_CANDIDATES'),
-                    reason='unmeasured round-2 candidates run only with MDB_TEST_CANDIDATES=1')
-def test_candidate_van_hove_float32_estimate(small, md, monkeypatch):
-    """MDB_HIST_F32=1 (csrc/corr_kernels.cu::process_tile_hist_f32): float32 displacements for the bin estimate,
-    the reference's float64 arithmetic for samples near an edge -- the counts must stay EXACT."""
+def test_van_hove_float32_estimate_is_exact(small, md, tuning):
+    """van Hove with a constant float32 box (the default path): float32 displacements feed the bin estimate, the
+    reference's float64 arithmetic decides the samples near an edge -- the counts must equal those of the float64
+    chain (tuning.hist_float64) and of the reference."""
     from mdevaluate_b200.synthetic import random_walk
     g, coords = small
     c = md.correlation
-    monkeypatch.setenv('MDB_HIST_F32', '1')
     t, r = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords.nojump, segments=12, window=0.4)
     np.testing.assert_array_equal(r, g['vh_nojump'])
     sel = c.subensemble_correlation(lambda f: np.where(np.asarray(f)[:, 2] % 1.5 < 0.6)[0])
     _, masked = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords.nojump, segments=9, window=0.4,
                                       correlation=sel)
-    monkeypatch.delenv('MDB_HIST_F32')
+    tuning.hist_float64 = 1
+    t, r64 = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords.nojump, segments=12, window=0.4)
+    np.testing.assert_array_equal(r64, g['vh_nojump'])
     _, masked_ref = c.shifted_correlation(partial(c.van_hove_self, bins=g['bins']), coords.nojump, segments=9, window=0.4,
                                           correlation=sel)
+    tuning.hist_float64 = 0
     np.testing.assert_array_equal(masked, masked_ref)
-    # a box of config-2 size, 500 bins, enough samples to land within 1e-6 of bin edges
+    # a box of config-2 size, 500 bins, enough samples to land within 1e-6 of bin edges; alone and next to alpha_2
     pos, box, times = random_walk(20000, 300, seed=3, sigma=0.05, box=14.4)
     big = md.Coordinates.from_arrays(pos, box, times)
     bins = np.linspace(0, 3.0, 501)
-    _, ref = c.shifted_correlation(partial(c.van_hove_self, bins=bins), big.nojump, segments=20)
-    monkeypatch.setenv('MDB_HIST_F32', '1')
-    _, got = c.shifted_correlation(partial(c.van_hove_self, bins=bins), big.nojump, segments=20)
-    monkeypatch.delenv('MDB_HIST_F32')
+    vh = partial(c.van_hove_self, bins=bins)
+    _, got = c.shifted_correlation(vh, big.nojump, segments=20)
+    _, fused = c.shifted_correlation_multi({'vh': vh, 'a2': c.non_gaussian}, big.nojump, segments=20)
+    _, a2 = c.shifted_correlation(c.non_gaussian, big.nojump, segments=20)
+    tuning.hist_float64 = 1
+    _, ref = c.shifted_correlation(vh, big.nojump, segments=20)
+    _, fused64 = c.shifted_correlation_multi({'vh': vh, 'a2': c.non_gaussian}, big.nojump, segments=20)
+    tuning.hist_float64 = 0
     np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(fused['vh'], ref)
+    np.testing.assert_array_equal(fused64['vh'], ref)
+    assert got.sum(axis=-1).min() > 0.99                     # (nearly) every atom lands in a bin
+    # alpha_2 next to the histogram: float32 displacements, good to 1e-7 relative per atom (north star: 1e-5);
+    # through the float64 chain it equals the stand-alone kernel to rounding
+    close(fused['a2'][:, 1:], a2[:, 1:], atol=1e-7)
+    close(fused64['a2'][:, 1:], a2[:, 1:], rtol=1e-11, atol=1e-13)
+
+
+def test_peer_comm_of_one_rank(small, md):
+    """A communicator of world size 1 drives the whole peer-memory path of the finish kernel on one GPU (stores into
+    the inbox, flags, wait, ordered sum): same results as without it, histograms included."""
+    from mdevaluate_b200._cuda import engine
+    g, coords = small
+    c = md.correlation
+    comm = engine.Comm(0, 1, lambda h: [h], capacity_words=1 << 16)
+    try:
+        res = coords._resident()
+        store = res.store_for(np.arange(len(coords)), nojump=True)
+        starts, idx = c._schedule(coords, c.log_indices, 12, 0.4, None)
+        rows = store.rows_for(starts[:, None] + idx[None, :])
+        for fn in (c.msd, partial(c.isf, q=22.7), partial(c.van_hove_self, bins=g['bins'])):
+            spec = c._kernel_spec(fn)
+            plain = engine.CorrPlan(store, rows, spec.corr)
+            peer = engine.CorrPlan(store, rows, spec.corr, comm=comm)
+            for _ in range(3):                               # both parities of the inbox
+                s0, h0 = plain.run()
+                s1, h1 = peer.run()
+                np.testing.assert_array_equal(s0, s1)
+                if h0 is not None:
+                    np.testing.assert_array_equal(h0, h1)
+            plain.close()
+            peer.close()
+    finally:
+        comm.close()

@@ -1,16 +1,16 @@
 """The float32 bin estimate of the van Hove kernel, replayed on the CPU against the reference's rule.
 
-csrc/corr_kernels.cu::eval_group decides the bin of a sample from a float32 estimate t = r / dx whenever t lies
-farther from every bin edge than a margin, and sends the rest through the exact float64 path (utils.histogram's
-floor_divide rule on the reference's own arithmetic).  The counts are exact only if the margin really bounds the
+csrc/corr_kernels.cu::hist_fast4 decides the bin of a sample from a float32 estimate th = r / dx - 1/2 (one FMA)
+whose nearest integer is floor(r / dx) whenever r / dx lies farther from every bin edge than a margin, and sends the
+rest through the exact float64 path (utils.histogram's floor_divide rule on the reference's own arithmetic).  The counts are exact only if the margin really bounds the
 error of the estimate.  Here the estimate is recomputed with NumPy float32 operations -- MUFU.RSQ modelled as the
 correctly rounded 1/sqrt perturbed by up to 2^-22 relative, its documented bound -- on samples placed within
 1e-8 .. 1e-2 bin widths of bin edges, and every sample the estimate would decide is checked against
 np.floor_divide(r, dx) of the reference's float64 r.  Two variants:
 
-* 'f64': r^2 from the float64 displacement chain (what the kernel does today), margin 8e-7 t + 1e-6;
-* 'f32': r^2 from the float32 displacements of the ISF path (tests/test_float32_displacement.py), the candidate for
-  histogram-only launches, which needs the wider margin 1.6e-6 t + 1e-6.
+* 'f64': r^2 from the float64 displacement chain (tuning.hist_float64, per-frame boxes), margin 8e-7 t + 1e-6;
+* 'f32': r^2 from the float32 displacements (process_tile_f32d, tests/test_float32_displacement.py), the default
+  for van Hove alone and van Hove + alpha_2 on a constant float32 box, which needs the wider margin 1.6e-6 t + 1e-6.
 """
 import numpy as np
 import pytest
@@ -21,16 +21,19 @@ MAGIC = np.float32(12582912.0)          # 1.5 * 2^23
 
 
 def estimate_bins(r2f, inv_dx_f, slope, rng):
-    """(bin, decided) of the kernel's branch-free estimate for float32 r^2."""
+    """(bin, decided) of the kernel's branch-free estimate for float32 r^2 (hist_fast4; the constants as
+    corr_host.cu::device_args sets them)."""
     exact_rs = (1.0 / np.sqrt(r2f.astype(np.float64)))
     rs = (exact_rs * (1.0 + rng.uniform(-2.0 ** -22, 2.0 ** -22, r2f.shape))).astype(np.float32)
-    t = (r2f * rs) * inv_dx_f                              # float32 products, as in the kernel
-    tb = t + MAGIC
-    tr = tb - MAGIC                                        # rint(t)
-    dist = t - tr
-    margin = fma32(t, np.full_like(t, np.float32(slope)), np.full_like(t, np.float32(1e-6)))
-    bins = tb.view(np.int32) - np.int32(0x4B400000) - (dist < 0)
-    return bins.astype(np.int64), np.abs(dist) > margin
+    r = r2f * rs                                           # float32 product
+    th = fma32(r, np.full_like(r, inv_dx_f), np.full_like(r, np.float32(-0.5)))
+    tb = th + MAGIC
+    dd = th - (tb - MAGIC)                                 # frac(r / dx) - 1/2
+    c1 = np.float32(-slope)
+    lim0 = np.float32(0.5 - 1e-6 - 0.5 * slope)
+    lim = fma32(th, np.full_like(th, c1), np.full_like(th, lim0))
+    bins = tb.view(np.int32).astype(np.int64) - 0x4B400000
+    return bins, np.abs(dd) < lim
 
 
 def samples_near_edges(n, box, dx, n_bins, rng):
