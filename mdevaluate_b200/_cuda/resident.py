@@ -76,6 +76,7 @@ class Resident:
         self._compact = {}              # (mode, hash of frame ids) -> DeviceStore
         self.force_compact = False
         self.pack_images = True         # re-code byte image rows as packed rows when no count leaves [-1, 1]
+        self.lookup = {}                # correlation._provider: schedule -> (store, rows) of repeated calls
 
     @property
     def reader(self):
@@ -130,6 +131,13 @@ class Resident:
     def _segments(self):
         """Yield ``(t0, t1, device_tensor)`` over the whole trajectory, double-buffered."""
         torch = _lib.require_cuda()
+        generated = getattr(self.reader, 'device_segments', None)
+        if generated is not None:
+            # a reader that produces its frames on the device in time order (synthetic.RandomWalkStream)
+            if self.atom_filter is not None:
+                raise _lib.CudaPathError('a generated stream is read with all of its atoms')
+            yield from generated(self.device)
+            return
         block = getattr(self.reader, 'device_block', None)
         if block is not None and block.dtype == torch.float32 and (self.atom_filter is None or self._filter_run):
             # already in HBM: views of the block (all atoms, or the columns of one contiguous run of atoms)
@@ -352,9 +360,18 @@ class Resident:
         from ..reader import jump_columns
         lists = self._jump_lists
         if lists is None or lists[0] is not mats:
-            indptr, frames, jumps = jump_columns(mats, self.atom_filter)
-            lists = self._jump_lists = (mats,) + tuple(torch.from_numpy(a).to(self.device)
-                                                       for a in (indptr, frames, jumps))
+            # the column lists are a pure function of the matrices: readers that share a `host_cache` dict (clones of
+            # one trajectory, reader.SparseFrameReader.fresh) convert them once and keep them page-locked
+            cache = getattr(self.reader, 'host_cache', None)
+            key = ('jump_columns', id(mats), None if self.atom_filter is None else self.atom_filter.tobytes())
+            host = cache.get(key) if cache is not None else None
+            if host is None or host[0] is not mats:
+                arrays = jump_columns(mats, self.atom_filter)
+                host = (mats,) + tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in arrays)
+                if cache is not None:
+                    host = (mats,) + tuple(t.pin_memory() for t in host[1:])
+                    cache[key] = host
+            lists = self._jump_lists = (mats,) + tuple(t.to(self.device, non_blocking=True) for t in host[1:])
         overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
         keep_dev = None
         if keep is not None:
@@ -402,6 +419,42 @@ class Resident:
             self._compress_images(store)
         return store
 
+    def sparse_jumps(self):
+        """Per-step jumps of every frame in coordinate form, host arrays ``(frame int32, component int64, jump int8)``
+        sorted by frame and component (component = 3 * atom + dimension): the scan runs segment by segment and only
+        the non-zero entries leave the device, so this also serves trajectories that never fit in memory."""
+        torch = _lib.require_cuda()
+        n3 = 3 * self.n_atoms
+        prev = torch.zeros((n3,), dtype=torch.float32, device=self.device)
+        cum = torch.zeros((n3,), dtype=torch.int32, device=self.device)
+        box0 = self._box_of(0)
+        whole0 = None
+        ref0 = getattr(self.reader, 'whole0', None)
+        if ref0 is not None:
+            ref0 = ref0 if self.atom_filter is None else ref0[self.atom_filter]
+            whole0 = torch.from_numpy(np.ascontiguousarray(ref0.reshape(-1))).to(self.device)
+        dense = self._dense
+        if dense is not None and dense.coords.dtype == torch.float32:
+            step = max(1, (256 << 20) // self.pitch)
+            source = ((t0, min(self.n_frames, t0 + step), dense.coords[t0:t0 + step])
+                      for t0 in range(0, self.n_frames, step))
+        else:
+            source = self._segments()
+        frames, comps, vals = [], [], []
+        for t0, t1, seg in source:
+            jumps = torch.empty((t1 - t0, self.pitch), dtype=torch.int8, device=self.device)
+            engine.nojump_scan(seg, self.n_atoms, box0, box0.dtype == np.float32, prev, cum, first_segment=(t0 == 0),
+                               jumps=jumps, whole0=whole0)
+            nz = torch.nonzero(jumps[:, :n3])
+            if nz.numel():
+                frames.append((nz[:, 0] + t0).to(torch.int32).cpu().numpy())
+                comps.append(nz[:, 1].cpu().numpy())
+                vals.append(jumps[:, :n3][nz[:, 0], nz[:, 1]].cpu().numpy())
+            del jumps, nz
+        if not frames:
+            return (np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int8))
+        return np.concatenate(frames), np.concatenate(comps), np.concatenate(vals)
+
     def dense_jumps(self):
         """Per-step jumps of every frame as a host int8 array (T, N, 3) -- for parse_jumps."""
         torch = _lib.require_cuda()
@@ -445,6 +498,13 @@ class Resident:
             idx = torch.from_numpy(frame_ids).to(self.device)
             w = min(block.shape[1], self.pitch)
             coords[:, :w] = block.index_select(0, idx)[:, :w]
+        elif self.atom_filter is None and getattr(self.reader, 'pinned_rows', None) is not None and \
+                self.reader.pinned_rows(frame_ids) is not None:
+            # the reader holds exactly these frames in page-locked memory: DMA straight out of it
+            src = self.reader.pinned_rows(frame_ids)              # torch (n_rows, 3N), pinned
+            step = max(1, (1 << 30) // (n3 * 4))
+            for r0 in range(0, n_rows, step):
+                coords[r0:r0 + step, :n3].copy_(src[r0:r0 + step], non_blocking=True)
         else:
             # only the kept frames are read from the reader
             chunk = max(1, (256 << 20) // (self.pitch * coords.element_size()))
@@ -481,6 +541,14 @@ class Resident:
         on the reader: its HBM store lives as long as the caller holds it."""
         own = np.arange(self.n_atoms_all) if self.atom_filter is None else self.atom_filter
         return Resident(self.reader, own[a0:a1], device=self.device)
+
+    def serves(self, store, nojump):
+        """Whether ``store`` is still one of this resident's stores and up to date (correlation._provider)."""
+        if self.force_compact and store is self._dense:
+            return False
+        if store is not self._dense and not any(store is s for s in self._compact.values()):
+            return False
+        return not nojump or (store.has_images and store.source is self._matrices())
 
     def store_for(self, frame_ids, nojump):
         """A DeviceStore holding (at least) ``frame_ids``; with image counts if ``nojump``."""

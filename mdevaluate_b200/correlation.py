@@ -278,13 +278,25 @@ def _provider(frames, frame_ids):
     if isinstance(frames, Coordinates):
         res = frames._resident()
         nojump = frames.mode == 'nojump'
-        store = res.store_for(ids.ravel(), nojump=nojump)
+        # repeated calls: the store and the row table of this schedule, as long as the resident still serves that
+        # store (and, for nojump, its image counts still come from the reader's current jump matrices)
+        key = (nojump, ids.shape, ids.tobytes())
+        hit = res.lookup.get(key)
+        if hit is not None and res.serves(hit[0], nojump):
+            store, rows = hit
+        else:
+            store = res.store_for(ids.ravel(), nojump=nojump)
+            rows = store.rows_for(ids)
+            if len(res.lookup) > 32:
+                res.lookup.clear()
+            res.lookup[key] = (store, rows)
+        _provider.base = (res, store)
         if not nojump:
             store = store.without_images()
-        rows = store.rows_for(ids)
         float32 = (not nojump) and res.dtype == np.float32
         return store, rows, res.n_atoms, float32, frames.comm
     # generic frames protocol (coordinates.py:257-293): pull the needed frames through __getitem__
+    _provider.base = None
     uniq, inverse = np.unique(ids.ravel(), return_inverse=True)
     store, float32 = _store_from_host_frames([frames[int(i)] for i in uniq])
     rows = inverse.reshape(ids.shape).astype(np.int32)
@@ -525,6 +537,7 @@ def _run(frames, frame_ids, specs, select=None):
     p2p = getattr(comm, 'p2p', None) if comm is not None else None
     plan = _plan_for(store, rows, corr, select_dev, p2p)
     sums, hist = plan.run()
+    _run.last = (plan, _provider.base, float32) if (select is None and (comm is None or p2p is not None)) else None
     if comm is not None:
         if p2p is None:      # no peer memory (gloo / IPC refused): the torch.distributed all-reduce
             from . import parallel
@@ -564,6 +577,68 @@ for _f in (log_indices, correlation, msd, isf, van_hove_self, non_gaussian, rota
 del _f
 
 
+# --------------------------------------------------------------------------------------------
+# repeated calls: everything a call needs besides the kernel launch, remembered per (trajectory, function, schedule)
+# --------------------------------------------------------------------------------------------
+class _CachedCall:
+    __slots__ = ('res_ref', 'base_store', 'plan', 'spec', 'times', 'n_origins', 'float32', 'tuning', 'comm')
+
+
+_call_cache = {}
+MAX_CACHED_CALLS = 64
+
+
+def _call_key(function, frames, index_distribution, segments, window, skip):
+    """Hashable identity of a plain call with the default lag distribution on a Coordinates object, or None."""
+    from .coordinates import Coordinates
+    if index_distribution is not log_indices or not isinstance(frames, Coordinates):
+        return None, None
+    res = frames.__dict__.get('_resident_obj')
+    if res is None:
+        return None, None
+    fn, kws = function, ()
+    if isinstance(fn, functools.partial):
+        if fn.args or isinstance(fn.func, functools.partial):
+            return None, None
+        kws = tuple(sorted(fn.keywords.items()))
+        fn = fn.func
+    sl = frames._slice
+    key = (id(res), frames.mode, sl.start, sl.stop, sl.step, fn, kws, segments, window, skip, id(frames.comm))
+    try:
+        hash(key)
+    except TypeError:          # e.g. bins given as an array: the general path has its own caches
+        return None, None
+    return key, res
+
+
+def _cached_call(key, res, frames, average):
+    entry = _call_cache.get(key)
+    if entry is None or entry.res_ref() is not res or entry.comm is not frames.comm:
+        return None
+    if entry.tuning != engine.tuning.key() or not res.serves(entry.base_store, frames.mode == 'nojump'):
+        del _call_cache[key]
+        return None
+    sums, hist = entry.plan.run()
+    n_atoms = res.n_atoms if entry.comm is None else entry.comm[1]
+    values = entry.spec.finalize(sums, hist, n_atoms, entry.float32)
+    return entry.times.copy(), _average(values, entry.n_origins, average)
+
+
+def _remember_call(key, res, frames, spec, times, n_origins):
+    import weakref
+    last = getattr(_run, 'last', None)
+    if last is None or last[1] is None or last[1][0] is not res:
+        return
+    entry = _CachedCall()
+    entry.res_ref = weakref.ref(res)
+    entry.plan, (_, entry.base_store), entry.float32 = last
+    entry.spec, entry.times, entry.n_origins = spec, np.array(times), n_origins
+    entry.tuning, entry.comm = engine.tuning.key(), frames.comm
+    if len(_call_cache) >= MAX_CACHED_CALLS:
+        _call_cache.clear()
+    _call_cache[key] = entry
+
+
 @autosave_data(nargs=2, kwargs_keys=(
     'index_distribution', 'correlation', 'segments', 'window', 'skip', 'average'
 ), version='shifted_correlation-1')
@@ -585,6 +660,13 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
         raise NotImplementedError('only the default strategy, subensemble_correlation(selector) and '
                                   'multi_subensemble_correlation(selector) are on the B200 path; '
                                   'there is no CPU fallback')
+    call_key = res_key = None
+    if plain:
+        call_key, res_key = _call_key(function, frames, index_distribution, segments, window, skip)
+        if call_key is not None:
+            hit = _cached_call(call_key, res_key, frames, average)
+            if hit is not None:
+                return hit
     spec = _kernel_spec(function)
     start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
     frame_ids = _frame_ids(start_frames, idx, len(frames))
@@ -599,6 +681,8 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
         if batch >= n_origins:
             sums, hist, n_atoms, float32 = _run(frames, frame_ids, [spec])
             values = spec.finalize(sums, hist, n_atoms, float32)
+            if call_key is not None:
+                _remember_call(call_key, res_key, frames, spec, times, n_origins)
             return times, _average(values, n_origins, average)
         # very many (origin, lag) pairs (dense schedules): origins go through in batches so that the
         # per-pair device buffers stay bounded; the average is accumulated origin by origin as above
@@ -614,6 +698,11 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
         return times, (acc / n_origins if average else np.concatenate(acc, axis=0))
 
     # ---- sub-ensembles: the selector sees every origin frame on the host, the kernel gets masks ----
+    from .coordinates import Coordinates
+    if isinstance(frames, Coordinates):
+        # the schedule's store first: the origin frames below (and every batch) are then served from it instead of
+        # one single-frame store -- for a streamed trajectory one pass over all frames -- per origin
+        frames._resident().store_for(frame_ids.ravel(), nojump=frames.mode == 'nojump')
     origins = [frames[int(i)] for i in frame_ids[:, 0]]
     n_all = len(origins[0])
     if strategy[0] == 'sub':
@@ -695,7 +784,12 @@ def chi4(frames, q, index_distribution=log_indices, segments=20, window=0.2, ski
     ``N * Fqt.var(axis=0)`` of the non-averaged ISF; ``smooth=k`` applies ``runningmean(chi4, k)``."""
     t, fqt = shifted_correlation(functools.partial(isf, q=q), frames, index_distribution=index_distribution,
                                  segments=segments, window=window, skip=skip, average=False)
-    n_atoms = len(frames[0]) if getattr(frames, 'comm', None) is None else frames.comm[1]
+    if getattr(frames, 'comm', None) is not None:
+        n_atoms = frames.comm[1]
+    elif hasattr(frames, '_resident'):
+        n_atoms = frames._resident().n_atoms          # len(OW[0]) without fetching (and unwrapping) frame 0
+    else:
+        n_atoms = len(frames[0])
     x4 = n_atoms * fqt.var(axis=0)
     if smooth:
         return t, x4, runningmean(x4, smooth)

@@ -139,6 +139,86 @@ class MemoryReader:
         self._nojump_matrixes = mats
 
 
+class SparseFrameReader:
+    """Reader protocol over only the frames an analysis touches, held in page-locked host memory -- what a file reader
+    with a frame index delivers cheaply -- plus the trajectory's jump matrices (``nojump_matrixes``, e.g. from the
+    ``.nojump.npz`` cache), which make it complete for nojump: the GPU path then uploads just these frames
+    (``_cuda/resident.py``: strided DMA out of ``pinned_rows``) and derives their image counts from the matrices.
+
+    Args:
+        frame_ids: ascending trajectory frames that are present.
+        positions: ``(len(frame_ids), M, 3)`` float32 host array (page-locked for DMA speed).
+        box, times: as for :class:`MemoryReader`; ``times`` covers ALL ``n_frames`` frames.
+    """
+
+    def __init__(self, frame_ids, positions, box, times, filename='<sparse>', host_cache=None):
+        self.filename = filename
+        self.frame_ids = np.ascontiguousarray(frame_ids, dtype=np.int64)
+        if positions.ndim != 3 or positions.shape[2] != 3 or positions.shape[0] != len(self.frame_ids):
+            raise ValueError('positions must have shape (len(frame_ids), M, 3)')
+        self.positions = positions
+        self.times = np.asarray(times, dtype=np.float64)
+        self.n_frames = len(self.times)
+        self.n_atoms = positions.shape[1]
+        self.dtype = positions.dtype
+        self.box_constant, self.box_diag = _box_diagonals(box, self.n_frames)
+        self._slot = np.full((self.n_frames,), -1, dtype=np.int64)
+        self._slot[self.frame_ids] = np.arange(len(self.frame_ids))
+        self._nojump_matrixes = None
+        self.device_block = None
+        self.host_block = None
+        self.whole0 = None
+        self.host_cache = {} if host_cache is None else host_cache
+
+    def fresh(self):
+        """A new reader over the same host data (nothing cached on the GPU side is shared, the host-side caches are)."""
+        other = SparseFrameReader(self.frame_ids, self.positions, self.box_diag, self.times, self.filename,
+                                  host_cache=self.host_cache)
+        other._nojump_matrixes = self._nojump_matrixes
+        return other
+
+    def __len__(self):
+        return self.n_frames
+
+    def box_of(self, i):
+        return self.box_diag if self.box_constant else self.box_diag[i]
+
+    def __getitem__(self, i):
+        i = int(i)
+        if i < 0:
+            i += self.n_frames
+        if not 0 <= i < self.n_frames:
+            raise IndexError('frame %d out of range' % i)
+        slot = self._slot[i]
+        if slot < 0:
+            if i == 0:         # Coordinates only asks frame 0 for the number of atoms
+                return MemoryFrame(np.zeros((self.n_atoms, 3), dtype=self.dtype), np.diag(self.box_of(0)),
+                                   self.times[0], 0)
+            raise IndexError('frame %d is not held by this reader' % i)
+        diag = self.box_of(i)
+        return MemoryFrame(self.positions[slot], np.diag(diag).astype(diag.dtype), self.times[i], i)
+
+    def pinned_rows(self, frame_ids):
+        """Page-locked ``(n, 3M)`` torch view of exactly these frames, or None (not all present in one run / not
+        page-locked)."""
+        import torch
+        slots = self._slot[np.asarray(frame_ids, dtype=np.int64)]
+        if len(slots) == 0 or slots[0] < 0 or np.any(np.diff(slots) != 1):
+            return None
+        flat = torch.from_numpy(self.positions).view(len(self.frame_ids), 3 * self.n_atoms)
+        return flat[int(slots[0]):int(slots[-1]) + 1] if flat.is_pinned() else None
+
+    @property
+    def nojump_matrixes(self):
+        if self._nojump_matrixes is None:
+            raise NojumpError('Nojump Data not available: {}'.format(self.filename))
+        return self._nojump_matrixes
+
+    @nojump_matrixes.setter
+    def nojump_matrixes(self, mats):
+        self._nojump_matrixes = mats
+
+
 SparseData = namedtuple('SparseData', ['data', 'row', 'col'])
 
 
@@ -149,11 +229,11 @@ def parse_jumps(trajectory):
     ``round((x_t - x_{t-1}) / box_0)`` runs on the GPU (bit-exact int8, csrc/nojump_kernels.cu);
     the triplets are extracted from the dense result on the host for API compatibility.
     """
-    jumps = trajectory._resident().dense_jumps()          # (T, N, 3) int8 on the host
+    frames, comps, vals = trajectory._resident().sparse_jumps()      # non-zero jumps, sorted by frame and component
     out = []
     for d in range(3):
-        row, col = np.nonzero(jumps[:, :, d])
-        out.append(SparseData(data=jumps[row, col, d], row=row, col=col))
+        pick = (comps % 3) == d
+        out.append(SparseData(data=vals[pick], row=frames[pick].astype(np.int64), col=comps[pick] // 3))
     return tuple(out)
 
 

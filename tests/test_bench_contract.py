@@ -1,4 +1,5 @@
-"""bench.py's reference arm (the CPU port of the reference) runs here and prints the contract's JSON line."""
+"""bench.py's reference arm (the unmodified reference from baseline/_ref, or its NumPy port where that copy is absent)
+runs here and prints the contract's JSON line."""
 import json
 import os
 import subprocess
@@ -15,7 +16,8 @@ def test_reference_arm_json_line():
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['unit'] == 'evals/s' and line['value'] > 0
     assert line['higher_is_better'] is True and line['gpu_launches'] == 0
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] == 1
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] == 1
+    assert line['scaling'] == 'strong' and 'sample_atoms' not in line['config']
     assert line['cpu_baseline']['value'] == line['value']
     assert line['e2e'] == {'value': line['value'], 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     for key in ('metric', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'scaling', 'dtype', 'data', 'config'):

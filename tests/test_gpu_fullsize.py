@@ -177,8 +177,18 @@ def test_config3_van_hove_and_alpha2_full_size():
     np.testing.assert_array_equal(vh_alone, vh)
     with np.errstate(all='ignore'):
         _, a2_alone = c.shifted_correlation(c.non_gaussian, coords.nojump, segments=10)
-    np.testing.assert_array_equal(a2_alone, a2)
-    # oracle on an atom sub-block of the same trajectory: counts exact, alpha_2 to 1e-10
+    # alpha_2 rides on the float32 displacements of the histogram in the fused pass (1e-7 relative per atom, far
+    # inside the north star's 1e-5); through the float64 chain the fused pass equals the stand-alone kernel
+    np.testing.assert_allclose(a2[:, 1:], a2_alone[:, 1:], rtol=1e-5, atol=1e-7)
+    engine.tuning.hist_float64 = 1
+    try:
+        _, out64 = c.shifted_correlation_multi({'vh': partial(c.van_hove_self, bins=bins), 'a2': c.non_gaussian},
+                                               coords.nojump, segments=10)
+    finally:
+        engine.tuning.hist_float64 = 0
+    np.testing.assert_array_equal(out64['vh'], vh)
+    np.testing.assert_array_equal(out64['a2'], a2_alone)
+    # oracle on an atom sub-block of the same trajectory: counts exact, alpha_2 to 1e-5 (float32 displacements)
     n_sub = 128
     sub = block[:, :3 * n_sub].cpu().numpy().reshape(t_frames, n_sub, 3)
     unw = orc.UnwrappedTrajectory(sub, box, times)
@@ -195,6 +205,6 @@ def test_config3_van_hove_and_alpha2_full_size():
         _, ref_vh = orc.shifted_correlation(partial(orc.van_hove_self, bins=bins), unw, segments=10)
         _, ref_a2 = orc.shifted_correlation(orc.non_gaussian, unw, segments=10)
     np.testing.assert_array_equal(got_vh, ref_vh)
-    np.testing.assert_allclose(got_a2[:, 1:], ref_a2[:, 1:], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(got_a2[:, 1:], ref_a2[:, 1:], rtol=1e-5, atol=1e-7)
     del coords, block, store, sub_store
     torch.cuda.empty_cache()

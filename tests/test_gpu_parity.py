@@ -996,3 +996,45 @@ def test_peer_comm_of_one_rank(small, md):
             peer.close()
     finally:
         comm.close()
+
+
+def test_repeated_calls_reuse_their_plan(small, md, tuning):
+    """The second call of the same request on the same trajectory is a dictionary lookup and two kernel launches
+    (correlation._cached_call): same numbers, fresh arrays, and no stale answers when a switch or the jump matrices
+    change."""
+    g, coords = small
+    c = md.correlation
+    fn = partial(c.isf, q=22.7)
+    kw = dict(segments=12, window=0.4)
+    t1, r1 = c.shifted_correlation(fn, coords.nojump, **kw)
+    assert any(k[5] is c.isf for k in c._call_cache)
+    t2, r2 = c.shifted_correlation(fn, coords.nojump, **kw)
+    np.testing.assert_array_equal(r1, r2)
+    np.testing.assert_array_equal(t1, t2)
+    assert r2 is not r1 and t2 is not t1
+    r2[:] = 0                                                    # results belong to the caller
+    _, r3 = c.shifted_correlation(fn, coords.nojump, **kw)
+    np.testing.assert_array_equal(r1, r3)
+    _, avg = c.shifted_correlation(fn, coords.nojump, average=True, **kw)
+    np.testing.assert_allclose(avg, r1.sum(axis=0) / len(r1), rtol=1e-14)
+    close(r1, g['isf_nojump'])
+    tuning.isf_float64 = 1                                       # another kernel path: not the cached plan
+    _, r64 = c.shifted_correlation(fn, coords.nojump, **kw)
+    tuning.isf_float64 = 0
+    assert not np.array_equal(r64, r1) and np.abs(r64 - r1).max() < 5e-8
+    _, raw = c.shifted_correlation(c.msd, coords, **kw)          # raw mode of the same trajectory: its own entry
+    _, raw2 = c.shifted_correlation(c.msd, coords, **kw)
+    np.testing.assert_array_equal(raw, raw2)
+    assert raw.dtype == np.float32
+    _, unw = c.shifted_correlation(c.msd, coords.nojump, **kw)
+    assert unw.dtype == np.float64 and not np.allclose(unw, raw)
+    # replacing the reader's jump matrices invalidates what was derived from the scan (they are authoritative)
+    md.reader.generate_nojump_matrixes(coords)
+    _, r4 = c.shifted_correlation(fn, coords.nojump, **kw)
+    np.testing.assert_array_equal(r4, r1)
+    mats = coords.frames.nojump_matrixes
+    coords.frames.nojump_matrixes = tuple(m * 0 for m in mats)   # "no atom ever jumps"
+    _, r5 = c.shifted_correlation(fn, coords.nojump, **kw)
+    assert not np.array_equal(r5, r1)
+    coords.frames.nojump_matrixes = None
+    coords.frames._nojump_matrixes = None
