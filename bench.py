@@ -367,15 +367,15 @@ def ours_arm(a):
     def step():
         return c.chi4(frames, Q, **kw)
 
-    t_axis, x4 = step()
-    for _ in range(a.warmup):
-        step()
-
-    # ---- timed region: K steps, rows resident in HBM -----------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
+        sampler.start()               # nvidia-smi needs ~0.3 s to deliver its first sample: started before the warm-up
+    t_axis, x4 = step()
+    time.sleep(0.3)
+    for _ in range(a.warmup):         # W untimed steps, immediately before the timed region (no idle gap: the
+        step()                        # clocks of an idle GPU drop within a few hundred ms)
+
+    # ---- timed region: K steps, rows resident in HBM -----------------------------------------------------
     launches0 = engine.launches()
     barrier()
     w0 = time.time()
@@ -598,6 +598,16 @@ def measure_e2e(a, torch, md, c, parallel, res, store, stream, starts, idx, kw, 
     t, x4 = e2e_step()          # also converts the matrices to column lists once (host side, cached page-locked)
     lists = next(iter(base.host_cache.values()))
     list_bytes = int(sum(t_.numel() * t_.element_size() for t_ in lists[1:]))
+    # the floor: the same page-locked bytes copied to the device by all ranks at once, nothing else
+    sink = torch.empty((min(len(ids), step_rows), n3), dtype=torch.float32, device=dev)
+    barrier()
+    ev[0].record()
+    for r0 in range(0, len(ids), step_rows):
+        sink[:len(ids) - r0].copy_(host[r0:r0 + step_rows], non_blocking=True)
+    ev[1].record()
+    barrier()
+    floor_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
+    del sink
     barrier()
     ev[0].record()
     for _ in range(a.e2e_steps):
@@ -610,6 +620,10 @@ def measure_e2e(a, torch, md, c, parallel, res, store, stream, starts, idx, kw, 
     return {'value': evals_step / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d * world,
             'd2h_bytes_per_step': int(S * L * 3 * 8) * world, 'ms_per_step': e2e_ms, 'steps': a.e2e_steps,
             'h2d_GBps_per_gpu': h2d / (e2e_ms * 1e-3) / 1e9, 'matches_resident': bool(np.array_equal(x4, x4_e2e)),
+            'h2d_floor': {'ms': floor_ms, 'GBps_per_gpu': len(ids) * n3 * 4 / (floor_ms * 1e-3) / 1e9,
+                          'GBps_all_gpus': world * len(ids) * n3 * 4 / (floor_ms * 1e-3) / 1e9,
+                          'note': 'the frame bytes alone, copied by all %d ranks at the same time: what the host\'s '
+                                  'PCIe / memory system delivers' % world},
             'note': 'per step and GPU: %d frames of the schedule (page-locked host, %.2f GB) + the jump matrices as column '
                     'lists (%.0f MB) -> HBM, image counts from the matrices, packing, correlation, chi4, result read '
                     'back; matrices prepared once in %.1f s (not timed)'

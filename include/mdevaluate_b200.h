@@ -183,6 +183,10 @@ int mdb_corr_plan_run(mdb_corr_plan *plan, void *stream, int32_t time_slot);
 int mdb_corr_plan_launch(mdb_corr_plan *plan, void *stream, int32_t time_slot);
 int mdb_corr_plan_wait(mdb_corr_plan *plan);
 int mdb_corr_plan_kernel_ms(mdb_corr_plan *plan, int32_t time_slot, float *ms);
+/* How the host learns that a run is complete: 0 (default) the finish kernel writes the sums through the mapped host
+ * block and raises a flag the host polls; 1 the same writes, cudaStreamSynchronize instead of polling; 2 the sums
+ * stay on the device and are copied with cudaMemcpyAsync + cudaStreamSynchronize. */
+int mdb_corr_plan_set_wait(mdb_corr_plan *plan, int32_t mode);
 /* HOST pointers into the plan's page-locked result block, valid until mdb_corr_plan_destroy: sums [S*L*3]
  * (summed over the shards of `comm`), hist [S*L*B] or NULL.  Overwritten by the next run. */
 const double *mdb_corr_plan_sums(const mdb_corr_plan *plan);
@@ -291,6 +295,39 @@ int mdb_nojump_apply_format(const float *coords_row, const void *images_row, int
  * (frames x 3N) float32 trajectory.  Asynchronous when the source is page-locked. */
 int mdb_copy_rows_h2d(const void *src_host, int64_t src_pitch_bytes, void *dst_dev, int64_t dst_pitch_bytes,
                       int64_t width_bytes, int64_t n_rows, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Vectors between atoms for the frames a schedule touches (replaces `coordinates.vectors`, coordinates.py:524-563,
+ * mapped over the frames by CoordinatesMap, :332-393): the input rows of `rotational_autocorrelation`
+ * (MDB_SUM_LEGENDRE) are built on the device from the resident frame rows.
+ *   out[r][v] = pbc_diff( mean_i x[atoms_a[i][v]], mean_j x[atoms_b[j][v]], pbc_box ) [ / norm ]
+ * in the reference's arithmetic, operation by operation: float64 with images (the nojump frame x - n*box), float32
+ * for raw frames.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mdb_vectors_args {
+    const float *coords;         /* DEVICE [n_store_rows][pitch] float32 frame rows                */
+    int64_t pitch;
+    const void *images;          /* DEVICE image rows in `image_format`, or NULL (raw frames)      */
+    int32_t image_format;        /* MDB_IMAGE_BYTES / _PACKED / _I16                               */
+    int64_t img_pitch;           /* elements of that format per row                                */
+    const double *box;           /* DEVICE [n_store_rows][3] or NULL: box_const (for the unwrap)   */
+    double box_const[3];
+    const int32_t *rows;         /* DEVICE [n_rows] storage rows to transform, or NULL (0..n_rows-1) */
+    int32_t n_rows;
+    const int32_t *atoms_a;      /* DEVICE [m_a][n_vec] atom indices; the mean over m_a is taken   */
+    int32_t m_a;
+    const int32_t *atoms_b;      /* DEVICE [m_b][n_vec]                                            */
+    int32_t m_b;
+    int32_t n_vec;
+    int32_t normed;              /* divide by the norm                                             */
+    int32_t use_pbc;             /* 1: minimum image with pbc_box (pbc.py:44-56)                   */
+    double pbc_box[3];
+    int32_t out_type;            /* MDB_F32 (raw frames) or MDB_F64 (required with images)          */
+    void *out;                   /* DEVICE out [n_rows][out_pitch] of out_type, 3*n_vec used        */
+    int64_t out_pitch;
+} mdb_vectors_args;
+
+int mdb_vectors(const mdb_vectors_args *args, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense schedules: every origin of an arithmetic progression against a contiguous range of lags,

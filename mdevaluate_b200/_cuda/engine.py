@@ -545,3 +545,61 @@ def pack_images(images, n_atoms):
                                        C.c_void_p(st.cuda_stream)), 'mdb_images_pack')
     _count(1)
     return packed, int(worst.item())
+
+
+def vector_rows(store, rows, atoms_a, atoms_b, normed, pbc_box=None, stream=None):
+    """Rows of vectors between atoms (``mdb_vectors``) for the storage rows ``rows`` of ``store``: a new
+    :class:`DeviceStore` of ``len(rows)`` rows x ``n_vec`` "atoms" (float64 when the store carries image counts --
+    nojump frames are float64 -- else float32), row i = vectors of ``rows[i]``.  ``atoms_a`` / ``atoms_b``: int arrays
+    ``(n_vec,)`` or ``(m, n_vec)`` (mean over m)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = store.device
+    if store.coords.dtype != torch.float32:
+        raise _lib.CudaPathError('vector rows are built from float32 frame rows')
+    idx = []
+    for atoms in (atoms_a, atoms_b):
+        arr = np.ascontiguousarray(np.atleast_2d(np.asarray(atoms, dtype=np.int64)), dtype=np.int32)
+        if arr.ndim != 2 or arr.min() < 0 or arr.max() >= store.n_atoms:
+            raise IndexError('atom indices out of range')
+        idx.append(arr)
+    if idx[0].shape[1] != idx[1].shape[1]:
+        raise ValueError('atoms_a and atoms_b must select the same number of atoms')
+    n_vec = idx[0].shape[1]
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    f64 = store.has_images
+    out = torch.zeros((len(rows), row_pitch(n_vec)), dtype=torch.float64 if f64 else torch.float32, device=dev)
+    keep = [torch.from_numpy(a).to(dev) for a in idx] + [torch.from_numpy(rows).to(dev)]
+    a = _lib.VectorsArgs()
+    a.coords = store.coords.data_ptr()
+    a.pitch = store.coords.stride(0)
+    if f64:
+        if store.images is not None:
+            img, a.image_format = store.images, _lib.IMAGE_BYTES
+        elif store.images16 is not None:
+            img, a.image_format = store.images16, _lib.IMAGE_I16
+        else:
+            img, a.image_format = store.packed, _lib.IMAGE_PACKED
+        a.images = img.data_ptr()
+        a.img_pitch = img.stride(0)
+        if store.box_const is not None:
+            a.box_const[0], a.box_const[1], a.box_const[2] = store.box_const
+        else:
+            a.box = store.box.data_ptr()
+    a.rows = keep[2].data_ptr()
+    a.n_rows = len(rows)
+    a.atoms_a, a.m_a = keep[0].data_ptr(), idx[0].shape[0]
+    a.atoms_b, a.m_b = keep[1].data_ptr(), idx[1].shape[0]
+    a.n_vec = n_vec
+    a.normed = 1 if normed else 0
+    if pbc_box is not None:
+        a.use_pbc = 1
+        a.pbc_box[0], a.pbc_box[1], a.pbc_box[2] = (float(b) for b in pbc_box)
+    a.out_type = _lib.F64 if f64 else _lib.F32
+    a.out = out.data_ptr()
+    a.out_pitch = out.stride(0)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mdb_vectors(C.byref(a), C.c_void_p(st.cuda_stream)), 'mdb_vectors')
+    _count(1)
+    return DeviceStore(out, n_vec)

@@ -30,9 +30,9 @@ EXPORTS = (
     'mdb_dense_workspace_bytes', 'mdb_dense_corr', 'mdb_copy_rows_h2d',
     'mdb_corr_plan_create', 'mdb_corr_plan_run', 'mdb_corr_plan_launch', 'mdb_corr_plan_wait',
     'mdb_corr_plan_kernel_ms', 'mdb_corr_plan_sums', 'mdb_corr_plan_hist', 'mdb_corr_plan_sums_device',
-    'mdb_corr_plan_launches', 'mdb_corr_plan_destroy',
+    'mdb_corr_plan_launches', 'mdb_corr_plan_destroy', 'mdb_corr_plan_set_wait',
     'mdb_comm_create', 'mdb_comm_handle', 'mdb_comm_connect', 'mdb_comm_destroy',
-    'mdb_images_pack', 'mdb_nojump_apply_format',
+    'mdb_images_pack', 'mdb_nojump_apply_format', 'mdb_vectors',
 )
 
 
@@ -93,6 +93,16 @@ class DenseArgs(C.Structure):
     ]
 
 
+class VectorsArgs(C.Structure):
+    _fields_ = [
+        ('coords', C.c_void_p), ('pitch', C.c_int64), ('images', C.c_void_p), ('image_format', C.c_int32),
+        ('img_pitch', C.c_int64), ('box', C.c_void_p), ('box_const', C.c_double * 3), ('rows', C.c_void_p),
+        ('n_rows', C.c_int32), ('atoms_a', C.c_void_p), ('m_a', C.c_int32), ('atoms_b', C.c_void_p), ('m_b', C.c_int32),
+        ('n_vec', C.c_int32), ('normed', C.c_int32), ('use_pbc', C.c_int32), ('pbc_box', C.c_double * 3),
+        ('out_type', C.c_int32), ('out', C.c_void_p), ('out_pitch', C.c_int64),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -122,11 +132,13 @@ def _declare(lib):
     for name in ('mdb_corr_plan_sums', 'mdb_corr_plan_hist', 'mdb_corr_plan_sums_device'):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.mdb_corr_plan_launches.argtypes = [C.c_void_p]
+    lib.mdb_corr_plan_set_wait.argtypes = [C.c_void_p, C.c_int32]
     lib.mdb_corr_plan_destroy.argtypes = [C.c_void_p]
     lib.mdb_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]
     lib.mdb_comm_handle.argtypes = [C.c_void_p, C.c_void_p]
     lib.mdb_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
     lib.mdb_comm_destroy.argtypes = [C.c_void_p]
+    lib.mdb_vectors.argtypes = [C.POINTER(VectorsArgs), C.c_void_p]
     lib.mdb_images_pack.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_void_p]
     lib.mdb_nojump_apply_format.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32,

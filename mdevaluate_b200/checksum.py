@@ -55,7 +55,7 @@ def strip_comments(source):
     return ''.join(kept)
 
 
-def _feed(digest, arg):
+def _feed(digest, arg, _seen=None):
     if hasattr(arg, '__checksum__'):
         logger.debug('Checksum via __checksum__: %s', str(arg))
         digest.update(str(arg.__checksum__()).encode())
@@ -68,9 +68,12 @@ def _feed(digest, arg):
     elif isinstance(arg, FunctionType):
         digest.update(strip_comments(inspect.getsource(arg)).encode())
         free = inspect.getclosurevars(arg)
+        # the reference recurses into every referenced global; functions that refer to each other would never end
+        # there, so a function already on the way is fed once (identical digests for anything without such cycles)
+        seen = (_seen or ()) + (id(arg),)
         for value in {**free.nonlocals, **free.globals}.values():
-            if value is not arg:
-                _feed(digest, value)
+            if value is not arg and not (isinstance(value, FunctionType) and id(value) in seen):
+                _feed(digest, value, seen)
     elif isinstance(arg, functools.partial):
         logger.debug('Checksum via partial for %s', str(arg))
         _feed(digest, arg.func)

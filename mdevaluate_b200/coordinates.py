@@ -221,3 +221,110 @@ class Coordinates:
     @property
     def description(self):
         return getattr(self.atom_subset, 'description', '')
+
+
+class CoordinatesMap:
+    """A function applied to every frame of a Coordinates object (coordinates.py:332-393): ``map[i]`` is
+    ``function(coordinates[i])`` as a :class:`CoordinateFrame`.  ``shifted_correlation`` pulls such frames through the
+    generic frames protocol -- except for :func:`vectors`, whose rows are built on the device (``mdb_vectors``)."""
+
+    def __init__(self, coordinates, function):
+        from functools import partial
+        self.coordinates = coordinates
+        self.frames = self.coordinates.frames
+        self.atom_subset = self.coordinates.atom_subset
+        self.function = function
+        if isinstance(function, partial):
+            self._description = self.function.func.__name__
+        else:
+            self._description = self.function.__name__
+
+    def __iter__(self):
+        for frame in self.coordinates:
+            step = frame.step
+            frame = self.function(frame)
+            if not isinstance(frame, CoordinateFrame):
+                frame = frame.view(CoordinateFrame)
+                frame.coordinates = self
+                frame.step = step
+            yield frame
+
+    def __getitem__(self, item):
+        if isinstance(item, slice):
+            return self.__class__(self.coordinates[item], self.function)
+        frame = self.function(self.coordinates.__getitem__(item))
+        if not isinstance(frame, CoordinateFrame):
+            frame = frame.view(CoordinateFrame)
+        frame.coordinates = self
+        frame.step = item
+        return frame
+
+    def __len__(self):
+        return len(self.coordinates.frames)
+
+    def __checksum__(self):
+        from .checksum import checksum
+        return checksum(self.coordinates, self.function)
+
+    @property
+    def _slice(self):
+        return self.coordinates._slice
+
+    @property
+    def comm(self):
+        return self.coordinates.comm
+
+    @property
+    def description(self):
+        return '{}_{}'.format(self._description, self.coordinates.description)
+
+    @description.setter
+    def description(self, desc):
+        self._description = desc
+
+    @property
+    def nojump(self):
+        return CoordinatesMap(self.coordinates.nojump, self.function)
+
+
+def map_coordinates(func):
+    """Decorator: ``func(coordinates, **kwargs)`` becomes a :class:`CoordinatesMap` of ``func`` over the frames
+    (coordinates.py:464-468)."""
+    from functools import partial, wraps
+
+    @wraps(func)
+    def wrapped(coordinates, **kwargs):
+        return CoordinatesMap(coordinates, partial(func, **kwargs))
+    wrapped.frame_function = func
+    return wrapped
+
+
+def _pbc_diff(v1, v2, box):
+    """pbc.pbc_diff for no box / a rectangular box (pbc.py:34-56)."""
+    if box is None:
+        return v1 - v2
+    box = np.asarray(box)
+    if box.ndim != 1:
+        raise NotImplementedError('triclinic boxes are outside this package')
+    v = v1 - v2
+    s = v / box
+    return box * (s - s.round())
+
+
+@map_coordinates
+def vectors(coordinates, atoms_a, atoms_b, normed=False, box=None):
+    """Vectors between the atoms of two subsets (coordinates.py:524-563).  ``atoms_a`` / ``atoms_b`` are any NumPy
+    subscripts of a frame; a two-dimensional index list takes the mean over its first axis.  ``box`` (a box diagonal)
+    applies the minimum image convention.  Used as ``vectors(coords, atoms_a=..., atoms_b=..., normed=True)`` it is
+    the frames argument of ``shifted_correlation(partial(rotational_autocorrelation, order=2), ...)``; the rows are
+    then computed on the device."""
+    coords_a = coordinates[atoms_a]
+    if len(coords_a.shape) > 2:
+        coords_a = coords_a.mean(axis=0)
+    coords_b = coordinates[atoms_b]
+    if len(coords_b.shape) > 2:
+        coords_b = coords_b.mean(axis=0)
+    vec = _pbc_diff(coords_a, coords_b, box=box)
+    norm = np.linalg.norm(vec, axis=-1).reshape(-1, 1) if normed else 1
+    vec.reference = coords_a
+    return vec / norm

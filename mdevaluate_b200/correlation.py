@@ -18,6 +18,7 @@ strategy) raise ``NotImplementedError``; a missing CUDA library or device raises
 from __future__ import annotations
 
 import functools
+import weakref
 from itertools import chain
 
 import numpy as np
@@ -290,17 +291,62 @@ def _provider(frames, frame_ids):
             if len(res.lookup) > 32:
                 res.lookup.clear()
             res.lookup[key] = (store, rows)
-        _provider.base = (res, store)
+        _provider.base = (weakref.ref(res), weakref.ref(store))
         if not nojump:
             store = store.without_images()
         float32 = (not nojump) and res.dtype == np.float32
         return store, rows, res.n_atoms, float32, frames.comm
+    from .coordinates import CoordinatesMap
+    if isinstance(frames, CoordinatesMap):
+        mapped = _vector_map_provider(frames, ids)
+        if mapped is not None:
+            return mapped
     # generic frames protocol (coordinates.py:257-293): pull the needed frames through __getitem__
     _provider.base = None
     uniq, inverse = np.unique(ids.ravel(), return_inverse=True)
     store, float32 = _store_from_host_frames([frames[int(i)] for i in uniq])
     rows = inverse.reshape(ids.shape).astype(np.int32)
     return store, rows, store.n_atoms, float32, getattr(frames, 'comm', None)
+
+
+def _index_table(selector, n_atoms):
+    """A frame subscript (index list, 2-D index list, boolean mask, slice) as an int array ``(m, n_vec)``."""
+    probe = np.arange(n_atoms)[selector]
+    if probe.ndim == 1:
+        return probe[None, :]
+    if probe.ndim == 2:
+        return probe
+    raise NotImplementedError('atom selections of vectors() must be one- or two-dimensional')
+
+
+def _vector_map_provider(frames, ids):
+    """``coordinates.vectors`` mapped over a Coordinates object: the vector rows of the needed frames are built on
+    the device from the resident frame rows (``engine.vector_rows``).  None for any other map."""
+    from . import coordinates as crd
+    fn = frames.function
+    base = frames.coordinates
+    if not (isinstance(fn, functools.partial) and fn.func is crd.vectors.frame_function and not fn.args
+            and isinstance(base, crd.Coordinates)):
+        return None
+    kw = dict(fn.keywords)
+    if set(kw) - {'atoms_a', 'atoms_b', 'normed', 'box'} or 'atoms_a' not in kw or 'atoms_b' not in kw:
+        return None
+    box = kw.get('box')
+    if box is not None and np.ndim(box) != 1:
+        return None
+    res = base._resident()
+    if res.dtype != np.float32:
+        return None
+    nojump = base.mode == 'nojump'
+    uniq, inverse = np.unique(ids.ravel(), return_inverse=True)
+    store = res.store_for(uniq, nojump=nojump)
+    if not nojump:
+        store = store.without_images()
+    vec_store = engine.vector_rows(store, store.rows_for(uniq), _index_table(kw['atoms_a'], res.n_atoms),
+                                   _index_table(kw['atoms_b'], res.n_atoms), bool(kw.get('normed', False)), pbc_box=box)
+    _provider.base = None
+    rows = inverse.reshape(ids.shape).astype(np.int32)
+    return vec_store, rows, vec_store.n_atoms, not nojump, base.comm
 
 
 def _times(frames, idx):
@@ -537,7 +583,8 @@ def _run(frames, frame_ids, specs, select=None):
     p2p = getattr(comm, 'p2p', None) if comm is not None else None
     plan = _plan_for(store, rows, corr, select_dev, p2p)
     sums, hist = plan.run()
-    _run.last = (plan, _provider.base, float32) if (select is None and (comm is None or p2p is not None)) else None
+    _run.last = ((weakref.ref(plan), _provider.base, float32)
+                 if (select is None and (comm is None or p2p is not None) and _provider.base is not None) else None)
     if comm is not None:
         if p2p is None:      # no peer memory (gloo / IPC refused): the torch.distributed all-reduce
             from . import parallel
@@ -581,7 +628,9 @@ del _f
 # repeated calls: everything a call needs besides the kernel launch, remembered per (trajectory, function, schedule)
 # --------------------------------------------------------------------------------------------
 class _CachedCall:
-    __slots__ = ('res_ref', 'base_store', 'plan', 'spec', 'times', 'n_origins', 'float32', 'tuning', 'comm')
+    """Weak references only: the plan lives in its store's cache, the store in its resident, the resident on the
+    reader -- remembering a call must not keep gigabytes of HBM alive."""
+    __slots__ = ('res_ref', 'store_ref', 'plan_ref', 'spec', 'times', 'n_origins', 'float32', 'tuning', 'comm')
 
 
 _call_cache = {}
@@ -613,25 +662,26 @@ def _call_key(function, frames, index_distribution, segments, window, skip):
 
 def _cached_call(key, res, frames, average):
     entry = _call_cache.get(key)
-    if entry is None or entry.res_ref() is not res or entry.comm is not frames.comm:
+    if entry is None:
         return None
-    if entry.tuning != engine.tuning.key() or not res.serves(entry.base_store, frames.mode == 'nojump'):
+    store, plan = entry.store_ref(), entry.plan_ref()
+    if (entry.res_ref() is not res or entry.comm is not frames.comm or store is None or plan is None
+            or plan.handle is None or entry.tuning != engine.tuning.key()
+            or not res.serves(store, frames.mode == 'nojump')):
         del _call_cache[key]
         return None
-    sums, hist = entry.plan.run()
+    sums, hist = plan.run()
     n_atoms = res.n_atoms if entry.comm is None else entry.comm[1]
     values = entry.spec.finalize(sums, hist, n_atoms, entry.float32)
     return entry.times.copy(), _average(values, entry.n_origins, average)
 
 
 def _remember_call(key, res, frames, spec, times, n_origins):
-    import weakref
     last = getattr(_run, 'last', None)
-    if last is None or last[1] is None or last[1][0] is not res:
+    if last is None or last[1][0]() is not res:
         return
     entry = _CachedCall()
-    entry.res_ref = weakref.ref(res)
-    entry.plan, (_, entry.base_store), entry.float32 = last
+    entry.plan_ref, (entry.res_ref, entry.store_ref), entry.float32 = last
     entry.spec, entry.times, entry.n_origins = spec, np.array(times), n_origins
     entry.tuning, entry.comm = engine.tuning.key(), frames.comm
     if len(_call_cache) >= MAX_CACHED_CALLS:
@@ -639,9 +689,6 @@ def _remember_call(key, res, frames, spec, times, n_origins):
     _call_cache[key] = entry
 
 
-@autosave_data(nargs=2, kwargs_keys=(
-    'index_distribution', 'correlation', 'segments', 'window', 'skip', 'average'
-), version='shifted_correlation-1')
 def shifted_correlation(function, frames, index_distribution=log_indices, correlation=correlation,
                         segments=10, window=0.5, skip=None, average=False):
     """Calculate the time series of a correlation function over shifted time origins.
@@ -756,6 +803,14 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
     np.divide(result, count[bt], out=result, where=count[bt] != 0)
     result = np.moveaxis(result, 0, cdim)
     return times, result, count / len(origins)
+
+
+# the autosave decorator of the reference (correlation.py:83-85): result files are keyed by the version tag; the
+# source-based key of this package's own implementation is its name and version (like the functions above)
+_fixed_checksum(shifted_correlation, 1)
+shifted_correlation = autosave_data(nargs=2, kwargs_keys=(
+    'index_distribution', 'correlation', 'segments', 'window', 'skip', 'average'
+), version='shifted_correlation-1')(shifted_correlation)
 
 
 def shifted_correlation_multi(functions, frames, index_distribution=log_indices, segments=10, window=0.5,

@@ -259,11 +259,18 @@ __device__ __forceinline__ void store_result(const FinishDev &f, long long i, un
     }
 }
 
-// Last CTA through a ticket counter (all other CTAs have fenced their writes before taking theirs).
+// Last CTA through a ticket counter.  ONE system-scope fence per CTA: the barrier orders every thread's stores before
+// thread 0 at CTA scope, and thread 0's fence makes them visible system-wide before it takes its ticket (fences are
+// cumulative).  With a fence in every thread -- 5000 fences behind stores to mapped host memory -- this kernel took
+// 14 us (profiles/r2_launches_bench.csv); the last CTA fences again on the acquiring side.
 __device__ __forceinline__ bool last_cta(unsigned int *ticket, int *s_flag) {
-    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) *s_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const bool last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last) __threadfence_system();
+        *s_flag = last ? 1 : 0;
+    }
     __syncthreads();
     return *s_flag != 0;
 }
@@ -444,6 +451,7 @@ struct mdb_corr_plan {
     unsigned long long *comm_seq = nullptr;
     cudaStream_t last_stream = nullptr;
     bool pending = false;
+    int wait_mode = 0;                   // mdb_corr_plan_set_wait
     int grid = 1;
     cudaEvent_t events[2 * MDB_PLAN_TIME_SLOTS];
     bool have_events = false;
@@ -551,6 +559,9 @@ extern "C" int mdb_corr_plan_launch(mdb_corr_plan *pl, void *stream, int32_t tim
     MDB_CUDA_CHECK(cudaGetLastError());
     if (pl->hist_words)
         MDB_CUDA_CHECK(cudaMemcpyAsync(pl->hist_host, pl->dev.hist, pl->hist_words * 8, cudaMemcpyDeviceToHost, st));
+    if (pl->wait_mode == 2)
+        MDB_CUDA_CHECK(cudaMemcpyAsync(pl->sums_host, pl->fin.sums_dev, (size_t)pl->fin.n_sums * 8,
+                                       cudaMemcpyDeviceToHost, st));
     pl->last_stream = st;
     pl->pending = true;
     return MDB_OK;
@@ -560,6 +571,14 @@ extern "C" int mdb_corr_plan_wait(mdb_corr_plan *pl) {
     if (!pl) return fail(MDB_ERR_ARGUMENT, "plan is NULL");
     if (!pl->pending) return fail(MDB_ERR_ARGUMENT, "nothing was launched");
     pl->pending = false;
+    if (pl->wait_mode != 0) {
+        MDB_CUDA_CHECK(cudaStreamSynchronize(pl->last_stream));
+        if (*pl->flag_host == kFlagTimeout) {
+            *pl->flag_host = 0;
+            return fail(MDB_ERR_TIMEOUT, "a peer GPU did not deliver its partial sums in time");
+        }
+        return MDB_OK;
+    }
     // the finish kernel raises the flag through the mapped block as its last store: poll it (no driver call on the
     // fast path); look at the stream now and then so that a failed launch cannot hang the caller
     const auto t0 = std::chrono::steady_clock::now();
@@ -586,6 +605,16 @@ extern "C" int mdb_corr_plan_wait(mdb_corr_plan *pl) {
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     if (pl->hist_words) MDB_CUDA_CHECK(cudaStreamSynchronize(pl->last_stream));     // the histogram's D2H copy
+    return MDB_OK;
+}
+
+extern "C" int mdb_corr_plan_set_wait(mdb_corr_plan *pl, int32_t mode) {
+    if (!pl || mode < 0 || mode > 2) return fail(MDB_ERR_ARGUMENT, "mode must be 0, 1 or 2");
+    if (pl->pending) return fail(MDB_ERR_ARGUMENT, "a run is pending");
+    pl->wait_mode = mode;
+    void *mapped = nullptr;
+    MDB_CUDA_CHECK(cudaHostGetDevicePointer(&mapped, pl->host_block, 0));
+    pl->fin.sums_host = mode == 2 ? nullptr : reinterpret_cast<double *>(static_cast<char *>(mapped) + 64);
     return MDB_OK;
 }
 

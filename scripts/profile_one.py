@@ -15,8 +15,11 @@ block, box, times = random_walk_device(N, T, seed=1, box=box_length(N), device=d
 coords = md.Coordinates.from_arrays(block, box, times, n_atoms=N)
 c = md.correlation
 bins = np.linspace(0, 3.0, 501)
-fn = {'vh': partial(c.van_hove_self, bins=bins), 'ng': c.non_gaussian, 'msd': c.msd, 'isf': partial(c.isf, q=22.7)}[name]
+fns = {'vh': partial(c.van_hove_self, bins=bins), 'ng': c.non_gaussian, 'msd': c.msd, 'isf': partial(c.isf, q=22.7)}
 engine.profile_kernels(True)
 for _ in range(3):
-    t, r = c.shifted_correlation(fn, coords.nojump, segments=S)
+    if name == 'fused':
+        t, r = c.shifted_correlation_multi({'vh': fns['vh'], 'a2': fns['ng']}, coords.nojump, segments=S)
+    else:
+        t, r = c.shifted_correlation(fns[name], coords.nojump, segments=S)
     print(name, engine.last_kernel_ms())

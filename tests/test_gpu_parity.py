@@ -1038,3 +1038,37 @@ def test_repeated_calls_reuse_their_plan(small, md, tuning):
     assert not np.array_equal(r5, r1)
     coords.frames.nojump_matrixes = None
     coords.frames._nojump_matrixes = None
+
+
+def test_vectors_and_rotational_autocorrelation_on_the_device(golden, md):
+    """coordinates.vectors mapped over the frames + rotational_autocorrelation (coordinates.py:524-563,
+    correlation.py:223-236): the vector rows are built on the device (mdb_vectors) in the reference's arithmetic --
+    float64 from the nojump frames, float32 with the minimum image from raw frames -- and feed the Legendre kernel."""
+    from mdevaluate_b200._cuda import engine
+    from mdevaluate_b200.coordinates import vectors
+    g = golden('vectors')
+    c = md.correlation
+    coords = md.Coordinates(md.MemoryReader(g['pos'], g['box'], g['times']))
+    launches = engine.launches()
+    vec_nj = vectors(coords.nojump, atoms_a=g['oxygen'], atoms_b=g['hydrogens'], normed=True)
+    for order in (1, 2):
+        t, r = c.shifted_correlation(partial(c.rotational_autocorrelation, order=order), vec_nj, segments=9, window=0.4)
+        np.testing.assert_array_equal(t, g['t'])
+        close(r, g['rot%d_nojump' % order], rtol=1e-11, atol=1e-13)
+    vec_raw = vectors(coords, atoms_a=g['oxygen'], atoms_b=g['oxygen'] + 1, normed=True, box=g['box'])
+    _, r = c.shifted_correlation(partial(c.rotational_autocorrelation, order=2), vec_raw, segments=9, window=0.4)
+    close(r, g['rot2_raw'], atol=1e-6)
+    assert engine.launches() > launches
+    # the rows themselves
+    res = coords._resident()
+    store = res.store_for(np.arange(len(coords)), nojump=True)
+    rows = store.rows_for(np.array([0, 17, 139]))
+    got = engine.vector_rows(store, rows, g['oxygen'][None, :], g['hydrogens'], True)
+    assert got.coords.dtype.is_floating_point and got.coords.element_size() == 8
+    np.testing.assert_allclose(got.coords[:, :150].cpu().numpy().reshape(3, 50, 3), g['vec_nojump'], rtol=1e-15, atol=0)
+    raw = engine.vector_rows(store.without_images(), rows, g['oxygen'][None, :], (g['oxygen'] + 1)[None, :], True,
+                             pbc_box=g['box'])
+    assert raw.coords.element_size() == 4
+    np.testing.assert_allclose(raw.coords[:, :150].cpu().numpy().reshape(3, 50, 3), g['vec_raw'], rtol=2e-7, atol=0)
+    # host frames of the map agree with the device rows (nojump frames come back through mdb_nojump_apply)
+    np.testing.assert_allclose(np.asarray(vec_nj[17]), g['vec_nojump'][1], rtol=1e-15, atol=0)

@@ -297,3 +297,22 @@ def test_dense_slab_plan():
             (0, 2048), (2048, 4096), (4096, 5000)]
     finally:
         c.DENSE_SLAB_ATOMS = None
+
+
+def test_vectors_map_on_raw_frames_matches_the_reference(golden):
+    """coordinates.vectors through CoordinatesMap on raw (float32) frames, on the host: the reference's numbers
+    (tests/golden/make_golden_vectors.py), minimum image included."""
+    import mdevaluate_b200 as md
+    from mdevaluate_b200.coordinates import CoordinatesMap, vectors
+    g = golden('vectors')
+    coords = md.Coordinates(md.MemoryReader(g['pos'], g['box'], g['times']))
+    vec = vectors(coords, atoms_a=g['oxygen'], atoms_b=g['oxygen'] + 1, normed=True, box=g['box'])
+    assert isinstance(vec, CoordinatesMap) and len(vec) == len(coords)
+    for k, i in enumerate((0, 17, 139)):
+        frame = vec[i]
+        assert frame.step == i and frame.dtype == np.float32
+        np.testing.assert_array_equal(np.asarray(frame), g['vec_raw'][k])
+    unnormed = vectors(coords, atoms_a=g['oxygen'], atoms_b=g['oxygen'] + 2, box=g['box'])
+    for k, i in enumerate((5, 100)):
+        np.testing.assert_array_equal(np.asarray(unnormed[i]), g['vec_raw_unnormed'][k])
+    assert vec[10:]._slice == slice(10, None) and vec.description.startswith('vectors')
