@@ -715,6 +715,31 @@ def config2_leg(a, torch, md, c, engine, orc, dev, peak):
     other['van_hove_self+non_gaussian f64 chain'] = {'kernel_ms': k, 'frac': alg / (k * 1e-3) / 1e9 / peak}
     out['other_kernels'] = other
 
+    # dense schedules (BASELINE config 5's shape: every frame an origin, linear lags, average=True) on the first 2 000
+    # frames of the same rows: the tiled kernel (csrc/dense_kernels.cu), bound by shared memory / FP32 / XU, not by HBM
+    try:
+        Td = 2000
+        dcoords = md.Coordinates.from_arrays(block[:Td], box, times[:Td], n_atoms=N)
+        lin = lambda lo, hi: np.arange(lo, hi)
+        dense = {}
+        for name, f in (('msd', c.msd), ('isf', fn)):
+            c.shifted_correlation(f, dcoords.nojump, segments=8, window=0.5, average=True, index_distribution=lin)
+            torch.cuda.synchronize()
+            ev[0].record()
+            _, r = c.shifted_correlation(f, dcoords.nojump, segments=Td // 2, window=0.5, average=True,
+                                         index_distribution=lin)
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1])
+            dense[name] = {'ms': ms, 'evals_per_s': float(N) * (Td // 2) * len(r) / (ms * 1e-3)}
+        dense['workload'] = 'dense: %d atoms, %d origins x %d linear lags, average=True (the call, scan excluded)' % (
+            N, Td // 2, Td // 2)
+        dense['full_size'] = 'profiles/r2_config5_full.json: 200 000 atoms x 50 000 frames from page-locked host memory'
+        out['dense'] = dense
+        del dcoords
+    except Exception as exc:
+        out['dense'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
+
     # parity of the sub-block against the oracle
     n_sub = 4096
     sub = block[:, :3 * n_sub].cpu().numpy().reshape(T, n_sub, 3)

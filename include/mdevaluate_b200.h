@@ -61,8 +61,9 @@ typedef struct mdb_tuning {
     int32_t isf_float64;     /* 1: ISF displacements through the float64 chain (default float32, see DESIGN)  */
     int32_t hist_float64;    /* 1: van Hove (and fused van Hove + alpha_2) displacements in float64           */
     int32_t scan_direct;     /* 1: register-load variant of the jump scan instead of the bulk-copy ring       */
-    int32_t dense_stage_cta; /* 1: CTA-wide staging loop of the dense kernel instead of warp-per-row          */
-    int32_t reserved[2];
+    int32_t dense_stage_cta; /* 1: CTA-wide staging loop of the float64 dense kernel instead of warp-per-row  */
+    int32_t dense_float64;   /* 1: dense schedules through the float64 tile (default: float32 offsets, v2)    */
+    int32_t reserved[1];
 } mdb_tuning;
 
 /* coordinate element type */
@@ -143,6 +144,10 @@ typedef struct mdb_corr_args {
     const int16_t *images16;     /* DEVICE [n_rows][img16_pitch] MDB_IMAGE_I16 rows, or NULL      */
     int64_t img16_pitch;         /* int16 elements per row, >= 3*n_atoms                         */
     mdb_tuning tuning;
+    int32_t n_segments;          /* 0 / 1: `select` is a mask.  > 1 (MDB_SUM_SINC alone): byte j of `select` names the
+                                    sub-ensemble 1..n_segments atom j belongs to for that origin (0 = none); ONE pass
+                                    accumulates all of them (multi_subensemble_correlation, correlation.py:38-81):
+                                    sums[((s*n_lags + l)*n_segments + k)*3 + c]                     */
 } mdb_corr_args;
 
 int mdb_corr_workspace_bytes(const mdb_corr_args *args, size_t *bytes);

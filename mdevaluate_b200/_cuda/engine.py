@@ -37,7 +37,8 @@ def row_pitch(n_atoms):
 class Tuning:
     """Explicit kernel switches (``mdb_tuning`` of the C ABI); 0 = the measured default.  Process-wide, read at every
     launch / plan creation.  ``engine.tuning.isf_float64 = 1`` e.g. sends the ISF through the float64 chain."""
-    FIELDS = ('ring_stages', 'atom_blocks', 'isf_float64', 'hist_float64', 'scan_direct', 'dense_stage_cta')
+    FIELDS = ('ring_stages', 'atom_blocks', 'isf_float64', 'hist_float64', 'scan_direct', 'dense_stage_cta',
+              'dense_float64')
 
     def __init__(self):
         for f in self.FIELDS:
@@ -186,7 +187,7 @@ def last_kernel_ms():
     return plan.kernel_ms(time_slot)
 
 
-def _fill_corr_args(a, store, rows_dev, S, L, spec, select, edges_dev):
+def _fill_corr_args(a, store, rows_dev, S, L, spec, select, edges_dev, n_segments=1):
     """The part of mdb_corr_args that describes the rows and the request (outputs are set by the caller)."""
     torch = _lib.require_cuda()
     a.coords = store.coords.data_ptr()
@@ -224,6 +225,7 @@ def _fill_corr_args(a, store, rows_dev, S, L, spec, select, edges_dev):
     a.dx = spec.dx
     a.edges = edges_dev.data_ptr() if edges_dev is not None else None
     tuning.fill(a.tuning)
+    a.n_segments = int(n_segments)
 
 
 def _rows_on_device(store, rows):
@@ -292,7 +294,7 @@ class CorrPlan:
     histogram and a page-locked host block; :meth:`run` is two kernel launches and returns NumPy views of that host
     block (valid until the next run).  With ``comm`` (a :class:`Comm`) the sums come back added over the GPUs."""
 
-    def __init__(self, store, rows, spec, select=None, comm=None):
+    def __init__(self, store, rows, spec, select=None, comm=None, n_segments=1):
         torch = _lib.require_cuda()
         lib = _lib.load()
         rows = np.ascontiguousarray(rows, dtype=np.int32)
@@ -304,7 +306,7 @@ class CorrPlan:
         self._keep = (_rows_on_device(store, rows)[0], _edges_on_device(store, spec), select, store.coords,
                       store.images, store.packed, store.images16, store.box)
         a = _lib.CorrArgs()
-        _fill_corr_args(a, store, self._keep[0], S, L, spec, select, self._keep[1])
+        _fill_corr_args(a, store, self._keep[0], S, L, spec, select, self._keep[1], n_segments)
         handle = C.c_void_p()
         with torch.cuda.device(store.device):
             _lib.check(lib.mdb_corr_plan_create(C.byref(a), comm.handle if comm is not None else None,
@@ -313,9 +315,11 @@ class CorrPlan:
         self._lib = lib
         self._stream_of = torch.cuda.current_stream
         self._device = store.device
-        n = S * L * 3
+        n_seg = max(1, int(n_segments))
+        n = S * L * 3 * n_seg
         ptr = lib.mdb_corr_plan_sums(handle)
-        self.sums = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)).reshape(S, L, 3)
+        self.sums = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,))
+        self.sums = self.sums.reshape((S, L, 3) if n_seg == 1 else (S, L, n_seg, 3))
         self.hist = None
         if spec.flags & _lib.HIST:
             hp = lib.mdb_corr_plan_hist(handle)

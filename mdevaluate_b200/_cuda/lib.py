@@ -44,7 +44,7 @@ class Tuning(C.Structure):
     """mdb_tuning: explicit kernel switches, 0 = the measured default."""
     _fields_ = [('ring_stages', C.c_int32), ('atom_blocks', C.c_int32), ('isf_float64', C.c_int32),
                 ('hist_float64', C.c_int32), ('scan_direct', C.c_int32), ('dense_stage_cta', C.c_int32),
-                ('reserved', C.c_int32 * 2)]
+                ('dense_float64', C.c_int32), ('reserved', C.c_int32 * 1)]
 
 
 class CorrArgs(C.Structure):
@@ -58,7 +58,7 @@ class CorrArgs(C.Structure):
         ('sums', C.c_void_p), ('hist', C.c_void_p),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
         ('packed', C.c_void_p), ('packed_pitch', C.c_int64), ('images16', C.c_void_p), ('img16_pitch', C.c_int64),
-        ('tuning', Tuning),
+        ('tuning', Tuning), ('n_segments', C.c_int32),
     ]
 
 

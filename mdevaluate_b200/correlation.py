@@ -550,6 +550,7 @@ def _spec_key(corr):
 
 
 MAX_PLANS_PER_STORE = 16
+MULTI_SEGMENTS_PER_PASS = 4      # sub-ensembles one kernel pass accumulates (shared memory: 16 KiB each); 1 = one pass each
 
 
 def _plan_for(store, rows, corr, select_dev, p2p):
@@ -568,10 +569,11 @@ def _plan_for(store, rows, corr, select_dev, p2p):
     return plan
 
 
-def _run(frames, frame_ids, specs, select=None):
+def _run(frames, frame_ids, specs, select=None, n_segments=1):
     """Kernel launch + shard reduction; returns host ``(sums, hist, n_atoms_global, float32)``.
-    ``select`` is an optional host uint8 ``(S, N)`` per-origin atom mask.  ``sums`` / ``hist`` are views of the
-    plan's page-locked result block: read them before the next call."""
+    ``select`` is an optional host uint8 ``(S, N)`` per-origin atom mask -- or, with ``n_segments`` > 1, the number
+    1..n_segments of the sub-ensemble every atom belongs to (0: none); ``sums`` is then ``(S, L, n_segments, 3)``.
+    ``sums`` / ``hist`` are views of the plan's page-locked result block: read them before the next call."""
     corr = _merged_spec(specs)
     store, rows, n_atoms, float32, comm = _provider(frames, frame_ids)
     select_dev = None
@@ -581,7 +583,10 @@ def _run(frames, frame_ids, specs, select=None):
         padded[:, :select.shape[1]] = select
         select_dev = torch.from_numpy(padded).to(store.device)
     p2p = getattr(comm, 'p2p', None) if comm is not None else None
-    plan = _plan_for(store, rows, corr, select_dev, p2p)
+    if n_segments > 1:
+        plan = engine.CorrPlan(store, rows, corr, select=select_dev, comm=p2p, n_segments=n_segments)
+    else:
+        plan = _plan_for(store, rows, corr, select_dev, p2p)
     sums, hist = plan.run()
     _run.last = ((weakref.ref(plan), _provider.base, float32)
                  if (select is None and (comm is None or p2p is not None) and _provider.base is not None) else None)
@@ -773,17 +778,40 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
     counts = np.array([[c for _, c in row] for row in per_origin]).reshape((len(origins),) + sel_shape)
     counts = _global_counts(frames, counts)
     values = None
-    for k, index in enumerate(np.ndindex(sel_shape)):
-        masks = np.stack([row[k][0] for row in per_origin])
+    indices = list(np.ndindex(sel_shape))
+
+    def put(index, sums, hist, float32):
+        nonlocal values
         cnt = counts[(slice(None),) + index]
-        sums, hist, _, float32 = _run(frames, frame_ids, [spec], select=masks)
         safe = np.where(cnt == 0, 1, cnt)
         vals = spec.finalize(sums, hist, safe, float32)                  # (S, L[, B])
         vals = np.where((cnt == 0).reshape((-1,) + (1,) * (vals.ndim - 1)), 0, vals)   # ``... else 0``
         if values is None:
             values = np.zeros((len(origins),) + sel_shape + vals.shape[1:], dtype=np.float64)
         values[(slice(None),) + index] = vals
-    assert n_sub == k + 1
+
+    # ONE pass for several sub-ensembles (ISF, disjoint selections -- e.g. radial shells): the selector table holds
+    # the number of the sub-ensemble of every atom and the kernel keeps one accumulator per sub-ensemble
+    # (mdb_corr_args.n_segments).  Anything else: one masked pass per sub-ensemble.
+    todo = list(range(n_sub))
+    all_masks = np.stack([np.stack([row[k][0] for row in per_origin]) for k in range(n_sub)])     # (n_sub, S, N)
+    if spec.name == 'isf' and n_sub > 1 and MULTI_SEGMENTS_PER_PASS > 1 and int(all_masks.sum(axis=0).max()) <= 1:
+        try:
+            for g0 in range(0, n_sub, MULTI_SEGMENTS_PER_PASS):
+                group = list(range(g0, min(n_sub, g0 + MULTI_SEGMENTS_PER_PASS)))
+                seg = np.zeros(all_masks.shape[1:], dtype=np.uint8)
+                for j, k in enumerate(group):
+                    seg[all_masks[k] != 0] = j + 1
+                sums, _, _, float32 = _run(frames, frame_ids, [spec], select=seg, n_segments=max(2, len(group)))
+                for j, k in enumerate(group):
+                    put(indices[k], sums[:, :, j, :], None, float32)
+                    todo.remove(k)
+        except CudaPathError as exc:
+            if 'status 3' not in str(exc):          # MDB_ERR_UNSUPPORTED: this store / box has no one-pass kernel
+                raise
+    for k in todo:
+        sums, hist, _, float32 = _run(frames, frame_ids, [spec], select=all_masks[k])
+        put(indices[k], sums, hist, float32)
     # values: (S, *sel_shape, L, ...); the reference's per-origin array is (L, *sel_shape, ...)
     cdim = len(sel_shape)
     if not average:

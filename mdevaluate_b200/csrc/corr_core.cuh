@@ -42,6 +42,7 @@ struct CorrDev {
     const uint8_t *select;   // [S][sel_pitch] 1 = atom takes part for origin s (sub-ensembles), or nullptr
     long long sel_pitch;
     int n_chunks, n_ablocks;
+    int n_segments;          // > 1: the select bytes name one of n_segments sub-ensembles per atom (ISF, one pass)
     double q2;
     int f32d;                // float32 displacements (ISF alone; van Hove [+ alpha_2] with uniform bins): uniform
     float q2f;               // float(q^2) and the negated (scaled) box as the packed pairs (x,y) (z,x) (y,z):

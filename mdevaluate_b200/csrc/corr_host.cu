@@ -58,7 +58,19 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
     const int kf = kernel_flags(a->flags);
     const int nv_kernel = ((kf & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) ? 1 : 0) + ((kf & MDB_SUM_R4) ? 1 : 0) +
                           ((kf & MDB_SUM_SINC) ? 1 : 0);
-    const size_t acc_smem = (size_t)nv_kernel * kLagChunk * kThreads * sizeof(double);
+    const int n_seg = a->n_segments > 1 ? a->n_segments : 1;
+    if (n_seg > 1) {
+        if (a->flags != MDB_SUM_SINC || !a->select || n_seg > 63)
+            return fail(MDB_ERR_UNSUPPORTED, "n_segments > 1 goes with MDB_SUM_SINC alone, a select table and at most 63 "
+                                             "sub-ensembles");
+        if (!bulk_coords || !any_images || a->box || a->tuning.isf_float64)
+            return fail(MDB_ERR_UNSUPPORTED, "several sub-ensembles per pass need the float32-displacement ISF kernel "
+                                             "(nojump rows with one constant box, aligned float32 rows)");
+        for (int d = 0; d < 3; ++d)
+            if ((double)(float)a->box_const[d] != a->box_const[d])
+                return fail(MDB_ERR_UNSUPPORTED, "several sub-ensembles per pass need a float32-representable box");
+    }
+    const size_t acc_smem = (size_t)nv_kernel * kLagChunk * kThreads * sizeof(double) * n_seg;
     for (int attempt = 0; attempt < 2; ++attempt) {
         const size_t stage_bytes = kCoordTileBytes + img_tile_bytes(plan->img);
         // ring depth: what fits next to the accumulators / histogram with two CTAs per SM, 3..8 stages
@@ -70,6 +82,8 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
         if (plan->stages > kMaxStages) plan->stages = kMaxStages;
         if (a->tuning.ring_stages >= 2 && a->tuning.ring_stages <= plan->stages) plan->stages = a->tuning.ring_stages;
         if (plan->stages >= 3 || !plan->bulk) break;
+        if (n_seg > 1)
+            return fail(MDB_ERR_UNSUPPORTED, "%d sub-ensembles per pass do not fit into shared memory", n_seg);
         // huge histograms: fall back to the direct-load kernel, which reads byte (or int16) counts
         plan->bulk = false;
         if (plan->img == IMG_PACKED) {
@@ -78,6 +92,8 @@ int make_plan(const mdb_corr_args *a, Plan *plan) {
                                                   "kernel needs the byte image rows", a->n_bins);
         }
     }
+    if (n_seg > 1 && !plan->bulk)
+        return fail(MDB_ERR_UNSUPPORTED, "several sub-ensembles per pass need the bulk-copy kernel (aligned rows)");
     const size_t bulk_smem = plan->stages * (size_t)(kCoordTileBytes + img_tile_bytes(plan->img)) + acc_smem + hist_smem;
     plan->smem = plan->bulk ? bulk_smem : hist_smem;
     if (plan->smem > 220 * 1024)
@@ -162,6 +178,7 @@ CorrDev device_args(const mdb_corr_args *a, const Plan &plan) {
     p.sel_pitch = a->sel_pitch;
     p.n_chunks = plan.n_chunks;
     p.n_ablocks = plan.n_ablocks;
+    p.n_segments = a->n_segments > 1 ? a->n_segments : 1;
     p.q2 = a->q * a->q;
     // Float32 displacements (process_tile_f32d) on rows with one float32-representable box (what trajectory formats
     // store): the ISF alone, van Hove alone and van Hove + alpha_2 with uniform bins -- unless the caller asks for
@@ -209,7 +226,8 @@ int launch_corr(const CorrDev &p, const Plan &plan, const mdb_corr_args *a, cuda
 struct FinishDev {
     const double *partial;         // [n_sums][n_ablocks] (component innermost: see index below)
     int n_ablocks;
-    long long n_sums;              // S*L*3
+    int comps;                     // sums per (origin, lag): 3, or 3 * sub-ensembles
+    long long n_sums;              // S*L*comps
     unsigned long long *hist;      // device counts of this shard, replaced by the total over the shards; or null
     long long n_hist;
     double *sums_dev;              // device out
@@ -241,10 +259,10 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
 // The value of word i of this shard: a sum of the atom-block partials in fixed order, or a histogram count.
 __device__ __forceinline__ unsigned long long local_word(const FinishDev &f, long long i) {
     if (i < f.n_sums) {
-        const long long sl = i / 3;
-        const int comp = (int)(i - 3 * sl);
+        const long long sl = i / f.comps;
+        const int comp = (int)(i - f.comps * sl);
         double v = 0.0;
-        for (int ab = 0; ab < f.n_ablocks; ++ab) v += f.partial[(sl * f.n_ablocks + ab) * 3 + comp];
+        for (int ab = 0; ab < f.n_ablocks; ++ab) v += f.partial[(sl * f.n_ablocks + ab) * f.comps + comp];
         return (unsigned long long)__double_as_longlong(v);
     }
     return f.hist[i - f.n_sums];
@@ -368,7 +386,8 @@ extern "C" int mdb_corr_workspace_bytes(const mdb_corr_args *a, size_t *bytes) {
     if (int rc = make_plan(a, &plan)) return rc;
     if (!bytes) return fail(MDB_ERR_ARGUMENT, "bytes is NULL");
     // partial sums of the atom blocks + the ticket counters of the finish kernel
-    *bytes = (size_t)a->n_origins * a->n_lags * plan.n_ablocks * 3 * sizeof(double) + 16;
+    const int n_seg = a->n_segments > 1 ? a->n_segments : 1;
+    *bytes = (size_t)a->n_origins * a->n_lags * plan.n_ablocks * 3 * n_seg * sizeof(double) + 16;
     return MDB_OK;
 }
 
@@ -380,7 +399,8 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     if (!a->sums) return fail(MDB_ERR_ARGUMENT, "sums is required");
     const bool hist = (a->flags & MDB_HIST) != 0;
     if (hist && !a->hist) return fail(MDB_ERR_ARGUMENT, "hist is required with MDB_HIST");
-    const size_t partial_bytes = (size_t)a->n_origins * a->n_lags * plan.n_ablocks * 3 * sizeof(double);
+    const int n_seg = a->n_segments > 1 ? a->n_segments : 1;
+    const size_t partial_bytes = (size_t)a->n_origins * a->n_lags * plan.n_ablocks * 3 * n_seg * sizeof(double);
     if (!a->workspace || a->workspace_bytes < partial_bytes + 16)
         return fail(MDB_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", partial_bytes + 16,
                     a->workspace_bytes);
@@ -401,7 +421,8 @@ extern "C" int mdb_shifted_corr(const mdb_corr_args *a, void *stream) {
     memset(&f, 0, sizeof(f));
     f.partial = p.partial;
     f.n_ablocks = plan.n_ablocks;
-    f.n_sums = (long long)a->n_origins * a->n_lags * 3;
+    f.comps = 3 * n_seg;
+    f.n_sums = (long long)a->n_origins * a->n_lags * 3 * n_seg;
     f.sums_dev = a->sums;
     f.ticket = ticket;
     finish_kernel<<<finish_grid(f.n_sums), 256, 0, st>>>(f);
@@ -475,7 +496,8 @@ extern "C" int mdb_corr_plan_create(const mdb_corr_args *a, mdb_comm *comm, mdb_
     pl->comm = comm;
     cudaGetDevice(&pl->device);
     const bool hist = (a->flags & MDB_HIST) != 0;
-    const size_t n_sums = (size_t)a->n_origins * a->n_lags * 3;
+    const int n_seg = a->n_segments > 1 ? a->n_segments : 1;
+    const size_t n_sums = (size_t)a->n_origins * a->n_lags * 3 * n_seg;
     pl->hist_words = hist ? (size_t)a->n_origins * a->n_lags * a->n_bins : 0;
     const size_t partial_bytes = n_sums * plan.n_ablocks * sizeof(double);
     const size_t dev_bytes = partial_bytes + n_sums * 8 + pl->hist_words * 8 + 64;
@@ -503,6 +525,7 @@ extern "C" int mdb_corr_plan_create(const mdb_corr_args *a, mdb_comm *comm, mdb_
     memset(&f, 0, sizeof(f));
     f.partial = pl->dev.partial;
     f.n_ablocks = plan.n_ablocks;
+    f.comps = 3 * n_seg;
     f.n_sums = (long long)n_sums;
     f.hist = pl->dev.hist;
     f.n_hist = 0;

@@ -288,8 +288,10 @@ __device__ __forceinline__ void eval_group(const CorrDev &p, const double (&u0)[
     }
 }
 
-// Which atoms of group g take part: they exist (tail of the shard) and, for sub-ensemble launches,
-// the selector of origin s picked them (one byte per atom, four atoms = one 32-bit word).
+// Which atoms of group g take part: they exist (tail of the shard) and, for sub-ensemble launches, the selector of
+// origin s picked them (one byte per atom, four atoms = one 32-bit word).  Bits 0..3: atom a takes part; bits
+// 4+6a .. 9+6a: the byte itself (1..63) -- the sub-ensemble the atom belongs to when ONE pass serves several of them
+// (p.n_segments > 1, multi_subensemble_correlation); with a plain mask the byte is 1.
 __device__ __forceinline__ uint32_t group_mask(const CorrDev &p, int s, int g) {
     const int nv = max(0, min(4, p.n_atoms - 4 * g));
     uint32_t m = (1u << nv) - 1u;
@@ -297,6 +299,7 @@ __device__ __forceinline__ uint32_t group_mask(const CorrDev &p, int s, int g) {
         const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p.select + (long long)s * p.sel_pitch) + g);
         m &= ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) |
              ((w & 0xff000000u) ? 8u : 0u);
+        m |= ((w & 0x3fu) << 4) | (((w >> 8) & 0x3fu) << 10) | (((w >> 16) & 0x3fu) << 16) | (((w >> 24) & 0x3fu) << 22);
     }
     return m;
 }
@@ -347,10 +350,12 @@ __device__ __forceinline__ void load_rows(const CorrDev &p, const CtaWork &w, in
 }
 
 // CTA epilogue: one block reduction, partial sums out, histogram flush.  Called by the kThreads
-// compute threads only; `sync` is the barrier that joins exactly those threads.
+// compute threads only; `sync` is the barrier that joins exactly those threads.  `seg` / `n_seg`: the sub-ensemble
+// these accumulators belong to (0 / 1 for ordinary launches).
 template <int FLAGS, typename Sync>
 __device__ __forceinline__ void cta_epilogue(const CorrDev &p, const CtaWork &w, int tid, Accum<FLAGS> &acc,
-                                             double (*s_red)[kLagChunk * 3], const unsigned int *s_hist, Sync sync) {
+                                             double (*s_red)[kLagChunk * 3], const unsigned int *s_hist, Sync sync,
+                                             int seg = 0, int n_seg = 1) {
     constexpr bool kR2 = (FLAGS & (MDB_SUM_R2 | MDB_SUM_LEGENDRE)) != 0;
     constexpr bool kR4 = (FLAGS & MDB_SUM_R4) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
@@ -376,9 +381,9 @@ __device__ __forceinline__ void cta_epilogue(const CorrDev &p, const CtaWork &w,
 #pragma unroll
         for (int wi = 0; wi < kWarps; ++wi) v += s_red[wi][tid];
         const int k = tid / 3, comp = tid - 3 * k;
-        p.partial[(((long long)w.s * p.L + w.l0 + k) * p.n_ablocks + w.ab) * 3 + comp] = v;
+        p.partial[((((long long)w.s * p.L + w.l0 + k) * p.n_ablocks + w.ab) * n_seg + seg) * 3 + comp] = v;
     }
-    if (kHist) {
+    if (kHist && seg == 0) {
         for (int i = tid; i < w.nl * p.n_bins; i += kThreads) {
             const unsigned int cnt = s_hist[i];
             if (cnt) {
@@ -387,6 +392,7 @@ __device__ __forceinline__ void cta_epilogue(const CorrDev &p, const CtaWork &w,
             }
         }
     }
+    if (n_seg > 1) sync();                 // s_red is reused by the next sub-ensemble
 }
 
 #if MDB_CORR_PART == 0
@@ -666,7 +672,20 @@ __device__ __forceinline__ void process_tile_f32d(const CorrDev &p, Ring &ring, 
                 v2 = (vmask & 4u) ? v2 : 0.0f;
                 v3 = (vmask & 8u) ? v3 : 0.0f;
             }
-            col[(kR2 ? 2 : 0) * kThreads] += (double)((v0 + v1) + (v2 + v3));
+            if (MASKED && FLAGS == MDB_SUM_SINC && p.n_segments > 1) {
+                // several sub-ensembles in one pass: atom a adds to the accumulator of its sub-ensemble (the byte of
+                // the selector, carried in vmask); column layout [lag][sub-ensemble][thread]
+                const uint32_t s0 = (vmask >> 4) & 63u, s1 = (vmask >> 10) & 63u, s2 = (vmask >> 16) & 63u,
+                               s3 = (vmask >> 22) & 63u;
+                double *seg_col = s_acc + (size_t)k * p.n_segments * kThreads + tid;
+                for (uint32_t j = 1; j <= (uint32_t)p.n_segments; ++j) {
+                    const float part = ((s0 == j ? v0 : 0.0f) + (s1 == j ? v1 : 0.0f)) +
+                                       ((s2 == j ? v2 : 0.0f) + (s3 == j ? v3 : 0.0f));
+                    seg_col[(size_t)(j - 1) * kThreads] += (double)part;
+                }
+            } else {
+                col[(kR2 ? 2 : 0) * kThreads] += (double)((v0 + v1) + (v2 + v3));
+            }
         }
         if constexpr (kHist) {
             const uint32_t slow = hist_fast4<MASKED>(p, r2, vmask, table0 + 4u * (uint32_t)(k * p.n_bins), trash);
@@ -757,8 +776,9 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
 
     const CtaWork w = cta_work(p);
     const int tid = threadIdx.x;
+    const int n_seg = (FLAGS == MDB_SUM_SINC && p.n_segments > 1) ? p.n_segments : 1;     // sub-ensembles per pass
     double *s_acc = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * kStageBytes);
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_acc + (size_t)NV * kLagChunk * kThreads);
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_acc + (size_t)NV * kLagChunk * n_seg * kThreads);
     double *s_edges = reinterpret_cast<double *>(s_hist + (size_t)kLagChunk * p.n_bins);
     const uint32_t trash = trash_slot(p, s_edges, tid);
 
@@ -771,7 +791,7 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < kThreads)
-        for (int i = 0; i < NV * kLagChunk; ++i) s_acc[(size_t)i * kThreads + tid] = 0.0;
+        for (int i = 0; i < NV * kLagChunk * n_seg; ++i) s_acc[(size_t)i * kThreads + tid] = 0.0;
     if (kHist) {
         for (int i = tid; i < kLagChunk * p.n_bins; i += kBulkThreads) s_hist[i] = 0u;
         if (p.bin_mode == MDB_BINS_EDGES)
@@ -836,16 +856,18 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
         }
     }
 
-    Accum<FLAGS> acc;
+    for (int seg = 0; seg < n_seg; ++seg) {
+        Accum<FLAGS> acc;
 #pragma unroll
-    for (int k = 0; k < kLagChunk; ++k) {
-        const double *col = s_acc + (size_t)k * NV * kThreads + tid;
-        int v = 0;
-        if constexpr (kR2) { acc.r2[k] = col[v * kThreads]; ++v; }
-        if constexpr (kR4) { acc.r4[k] = col[v * kThreads]; ++v; }
-        if constexpr (kSinc) { acc.sc[k] = col[v * kThreads]; ++v; }
+        for (int k = 0; k < kLagChunk; ++k) {
+            const double *col = s_acc + ((size_t)k * NV * n_seg + seg) * kThreads + tid;
+            int v = 0;
+            if constexpr (kR2) { acc.r2[k] = col[v * kThreads]; ++v; }
+            if constexpr (kR4) { acc.r4[k] = col[v * kThreads]; ++v; }
+            if constexpr (kSinc) { acc.sc[k] = col[v * kThreads]; ++v; }
+        }
+        cta_epilogue<FLAGS>(p, w, tid, acc, s_red, s_hist, [] { compute_barrier(); }, seg, n_seg);
     }
-    cta_epilogue<FLAGS>(p, w, tid, acc, s_red, s_hist, [] { compute_barrier(); });
 }
 #endif  // MDB_CORR_PART != 0
 

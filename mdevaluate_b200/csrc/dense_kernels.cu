@@ -316,6 +316,192 @@ __global__ void __launch_bounds__(kDenseThreads, MDB_DENSE_CTAS) dense_corr_kern
     }
 }
 
+// =================================================================================================
+// Version 2 (round 2): the same blocking with the rows held in shared memory as FLOAT32 OFFSETS from a per-atom
+// reference -- the unwrapped position at the first origin frame of the block, taken in float64 -- and packed
+// float32 arithmetic on PAIRS OF ATOMS.
+//
+// Why: the float64 tile above is bound by shared-memory bandwidth and the half-rate FP64 pipe (three LDS.64 and seven
+// FP64 operations per evaluation: 8.0e11 evals/s for the MSD).  An offset from a reference that is at most a few
+// hundred frames away from the origin rows is small where the displacement is small and of the size of the
+// displacement where it is large, so rounding it to float32 costs 2^-24 of max(|offset|, |d|): every displacement is
+// good to ~1e-7 relative (the float64 chain: 1e-16), inside the north star's 1e-5 for the averaged functions and far
+// below the float32 sinc.  In exchange a thread (atom pair, lag slice) needs three LDS.64 per TWO evaluations and the
+// whole displacement / r^2 / accumulate chain is seven packed instructions per two evaluations; sinc_of_square_x2
+// takes its pair as it comes.  `tuning.dense_float64` selects the float64 tile (and per-frame boxes always do).
+//
+// Thread layout: lane = atom pair (atoms 2*lane, 2*lane+1 of the 64-atom tile), warp = lag slice j: lags 4j .. 4j+3
+// of the 32-lag block; every warp owns its lags, so there is no cross-warp reduction.  Rows: [row][3][64] float32,
+// 768 bytes each; 32 origins x 32 lags need 95 rows = 71 KiB: three CTAs per SM.
+// =================================================================================================
+constexpr int kV2Lags = 32;                 // lags per block
+constexpr int kV2Slots = 4;                 // consecutive lags per warp
+constexpr int kV2MaxOrigins = 32;
+constexpr int kV2MaxRows = kV2MaxOrigins + (kV2MaxOrigins - 1) + kV2Lags;     // 95 at origin step 1
+constexpr int kV2RowFloats = 3 * kTileAtoms;                                   // 192
+static_assert(kTileAtoms == 64 && kDenseThreads == 256, "dense v2 is laid out for 64-atom tiles and 8 warps");
+
+constexpr int kV2RowBatch = 2;              // row pairs in flight per warp while staging
+
+template <bool IMG>
+__device__ __forceinline__ double unwrapped(float x, uint32_t n, int k, double box) {
+    double value = (double)x;
+    if (IMG) value = fma(-image_count(n, k), box, value);      // pbc.py:235-247
+    return value;
+}
+
+// Staging: a HALF-WARP per row.  Lane t (0..15) of a half takes atoms 4t .. 4t+3 of the tile: 12 consecutive values
+// = three 128-bit loads (+ three image words), whose component pattern x y z x y z ... is the same for every lane,
+// so the box lengths are uniform operands; every value is unwrapped in float64, the lane's reference (the same 12
+// values of the block's first origin row) is subtracted, and the four float32 offsets of each component go out as
+// one 128-bit store into the [component][atom] row.  A warp stages rows 2w, 2w+1 (halves), then 2w+16, ...
+template <bool IMG, bool FULL>
+__device__ __forceinline__ void stage_rows_v2(const DenseDev &p, int lane, int warp, int atom0, int ns, int n_rows,
+                                              int f_origin0, int f_partner0, float *s_rows) {
+    const int t = lane & 15, half = lane >> 4;
+    const long long e0 = 3ll * atom0 + 12 * t, e_end = 3ll * p.n_atoms;
+    const float *src0 = p.coords + e0;
+    const uint8_t *img0 = IMG ? p.images + e0 : nullptr;
+    const double bx = p.box_const[0], by = p.box_const[1], bz = p.box_const[2];
+    auto load = [&](long long row, float (&x)[12], uint32_t (&n)[3]) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            n[q] = 0x80808080u;
+            if (FULL || e0 + 4 * q < e_end) {          // rows are padded: a quad that starts inside may run over
+                v = __ldg(reinterpret_cast<const float4 *>(src0 + row * p.pitch) + q);
+                if (IMG) n[q] = __ldg(reinterpret_cast<const uint32_t *>(img0 + row * p.img_pitch) + q);
+            }
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    };
+    double ref[12];
+    {
+        float x[12];
+        uint32_t n[3];
+        load(row_of(p, f_origin0), x, n);
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+            ref[k] = unwrapped<IMG>(x[k], n[k >> 2], k & 3, k % 3 == 0 ? bx : (k % 3 == 1 ? by : bz));
+    }
+    for (int rb = 2 * warp + half; rb < n_rows; rb += 16 * kV2RowBatch) {
+        float x[kV2RowBatch][12];
+        uint32_t n[kV2RowBatch][3];
+#pragma unroll
+        for (int u = 0; u < kV2RowBatch; ++u) {
+            const int r = min(rb + 16 * u, n_rows - 1);
+            const int frame = (r < ns) ? f_origin0 + r * p.ostep : f_partner0 + (r - ns);
+            load(row_of(p, frame), x[u], n[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kV2RowBatch; ++u) {
+            const int r = min(rb + 16 * u, n_rows - 1);
+            float w[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                w[k] = (float)(unwrapped<IMG>(x[u][k], n[u][k >> 2], k & 3, k % 3 == 0 ? bx : (k % 3 == 1 ? by : bz)) -
+                               ref[k]);
+            float4 *dst = reinterpret_cast<float4 *>(s_rows + (size_t)r * kV2RowFloats) + t;      // atoms 4t..4t+3
+            dst[0] = make_float4(w[0], w[3], w[6], w[9]);                        // x of the four atoms
+            dst[kTileAtoms / 4] = make_float4(w[1], w[4], w[7], w[10]);          // y
+            dst[2 * (kTileAtoms / 4)] = make_float4(w[2], w[5], w[8], w[11]);    // z
+        }
+    }
+}
+
+__device__ __forceinline__ f32x2 lds_pair(const float *ptr) {
+    return *reinterpret_cast<const f32x2 *>(ptr);
+}
+
+template <bool IMG, int FLAGS>
+__global__ void __launch_bounds__(kDenseThreads, 3) dense_corr_kernel_v2(const DenseDev p) {
+    constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
+    constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
+    extern __shared__ __align__(16) float s_rows_f[];      // [ks + n_partner][3][64]
+
+    const int lb = blockIdx.x % p.n_lblocks;
+    const int split = blockIdx.x / p.n_lblocks;
+    const int lam = lb * kV2Lags;                          // first lag of the block
+    const int nl = min(kV2Lags, p.L - lam);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, j = tid >> 5;               // atom pair, lag slice
+    const f32x2 q2 = bcast2((float)p.q2);
+
+    double acc2[kV2Slots], accs[kV2Slots];
+#pragma unroll
+    for (int m = 0; m < kV2Slots; ++m) acc2[m] = accs[m] = 0.0;
+
+    const int t_begin = split * p.tiles_per_split;
+    const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const int atom0 = tile * kTileAtoms;
+        const bool live_lo = atom0 + 2 * lane < p.n_atoms, live_hi = atom0 + 2 * lane + 1 < p.n_atoms;
+        for (int sb = 0; sb < p.n_sblocks; ++sb) {
+            const int s0 = sb * p.ks;
+            const int ns = min(p.ks, p.S - s0);
+            const int f_origin0 = p.o0 + s0 * p.ostep;
+            const int f_partner0 = f_origin0 + p.i0 + lam;
+            const int n_rows = ns + (ns - 1) * p.ostep + nl;
+            __syncthreads();                               // the previous block is done with the rows
+            if (atom0 + kTileAtoms <= p.n_atoms)
+                stage_rows_v2<IMG, true>(p, lane, j, atom0, ns, n_rows, f_origin0, f_partner0, s_rows_f);
+            else
+                stage_rows_v2<IMG, false>(p, lane, j, atom0, ns, n_rows, f_origin0, f_partner0, s_rows_f);
+            __syncthreads();
+            // The 4 lag slots of a warp are always evaluated; in the last lag block some lie beyond n_lags: they read
+            // rows that are allocated (stale data) and their sums are never written out.
+            f32x2 part2[kV2Slots], parts[kV2Slots];
+#pragma unroll
+            for (int m = 0; m < kV2Slots; ++m) part2[m] = parts[m] = pack2(0.f, 0.f);
+            const float *ro = s_rows_f + 2 * lane;
+            const float *rp = s_rows_f + (size_t)(ns + kV2Slots * j) * kV2RowFloats + 2 * lane;
+            const int partner_stride = p.ostep * kV2RowFloats;
+#pragma unroll 2
+            for (int a = 0; a < ns; ++a) {
+                const f32x2 ox = lds_pair(ro), oy = lds_pair(ro + kTileAtoms), oz = lds_pair(ro + 2 * kTileAtoms);
+#pragma unroll
+                for (int m = 0; m < kV2Slots; ++m) {
+                    const float *rq = rp + m * kV2RowFloats;
+                    const f32x2 dx = sub2(ox, lds_pair(rq)), dy = sub2(oy, lds_pair(rq + kTileAtoms)),
+                                dz = sub2(oz, lds_pair(rq + 2 * kTileAtoms));
+                    const f32x2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    if constexpr (kR2) part2[m] = add2(part2[m], r2);
+                    if constexpr (kSinc) {
+                        float y0, y1, v0, v1;
+                        unpack2(mul2(r2, q2), y0, y1);
+                        sinc_of_square_x2(y0, y1, v0, v1);
+                        parts[m] = add2(parts[m], pack2(v0, v1));
+                    }
+                }
+                ro += kV2RowFloats;
+                rp += partner_stride;
+            }
+#pragma unroll
+            for (int m = 0; m < kV2Slots; ++m) {
+                float lo, hi;
+                if constexpr (kR2) {
+                    unpack2(part2[m], lo, hi);
+                    acc2[m] += (double)((live_lo ? lo : 0.f) + (live_hi ? hi : 0.f));
+                }
+                if constexpr (kSinc) {
+                    unpack2(parts[m], lo, hi);
+                    accs[m] += (double)((live_lo ? lo : 0.f) + (live_hi ? hi : 0.f));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < kV2Slots; ++m) {
+        const double v2 = warp_sum(acc2[m]);
+        const double vs = warp_sum(accs[m]);
+        const int l = kV2Slots * j + m;
+        if (lane == 0 && l < nl) {
+            p.partial[((long long)split * p.L + lam + l) * 2] = v2;
+            p.partial[((long long)split * p.L + lam + l) * 2 + 1] = vs;
+        }
+    }
+}
+
 __global__ void dense_reduce_kernel(const double *__restrict__ partial, double *__restrict__ sums, int n_out,
                                     int n_splits) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,6 +514,7 @@ __global__ void dense_reduce_kernel(const double *__restrict__ partial, double *
 struct DensePlan {
     int ks, n_sblocks, n_lblocks, n_tiles, n_splits, tiles_per_split;
     size_t smem;
+    bool v2;              // float32 offsets in shared memory (dense_corr_kernel_v2)
 };
 
 int make_dense_plan(const mdb_dense_args *a, DensePlan *pl) {
@@ -341,13 +528,22 @@ int make_dense_plan(const mdb_dense_args *a, DensePlan *pl) {
     if (reinterpret_cast<uintptr_t>(a->coords) % 16 || a->pitch % 4 ||
         (a->images && (reinterpret_cast<uintptr_t>(a->images) % 4 || a->img_pitch % 4)))
         return fail(MDB_ERR_UNSUPPORTED, "dense: rows must be 16-byte aligned (pitch % 4 == 0, image pitch % 4 == 0)");
-    int ks = (kMaxPartnerRows - kL) / a->origin_step + 1;
-    if (ks > kMaxS) ks = kMaxS;
+    // version 2 wherever it applies: a constant box (per-frame boxes keep the float64 tile), unless the caller asks
+    pl->v2 = !a->tuning.dense_float64 && !(a->images && a->box);
+    int ks;
+    if (pl->v2) {
+        ks = (kV2MaxRows - kV2Lags + a->origin_step) / (1 + a->origin_step);     // ks + (ks-1)*step + 32 <= 95
+        if (ks > kV2MaxOrigins) ks = kV2MaxOrigins;
+    } else {
+        ks = (kMaxPartnerRows - kL) / a->origin_step + 1;
+        if (ks > kMaxS) ks = kMaxS;
+    }
     if (ks < 2) return fail(MDB_ERR_UNSUPPORTED, "dense: origin_step too large for row reuse (use mdb_shifted_corr)");
     if (ks > a->n_origins) ks = a->n_origins;
     pl->ks = ks;
     pl->n_sblocks = (a->n_origins + ks - 1) / ks;
     pl->n_lblocks = (a->n_lags + kL - 1) / kL;
+    static_assert(kL == kV2Lags, "both versions cut the lags into blocks of 32");
     pl->n_tiles = (a->n_atoms + kTileAtoms - 1) / kTileAtoms;
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -357,7 +553,7 @@ int make_dense_plan(const mdb_dense_args *a, DensePlan *pl) {
     pl->tiles_per_split = (int)((pl->n_tiles + want - 1) / want);
     pl->n_splits = (pl->n_tiles + pl->tiles_per_split - 1) / pl->tiles_per_split;
     const int max_partner = (ks - 1) * a->origin_step + kL;       // also what the padded lag slots may touch
-    pl->smem = (size_t)(ks + max_partner) * 3 * kTileAtoms * sizeof(double);
+    pl->smem = (size_t)(ks + max_partner) * 3 * kTileAtoms * (pl->v2 ? sizeof(float) : sizeof(double));
     return MDB_OK;
 }
 
@@ -419,6 +615,23 @@ extern "C" int mdb_dense_corr(const mdb_dense_args *a, void *stream) {
     };
     int rc;
     const bool img = a->images != nullptr;
+    if (pl.v2) {
+        auto pick2 = [&](auto flags_c) -> int {
+            constexpr int F = decltype(flags_c)::value;
+            return img ? launch(dense_corr_kernel_v2<true, F>) : launch(dense_corr_kernel_v2<false, F>);
+        };
+        switch (a->flags) {
+            case MDB_SUM_R2: rc = pick2(std::integral_constant<int, MDB_SUM_R2>{}); break;
+            case MDB_SUM_SINC: rc = pick2(std::integral_constant<int, MDB_SUM_SINC>{}); break;
+            default: rc = pick2(std::integral_constant<int, MDB_SUM_R2 | MDB_SUM_SINC>{});
+        }
+        if (rc) return rc;
+        const int n_out2 = a->n_lags * 2;
+        dense_reduce_kernel<<<(n_out2 + 255) / 256, 256, 0, st>>>(p.partial, a->sums, n_out2, pl.n_splits);
+        MDB_CUDA_CHECK(cudaGetLastError());
+        last_launch_count() = 2;
+        return MDB_OK;
+    }
     // warp-per-row staging (measured: MSD 7.0e11 -> 8.0e11, ISF 5.2e11 -> 6.4e11 evals/s, profiles/r2_call1.log) is
     // the default where it applies (constant box); tuning.dense_stage_cta = 1 selects the CTA-wide staging loop
     const bool warp_stage = !a->tuning.dense_stage_cta && kDenseThreads == 256 && !(img && a->box);

@@ -13,15 +13,24 @@ block, box, times = random_walk_device(N, T, seed=1, box=box_length(N), pitch=en
 coords = md.Coordinates.from_arrays(block, box, times, n_atoms=N).nojump
 dense = lambda a, b: np.arange(a, b)
 S = T // 2
+ref = {}
 for name, fn in (('msd', c.msd), ('isf', partial(c.isf, q=22.7))):
     c.shifted_correlation(fn, coords, segments=8, average=True, index_distribution=dense)      # warm (scan etc.)
+    engine.tuning.dense_float64 = 1
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    t, r64 = c.shifted_correlation(fn, coords, segments=S, window=0.5, average=True, index_distribution=dense)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    engine.tuning.dense_float64 = 0
+    print('%s tiled f64 S=%d L=%d N=%d: %.3f s  %.3e evals/s' % (name, S, len(r64), N, dt, N * S * len(r64) / dt))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     t, r = c.shifted_correlation(fn, coords, segments=S, window=0.5, average=True, index_distribution=dense)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     L = len(r)
-    print('%s tiled     S=%d L=%d N=%d: %.3f s  %.3e evals/s' % (name, S, L, N, dt, N * S * L / dt))
+    print('%s tiled v2  S=%d L=%d N=%d: %.3f s  %.3e evals/s   max rel diff to the float64 tile %.2e' % (name, S, L, N, dt, N * S * L / dt, np.abs(r / r64 - 1)[1:].max() if name == 'msd' else np.abs(r - r64).max()))
     save = c.DENSE_MIN_PAIRS
     c.DENSE_MIN_PAIRS = 1 << 62
     S2 = max(8, S // 16)

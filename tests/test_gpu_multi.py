@@ -68,7 +68,7 @@ if rank == 0:
     assert np.array_equal(out['multi_n'], n) and np.allclose(out['multi'], r, rtol=1e-9, atol=1e-12)
     t, rd = c.shifted_correlation(partial(c.isf, q=22.7), full.nojump, segments=150, window=0.5, average=True,
                                   index_distribution=dense)
-    assert np.allclose(out['dense'], rd, rtol=1e-9, atol=1e-12)
+    assert np.allclose(out['dense'], rd, rtol=1e-6, atol=1e-9)      # float32 offsets, another tiling per shard
     print('MULTI_GPU_OK')
 assert shard.comm.p2p is not None, 'peer-memory communicator not in use'
 parallel.release_peer_comms()
