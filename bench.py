@@ -434,6 +434,31 @@ def ours_arm(a):
                                  'value': evals_step / (sus_ms * 1e-3),
                                  'clocks': sampler.window(s0, s1) if rank == 0 else None}
 
+    # ---- where a step's time beyond its kernel goes: the plan's timeline (host clock + the GPU's %globaltimer) ----
+    try:
+        pairs = [engine.clock_pair() for _ in range(30)]
+        g_ns, before, seen = min(pairs, key=lambda p_: p_[2] - p_[1])
+        offset = g_ns - (before + seen) / 2.0
+        rows_tl = []
+        for _ in range(30):
+            t0 = time.perf_counter_ns()
+            step()
+            t1 = time.perf_counter_ns()
+            h0, h1, h2, g0, g1, g2 = plan.timeline()
+            rows_tl.append((t1 - t0, h2 - h0, h1 - h0, g0 - offset - h0, g1 - g0, g2 - g1, h2 - (g2 - offset)))
+        med = np.median(np.array(rows_tl, dtype=np.float64), axis=0) / 1e3
+        roofline['through_api']['timeline_us'] = {
+            'step (chi4 call, host clock)': med[0], 'mdb_corr_plan_run': med[1], 'launch call': med[2],
+            'launch entered -> first CTA': med[3], 'correlation kernel start -> finish kernel start': med[4],
+            'finish kernel': med[5], 'flag store -> host saw it': med[6], 'python around the run': med[0] - med[1],
+            'step beyond the correlation kernel': med[0] - med[4],
+            'clock_offset_uncertainty': (seen - before) / 2e3,
+            'note': 'medians of 30 steps WITHOUT kernel events, taken after the sustained leg (power-capped clocks); '
+                    'GPU and host clocks related by mdb_clock_pair.  host_overhead_ms above is ms_per_step minus the '
+                    'event-timed kernel and so includes what the two cudaEventRecords per step cost'}
+    except Exception as exc:
+        roofline['through_api']['timeline_us'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
+
     # ---- the second schedule of config 4 (S=10, L=84) and the ISF through the float64 chain ------------------
     def rate(fn_, kw_, reps=5, **tune):
         for k_, v_ in tune.items():

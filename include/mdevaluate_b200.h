@@ -199,6 +199,14 @@ const unsigned long long *mdb_corr_plan_hist(const mdb_corr_plan *plan);
 /* DEVICE copies of the same (e.g. to feed another kernel without a round trip). */
 const double *mdb_corr_plan_sums_device(const mdb_corr_plan *plan);
 int mdb_corr_plan_launches(const mdb_corr_plan *plan);      /* kernels one run enqueues */
+/* Where the time of the plan's last completed run went, in ns.  out[0..2]: the host's steady clock when
+ * mdb_corr_plan_launch was entered, when it returned and when the wait saw the result.  out[3..5]: the GPU's
+ * %globaltimer when the first CTA of the correlation kernel started, when the finish kernel started and just before it
+ * raised the host flag.  The clocks have different origins; mdb_clock_pair relates them (one tiny kernel that stores
+ * %globaltimer into mapped host memory: *gpu_ns lies between *host_before_ns and *host_seen_ns). */
+int mdb_corr_plan_timeline(const mdb_corr_plan *plan, unsigned long long *out6);
+int mdb_clock_pair(void *stream, unsigned long long *gpu_ns, unsigned long long *host_before_ns,
+                   unsigned long long *host_seen_ns);
 int mdb_corr_plan_destroy(mdb_corr_plan *plan);
 
 /* ------------------------------------------------------------------------------------------

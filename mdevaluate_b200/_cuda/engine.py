@@ -45,12 +45,20 @@ class Tuning:
             setattr(self, f, 0)
         self.use_packed = True          # host-side: hand the packed image rows to the kernels when a store has them
 
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        object.__setattr__(self, '_key', None)
+
     def fill(self, struct):
         for f in self.FIELDS:
             setattr(struct, f, int(getattr(self, f)))
 
     def key(self):
-        return tuple(int(getattr(self, f)) for f in self.FIELDS) + (bool(self.use_packed),)
+        key = self._key
+        if key is None:
+            key = tuple(int(getattr(self, f)) for f in self.FIELDS) + (bool(self.use_packed),)
+            object.__setattr__(self, '_key', key)
+        return key
 
 
 tuning = Tuning()
@@ -289,6 +297,15 @@ def correlate_device(store, rows, spec, stream=None, select=None):
     return sums, hist
 
 
+def clock_pair():
+    """(gpu_ns, host_before_ns, host_seen_ns): one tiny kernel stores the GPU's clock into mapped host memory."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    g, a, b = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+    _lib.check(lib.mdb_clock_pair(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.byref(g), C.byref(a), C.byref(b)), 'mdb_clock_pair')
+    return int(g.value), int(a.value), int(b.value)
+
+
 class CorrPlan:
     """One repeated correlation request on one store (``mdb_corr_plan``): the C side owns workspace, device sums /
     histogram and a page-locked host block; :meth:`run` is two kernel launches and returns NumPy views of that host
@@ -313,8 +330,11 @@ class CorrPlan:
                                                 C.byref(handle)), 'mdb_corr_plan_create')
         self.handle = handle
         self._lib = lib
+        # the raw handle of torch's current stream on the store's device, without building a Stream object per call
+        self._raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
         self._stream_of = torch.cuda.current_stream
         self._device = store.device
+        self._device_index = store.device.index if store.device.index is not None else torch.cuda.current_device()
         n_seg = max(1, int(n_segments))
         n = S * L * 3 * n_seg
         ptr = lib.mdb_corr_plan_sums(handle)
@@ -331,8 +351,11 @@ class CorrPlan:
     def run(self, slot=None):
         """Launch on the current stream, wait, and return ``(sums, hist)`` -- views of the plan's host block."""
         global last_plan
-        st = self._stream_of(self._device)
-        rc = self._lib.mdb_corr_plan_run(self.handle, C.c_void_p(st.cuda_stream), time_slot if slot is None else slot)
+        if self._raw_stream is not None:
+            st = self._raw_stream(self._device_index)
+        else:
+            st = self._stream_of(self._device).cuda_stream
+        rc = self._lib.mdb_corr_plan_run(self.handle, C.c_void_p(st), time_slot if slot is None else slot)
         if rc:
             _lib.check(rc, 'mdb_corr_plan_run')
         _count(self.launches)
@@ -343,6 +366,14 @@ class CorrPlan:
         ms = C.c_float(0.0)
         _lib.check(self._lib.mdb_corr_plan_kernel_ms(self.handle, time_slot, C.byref(ms)), 'mdb_corr_plan_kernel_ms')
         return float(ms.value)
+
+    def timeline(self):
+        """Where the time of the last run went (ns): host clock at launch entry / launch return / result seen, and
+        the GPU's clock at correlation-kernel start / finish-kernel start / finish-kernel end (different origins,
+        see :func:`clock_pair`)."""
+        out = (C.c_ulonglong * 6)()
+        _lib.check(self._lib.mdb_corr_plan_timeline(self.handle, out), 'mdb_corr_plan_timeline')
+        return [int(v) for v in out]
 
     def close(self):
         if self.handle is not None:

@@ -30,7 +30,8 @@ EXPORTS = (
     'mdb_dense_workspace_bytes', 'mdb_dense_corr', 'mdb_copy_rows_h2d',
     'mdb_corr_plan_create', 'mdb_corr_plan_run', 'mdb_corr_plan_launch', 'mdb_corr_plan_wait',
     'mdb_corr_plan_kernel_ms', 'mdb_corr_plan_sums', 'mdb_corr_plan_hist', 'mdb_corr_plan_sums_device',
-    'mdb_corr_plan_launches', 'mdb_corr_plan_destroy', 'mdb_corr_plan_set_wait',
+    'mdb_corr_plan_launches', 'mdb_corr_plan_destroy', 'mdb_corr_plan_set_wait', 'mdb_corr_plan_timeline',
+    'mdb_clock_pair',
     'mdb_comm_create', 'mdb_comm_handle', 'mdb_comm_connect', 'mdb_comm_destroy',
     'mdb_images_pack', 'mdb_nojump_apply_format', 'mdb_vectors',
 )
@@ -132,6 +133,8 @@ def _declare(lib):
     for name in ('mdb_corr_plan_sums', 'mdb_corr_plan_hist', 'mdb_corr_plan_sums_device'):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.mdb_corr_plan_launches.argtypes = [C.c_void_p]
+    lib.mdb_corr_plan_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+    lib.mdb_clock_pair.argtypes = [C.c_void_p] + [C.POINTER(C.c_ulonglong)] * 3
     lib.mdb_corr_plan_set_wait.argtypes = [C.c_void_p, C.c_int32]
     lib.mdb_corr_plan_destroy.argtypes = [C.c_void_p]
     lib.mdb_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]

@@ -196,6 +196,9 @@ class _Spec:
                     raise ZeroDivisionError('division by zero')      # the reference's ``1 / len(start)``
                 return (1 / n_atoms)[:, None, None] * hist
             n_atoms = n_atoms[:, None]
+        elif n_atoms and self.name == 'isf':
+            out = sums[..., 2] / n_atoms
+            return out.astype(np.float32) if float32 else out
         with np.errstate(divide='ignore', invalid='ignore'):
             if self.name in ('msd', 'rotational_autocorrelation'):
                 out = sums[..., 0] / n_atoms
@@ -873,7 +876,13 @@ def chi4(frames, q, index_distribution=log_indices, segments=20, window=0.2, ski
         n_atoms = frames._resident().n_atoms          # len(OW[0]) without fetching (and unwrapping) frame 0
     else:
         n_atoms = len(frames[0])
-    x4 = n_atoms * fqt.var(axis=0)
+    # fqt.var(axis=0), operation by operation as NumPy's _var evaluates it (same bits), without its Python overhead
+    fqt = np.asarray(fqt)
+    if fqt.ndim == 2 and fqt.dtype == np.float64 and len(fqt):
+        dev = fqt - np.add.reduce(fqt, axis=0, keepdims=True) / len(fqt)
+        x4 = n_atoms * (np.add.reduce(dev * dev, axis=0) / len(fqt))
+    else:
+        x4 = n_atoms * fqt.var(axis=0)
     if smooth:
         return t, x4, runningmean(x4, smooth)
     return t, x4

@@ -59,7 +59,14 @@ struct CorrDev {
     const double *edges;
     double *partial;         // [S*L][n_ablocks][3]
     unsigned long long *hist;
+    unsigned long long *stamp;   // plans: the first CTA stores %globaltimer here when it starts (timeline), or nullptr
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct Plan {
     int n_groups, n_chunks, n_ablocks, groups_per_block;

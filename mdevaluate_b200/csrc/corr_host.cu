@@ -235,6 +235,8 @@ struct FinishDev {
     unsigned long long *flag_host; // mapped host flag, or null
     unsigned long long seq_host;   // value the flag takes when the results are complete
     unsigned int *ticket;          // two device counters, zero between launches
+    const unsigned long long *corr_stamp;   // plans: where the correlation kernel left its start time, or null
+    unsigned long long *stamps_host;        // plans: mapped host words [corr start, finish start, finish end] (ns)
     int use_comm;
     unsigned long long seq_comm;
     CommDev comm;
@@ -280,17 +282,23 @@ __device__ __forceinline__ void store_result(const FinishDev &f, long long i, un
 // Last CTA through a ticket counter.  ONE system-scope fence per CTA: the barrier orders every thread's stores before
 // thread 0 at CTA scope, and thread 0's fence makes them visible system-wide before it takes its ticket (fences are
 // cumulative).  With a fence in every thread -- 5000 fences behind stores to mapped host memory -- this kernel took
-// 14 us (profiles/r2_launches_bench.csv); the last CTA fences again on the acquiring side.
+// 14 us (profiles/r2_launches_bench.csv).  The last CTA only RAISES FLAGS afterwards (st.release.sys, which orders its
+// own earlier stores); it never reads what the other CTAs wrote, so there is no fence on the acquiring side.
 __device__ __forceinline__ bool last_cta(unsigned int *ticket, int *s_flag) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
         const bool last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-        if (last) __threadfence_system();
         *s_flag = last ? 1 : 0;
     }
     __syncthreads();
     return *s_flag != 0;
+}
+
+__device__ __forceinline__ void stamp_end(const FinishDev &f) {
+    if (!f.stamps_host) return;
+    f.stamps_host[0] = f.corr_stamp ? *f.corr_stamp : 0ull;
+    f.stamps_host[2] = global_timer_ns();
 }
 
 __global__ void __launch_bounds__(256) finish_kernel(const FinishDev f) {
@@ -299,10 +307,12 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishDev f) {
     const long long n_total = f.n_sums + f.n_hist;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f.stamps_host && first == 0) f.stamps_host[1] = global_timer_ns();      // ordered by last_cta's fence
     if (!f.use_comm) {
         for (long long i = first; i < f.n_sums; i += stride) store_result(f, i, local_word(f, i));
         if (last_cta(f.ticket, &s_flag) && threadIdx.x == 0) {
             f.ticket[0] = 0u;
+            stamp_end(f);
             if (f.flag_host) st_release_sys(f.flag_host, f.seq_host);
         }
         return;
@@ -349,9 +359,11 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishDev f) {
     }
     if (timed_out && threadIdx.x == 0) atomicExch(&f.ticket[2], 1u);
     if (last_cta(f.ticket + 1, &s_flag) && threadIdx.x == 0) {
+        __threadfence();                 // the other CTAs' time-out marks, set before they took their tickets
         const bool any_timeout = atomicExch(&f.ticket[2], 0u) != 0u;
         f.ticket[0] = 0u;
         f.ticket[1] = 0u;
+        stamp_end(f);
         if (f.flag_host) st_release_sys(f.flag_host, any_timeout ? kFlagTimeout : f.seq_host);
     }
 }
@@ -477,7 +489,13 @@ struct mdb_corr_plan {
     cudaEvent_t events[2 * MDB_PLAN_TIME_SLOTS];
     bool have_events = false;
     int device = 0;
+    unsigned long long host_ns[3] = {0, 0, 0};     // steady clock: launch entered, launch returned, result seen
 };
+
+static inline unsigned long long steady_ns() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+               std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 namespace mdb {
 unsigned long long *comm_sequence(mdb_comm *comm);      // comm.cu: the launch counter all plans of a comm share
@@ -540,6 +558,9 @@ extern "C" int mdb_corr_plan_create(const mdb_corr_args *a, mdb_comm *comm, mdb_
     f.flag_host = reinterpret_cast<unsigned long long *>(mapped);
     f.sums_host = reinterpret_cast<double *>(static_cast<char *>(mapped) + 64);
     f.ticket = reinterpret_cast<unsigned int *>(d + partial_bytes + n_sums * 8 + pl->hist_words * 8);
+    pl->dev.stamp = reinterpret_cast<unsigned long long *>(d + partial_bytes + n_sums * 8 + pl->hist_words * 8 + 32);
+    f.corr_stamp = pl->dev.stamp;
+    f.stamps_host = reinterpret_cast<unsigned long long *>(static_cast<char *>(mapped) + 8);
     if (comm) {
         if (int rc = comm_device_view(comm, &f.comm)) {
             mdb_corr_plan_destroy(pl);
@@ -565,6 +586,7 @@ extern "C" int mdb_corr_plan_launch(mdb_corr_plan *pl, void *stream, int32_t tim
     if (pl->pending) return fail(MDB_ERR_ARGUMENT, "the previous run of this plan has not been waited for");
     if (time_slot >= MDB_PLAN_TIME_SLOTS) return fail(MDB_ERR_ARGUMENT, "time_slot out of range");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    pl->host_ns[0] = steady_ns();
     LaunchTiming tm;
     if (time_slot >= 0) {
         if (!pl->have_events) {
@@ -587,6 +609,7 @@ extern "C" int mdb_corr_plan_launch(mdb_corr_plan *pl, void *stream, int32_t tim
                                        cudaMemcpyDeviceToHost, st));
     pl->last_stream = st;
     pl->pending = true;
+    pl->host_ns[1] = steady_ns();
     return MDB_OK;
 }
 
@@ -596,6 +619,7 @@ extern "C" int mdb_corr_plan_wait(mdb_corr_plan *pl) {
     pl->pending = false;
     if (pl->wait_mode != 0) {
         MDB_CUDA_CHECK(cudaStreamSynchronize(pl->last_stream));
+        pl->host_ns[2] = steady_ns();
         if (*pl->flag_host == kFlagTimeout) {
             *pl->flag_host = 0;
             return fail(MDB_ERR_TIMEOUT, "a peer GPU did not deliver its partial sums in time");
@@ -626,6 +650,7 @@ extern "C" int mdb_corr_plan_wait(mdb_corr_plan *pl) {
                 return fail(MDB_ERR_TIMEOUT, "no result after 120 s");
         }
     }
+    pl->host_ns[2] = steady_ns();
     std::atomic_thread_fence(std::memory_order_acquire);
     if (pl->hist_words) MDB_CUDA_CHECK(cudaStreamSynchronize(pl->last_stream));     // the histogram's D2H copy
     return MDB_OK;
@@ -659,6 +684,50 @@ extern "C" const double *mdb_corr_plan_sums(const mdb_corr_plan *pl) { return pl
 extern "C" const unsigned long long *mdb_corr_plan_hist(const mdb_corr_plan *pl) { return pl ? pl->hist_host : nullptr; }
 extern "C" const double *mdb_corr_plan_sums_device(const mdb_corr_plan *pl) { return pl ? pl->fin.sums_dev : nullptr; }
 extern "C" int mdb_corr_plan_launches(const mdb_corr_plan *pl) { return pl ? 2 : 0; }
+
+extern "C" int mdb_corr_plan_timeline(const mdb_corr_plan *pl, unsigned long long *out) {
+    if (!pl || !out) return fail(MDB_ERR_ARGUMENT, "NULL argument");
+    if (pl->pending || pl->seq == 0) return fail(MDB_ERR_ARGUMENT, "no completed run");
+    const volatile unsigned long long *stamps = pl->flag_host + 1;
+    for (int i = 0; i < 3; ++i) out[i] = pl->host_ns[i];
+    for (int i = 0; i < 3; ++i) out[3 + i] = stamps[i];
+    return MDB_OK;
+}
+
+static __global__ void clock_kernel(unsigned long long *out) {
+    out[1] = global_timer_ns();
+    st_release_sys(out, 1ull);
+}
+
+extern "C" int mdb_clock_pair(void *stream, unsigned long long *gpu_ns, unsigned long long *host_before_ns,
+                              unsigned long long *host_seen_ns) {
+    if (!gpu_ns || !host_before_ns || !host_seen_ns) return fail(MDB_ERR_ARGUMENT, "NULL argument");
+    unsigned long long *block = nullptr;
+    MDB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&block), 64, cudaHostAllocMapped));
+    block[0] = block[1] = 0ull;
+    void *mapped = nullptr;
+    cudaError_t err = cudaHostGetDevicePointer(&mapped, block, 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err == cudaSuccess) {
+        *host_before_ns = steady_ns();
+        clock_kernel<<<1, 1, 0, st>>>(static_cast<unsigned long long *>(mapped));
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) {
+        volatile unsigned long long *flag = block;
+        const auto t0 = std::chrono::steady_clock::now();
+        while (*flag == 0ull) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) { err = cudaErrorTimeout; break; }
+        }
+        *host_seen_ns = steady_ns();
+        std::atomic_thread_fence(std::memory_order_acquire);
+        *gpu_ns = block[1];
+    }
+    cudaFreeHost(block);
+    if (err != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_clock_pair: %s", cudaGetErrorString(err));
+    return MDB_OK;
+}
 
 extern "C" int mdb_corr_plan_destroy(mdb_corr_plan *pl) {
     if (!pl) return MDB_OK;

@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, 2) corr_ldg_kernel(const CorrDev p) 
 
     const CtaWork w = cta_work(p);
     const int tid = threadIdx.x;
+    if (p.stamp != nullptr && (blockIdx.x | blockIdx.y | tid) == 0) *p.stamp = global_timer_ns();
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem_raw);
     double *s_edges = reinterpret_cast<double *>(smem_raw + (size_t)kLagChunk * p.n_bins * sizeof(unsigned int));
     const uint32_t trash = trash_slot(p, s_edges, tid);
@@ -776,6 +777,7 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
 
     const CtaWork w = cta_work(p);
     const int tid = threadIdx.x;
+    if (p.stamp != nullptr && (blockIdx.x | blockIdx.y | tid) == 0) *p.stamp = global_timer_ns();
     const int n_seg = (FLAGS == MDB_SUM_SINC && p.n_segments > 1) ? p.n_segments : 1;     // sub-ensembles per pass
     double *s_acc = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * kStageBytes);
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_acc + (size_t)NV * kLagChunk * n_seg * kThreads);

@@ -59,6 +59,23 @@ print('%-34s %8.1f us' % ('  wait - kernel', t_wait / n * 1e6 - k_us))
 for mode, label in ((1, 'mapped writes + cudaStreamSynchronize'), (2, 'cudaMemcpyAsync + cudaStreamSynchronize'), (0, 'mapped writes + flag polling')):
     lib.mdb_corr_plan_set_wait(plan.handle, mode)
     timeit('plan.run(), %s' % label, lambda: plan.run())
+# the timeline of a run: host clock and the GPU's clock, related by a clock pair measured here
+pairs = [engine.clock_pair() for _ in range(50)]
+gap = min(seen - before for g, before, seen in pairs)
+g, before, seen = min(pairs, key=lambda p: p[2] - p[1])
+offset = g - (before + seen) / 2          # gpu clock - host clock, +- gap / 2
+print('clock pair: launch-to-seen of a 1-thread kernel %.1f us (best of 50) -> clock offset known to +-%.1f us'
+      % (gap / 1e3, gap / 2e3))
+rows = []
+for _ in range(n):
+    plan.run()
+    h0, h1, h2, g0, g1, g2 = plan.timeline()
+    rows.append((h1 - h0, g0 - offset - h0, g1 - g0, g2 - g1, h2 - (g2 - offset), h2 - h0))
+rows = np.median(np.array(rows, dtype=np.float64), axis=0) / 1e3
+for label, v in zip(('launch call (2 kernels enqueued)', 'launch entered -> first CTA of the correlation kernel',
+                     'correlation kernel start -> finish kernel start', 'finish kernel (start -> flag store)',
+                     'flag store -> host saw it', 'plan.run() total (host clock)'), rows):
+    print('  timeline: %-56s %8.1f us' % (label, v))
 key, res = c._call_key(fn, coords, c.log_indices, S, 0.5, None)
 timeit('_call_key', lambda: c._call_key(fn, coords, c.log_indices, S, 0.5, None))
 entry = c._call_cache[key]
