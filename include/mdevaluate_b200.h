@@ -378,6 +378,56 @@ typedef struct mdb_dense_args {
 int mdb_dense_workspace_bytes(const mdb_dense_args *args, size_t *bytes);
 int mdb_dense_corr(const mdb_dense_args *args, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Overlap with a reference configuration.  Replaces correlation.overlap (correlation.py:288-312) evaluated through
+ * shifted_correlation on a coordinates.CoordinatesKDTree (coordinates.py:415-455): for every (origin s, lag l)
+ *   counts[s*L + l] = #{ atoms i of frame rows[s*L + l] : some tree atom j with |x_i - y_j| <= radius }
+ * where the tree of origin s holds the atoms of row ref_rows[s] of the tree's trajectory that ref_select marks
+ * (all when NULL).  The caller divides by the tree size (tree_sizes).  Distances as scipy's cKDTree computes them
+ * (float64, no fused multiply-adds); boxsize[d] > 0 makes dimension d periodic like cKDTree(boxsize=...): query
+ * points are wrapped, tree atoms must lie in [0, boxsize) (out_of_box reports a violation; scipy raises ValueError).
+ * Frames: float32 or float64 rows, raw or with image counts in any MDB_IMAGE_* format (nojump frames x - n*box).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mdb_overlap_args {
+    const void *ref_coords;      /* DEVICE rows of the tree's trajectory                         */
+    int64_t ref_pitch;
+    int32_t ref_type;            /* MDB_F32 / MDB_F64                                            */
+    int32_t n_ref;               /* atoms per tree row                                           */
+    const void *ref_images;      /* DEVICE image counts of those rows, or NULL (raw frames)      */
+    int32_t ref_image_format;    /* MDB_IMAGE_*                                                  */
+    int32_t reserved0;
+    int64_t ref_img_pitch;       /* elements of that format per row                              */
+    const double *ref_box;       /* DEVICE [rows][3] or NULL: ref_box_const                      */
+    double ref_box_const[3];
+    const int32_t *ref_rows;     /* DEVICE [n_origins] tree row of every origin                  */
+    const uint8_t *ref_select;   /* DEVICE [n_origins][ref_sel_pitch] 1 = atom is in the tree; or NULL */
+    int64_t ref_sel_pitch;
+    const void *coords;          /* DEVICE rows of the correlated trajectory                     */
+    int64_t pitch;
+    int32_t coord_type;
+    int32_t n_atoms;
+    const void *images;
+    int32_t image_format;
+    int32_t reserved1;
+    int64_t img_pitch;
+    const double *box;
+    double box_const[3];
+    const int32_t *rows;         /* DEVICE [n_origins*n_lags]                                    */
+    int32_t n_origins, n_lags;
+    double radius;
+    double boxsize[3];           /* periodic tree, or zeros                                      */
+    unsigned long long *counts;  /* DEVICE out [n_origins*n_lags]                                */
+    int32_t *tree_sizes;         /* DEVICE out [n_origins], or NULL                              */
+    double *bounds;              /* DEVICE out [n_origins][6] min xyz, max xyz of every tree, or NULL */
+    int32_t *out_of_box;         /* DEVICE out [1]: 1 if a periodic tree has atoms outside the box, or NULL */
+    void *workspace;             /* DEVICE scratch of mdb_overlap_workspace_bytes()              */
+    size_t workspace_bytes;
+} mdb_overlap_args;
+
+int mdb_overlap_workspace_bytes(const mdb_overlap_args *args, size_t *bytes);
+int mdb_overlap(const mdb_overlap_args *args, void *stream);
+int mdb_overlap_launches(void);                  /* kernels one mdb_overlap call enqueues */
+
 #ifdef __cplusplus
 }
 #endif

@@ -638,3 +638,78 @@ def vector_rows(store, rows, atoms_a, atoms_b, normed, pbc_box=None, stream=None
         _lib.check(lib.mdb_vectors(C.byref(a), C.c_void_p(st.cuda_stream)), 'mdb_vectors')
     _count(1)
     return DeviceStore(out, n_vec)
+
+
+def _fill_frame_rows(a, prefix, store):
+    """The fields of mdb_overlap_args that describe one trajectory's rows (``prefix`` '' or 'ref_')."""
+    torch = _lib.require_cuda()
+    setattr(a, prefix + 'coords', store.coords.data_ptr())
+    setattr(a, prefix + 'pitch', store.coords.stride(0))
+    setattr(a, 'ref_type' if prefix else 'coord_type', _lib.F32 if store.coords.dtype == torch.float32 else _lib.F64)
+    if not store.has_images:
+        return
+    if store.packed is not None and tuning.use_packed:
+        images, fmt = store.packed, _lib.IMAGE_PACKED
+    elif store.images is not None:
+        images, fmt = store.images, _lib.IMAGE_BYTES
+    else:
+        images, fmt = store.images16, _lib.IMAGE_I16
+    setattr(a, prefix + 'images', images.data_ptr())
+    setattr(a, prefix + 'image_format', fmt)
+    setattr(a, prefix + 'img_pitch', images.stride(0))
+    box_const = getattr(a, prefix + 'box_const')
+    if store.box_const is not None:
+        box_const[0], box_const[1], box_const[2] = store.box_const
+    else:
+        setattr(a, prefix + 'box', store.box.data_ptr())
+
+
+def overlap_counts(tree_store, tree_rows, store, rows, radius, boxsize=None, tree_select=None, stream=None):
+    """``mdb_overlap``: for every (origin, lag) the number of atoms of frame ``rows[s, l]`` of ``store`` that have an
+    atom of the tree of origin s -- row ``tree_rows[s]`` of ``tree_store``, restricted to ``tree_select[s]`` (uint8
+    device tensor (S, pitch)) -- within ``radius`` (cKDTree arithmetic, periodic with ``boxsize``).
+    Returns ``(counts (S, L) int64, tree sizes (S,), bounds (S, 6), out_of_box flag)`` as NumPy arrays."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = store.device
+    if tree_store.device != dev:
+        raise _lib.CudaPathError('the tree and the frames must live on the same device')
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    tree_rows = np.ascontiguousarray(tree_rows, dtype=np.int32).ravel()
+    S, L = rows.shape
+    if tree_rows.shape[0] != S:
+        raise ValueError('one tree row per origin')
+    a = _lib.OverlapArgs()
+    _fill_frame_rows(a, 'ref_', tree_store)
+    _fill_frame_rows(a, '', store)
+    a.n_ref = tree_store.n_atoms
+    a.n_atoms = store.n_atoms
+    rows_dev = torch.from_numpy(rows).to(dev)
+    tree_rows_dev = torch.from_numpy(tree_rows).to(dev)
+    a.rows = rows_dev.data_ptr()
+    a.ref_rows = tree_rows_dev.data_ptr()
+    if tree_select is not None:
+        if tree_select.shape[0] != S or tree_select.stride(0) < tree_store.n_atoms or tree_select.dtype != torch.uint8:
+            raise ValueError('tree_select must be (S, pitch) uint8 with pitch >= the atoms of a tree row')
+        a.ref_select = tree_select.data_ptr()
+        a.ref_sel_pitch = tree_select.stride(0)
+    a.n_origins, a.n_lags = S, L
+    a.radius = float(radius)
+    if boxsize is not None:
+        b = np.broadcast_to(np.asarray(boxsize, dtype=np.float64), (3,))
+        a.boxsize[0], a.boxsize[1], a.boxsize[2] = [float(v) for v in b]
+    counts = torch.empty((S, L), dtype=torch.int64, device=dev)
+    sizes = torch.empty((S,), dtype=torch.int32, device=dev)
+    bounds = torch.empty((S, 6), dtype=torch.float64, device=dev)
+    bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+    a.counts, a.tree_sizes, a.bounds, a.out_of_box = counts.data_ptr(), sizes.data_ptr(), bounds.data_ptr(), bad.data_ptr()
+    need = C.c_size_t(0)
+    _lib.check(lib.mdb_overlap_workspace_bytes(C.byref(a), C.byref(need)), 'mdb_overlap_workspace_bytes')
+    ws = torch.empty((max(int(need.value), 1),), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mdb_overlap(C.byref(a), C.c_void_p(st.cuda_stream)), 'mdb_overlap')
+    _count(lib.mdb_overlap_launches())
+    return counts.cpu().numpy(), sizes.cpu().numpy(), bounds.cpu().numpy(), bool(bad.item())
+

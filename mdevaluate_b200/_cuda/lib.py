@@ -33,7 +33,8 @@ EXPORTS = (
     'mdb_corr_plan_launches', 'mdb_corr_plan_destroy', 'mdb_corr_plan_set_wait', 'mdb_corr_plan_timeline',
     'mdb_clock_pair',
     'mdb_comm_create', 'mdb_comm_handle', 'mdb_comm_connect', 'mdb_comm_destroy',
-    'mdb_images_pack', 'mdb_nojump_apply_format', 'mdb_vectors',
+    'mdb_images_pack', 'mdb_nojump_apply_format', 'mdb_vectors', 'mdb_overlap_workspace_bytes', 'mdb_overlap',
+    'mdb_overlap_launches',
 )
 
 
@@ -104,6 +105,21 @@ class VectorsArgs(C.Structure):
     ]
 
 
+class OverlapArgs(C.Structure):
+    _fields_ = [
+        ('ref_coords', C.c_void_p), ('ref_pitch', C.c_int64), ('ref_type', C.c_int32), ('n_ref', C.c_int32),
+        ('ref_images', C.c_void_p), ('ref_image_format', C.c_int32), ('reserved0', C.c_int32),
+        ('ref_img_pitch', C.c_int64), ('ref_box', C.c_void_p), ('ref_box_const', C.c_double * 3),
+        ('ref_rows', C.c_void_p), ('ref_select', C.c_void_p), ('ref_sel_pitch', C.c_int64),
+        ('coords', C.c_void_p), ('pitch', C.c_int64), ('coord_type', C.c_int32), ('n_atoms', C.c_int32),
+        ('images', C.c_void_p), ('image_format', C.c_int32), ('reserved1', C.c_int32), ('img_pitch', C.c_int64),
+        ('box', C.c_void_p), ('box_const', C.c_double * 3), ('rows', C.c_void_p),
+        ('n_origins', C.c_int32), ('n_lags', C.c_int32), ('radius', C.c_double), ('boxsize', C.c_double * 3),
+        ('counts', C.c_void_p), ('tree_sizes', C.c_void_p), ('bounds', C.c_void_p), ('out_of_box', C.c_void_p),
+        ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -142,6 +158,9 @@ def _declare(lib):
     lib.mdb_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
     lib.mdb_comm_destroy.argtypes = [C.c_void_p]
     lib.mdb_vectors.argtypes = [C.POINTER(VectorsArgs), C.c_void_p]
+    lib.mdb_overlap_workspace_bytes.argtypes = [C.POINTER(OverlapArgs), C.POINTER(C.c_size_t)]
+    lib.mdb_overlap.argtypes = [C.POINTER(OverlapArgs), C.c_void_p]
+    lib.mdb_overlap_launches.restype = C.c_int
     lib.mdb_images_pack.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_void_p]
     lib.mdb_nojump_apply_format.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32,

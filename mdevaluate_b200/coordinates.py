@@ -287,6 +287,62 @@ class CoordinatesMap:
         return CoordinatesMap(self.coordinates.nojump, self.function)
 
 
+class DeviceTree:
+    """What ``CoordinatesKDTree[i]`` hands out: the selected atoms of frame i -- the points scipy's cKDTree would be
+    built from -- with the one query ``overlap`` needs, evaluated on the device (``mdb_overlap``)."""
+
+    def __init__(self, points, boxsize=None):
+        self.data = np.asarray(points)
+        if self.data.ndim != 2 or self.data.shape[1] != 3:
+            raise ValueError('a tree holds (n, 3) points')
+        self.n = len(self.data)
+        self.boxsize = None if boxsize is None else np.broadcast_to(np.asarray(boxsize, dtype=np.float64), (3,))
+
+    def count_within(self, frame, radius):
+        """``(tree.query(frame)[0] <= radius).sum()`` of the cKDTree this object stands for."""
+        from . import correlation
+        return correlation._overlap_pair(self, frame, radius)
+
+
+class CoordinatesKDTree:
+    """The trees of the reference configurations ``overlap`` compares with (coordinates.py:415-461): same
+    constructor, ``tree[i]`` is built from ``frames[i][selector(frames[i])]``, cached by an LRU cache.
+
+    There is no KD-tree on the device: :func:`mdevaluate_b200.correlation.shifted_correlation` recognises
+    ``partial(overlap, crds_tree=CoordinatesKDTree(...), radius=...)`` and evaluates the whole schedule with a cell
+    grid per origin (``csrc/overlap_kernels.cu``), in cKDTree's arithmetic.  ``ckdtree`` is accepted and ignored:
+    both scipy trees return the same nearest distances."""
+
+    def clear_cache(self):
+        """Clear the LRU cache."""
+        self._get_tree_at_index.cache_clear()
+
+    @property
+    def cache_info(self):
+        """Return info about the state of the cache."""
+        return self._get_tree_at_index.cache_info()
+
+    def _get_tree_at_index(self, index):
+        frame = self.frames[index]
+        return DeviceTree(np.asarray(frame)[self.selector(frame)], self.boxsize)
+
+    def __init__(self, frames, selector=None, boxsize=None, maxcache=128, ckdtree=True):
+        from functools import lru_cache
+        self.has_selector = selector is not None
+        self.selector = selector if selector is not None else (lambda x: slice(None))
+        self.frames = frames
+        self.boxsize = boxsize
+        self._get_tree_at_index = lru_cache(maxsize=maxcache)(self._get_tree_at_index)
+
+    def __getitem__(self, index):
+        return self._get_tree_at_index(index)
+
+    def __checksum__(self):
+        from .checksum import checksum
+        return checksum(self.selector if self.has_selector else None, self.frames,
+                        None if self.boxsize is None else np.asarray(self.boxsize, dtype=np.float64))
+
+
 def map_coordinates(func):
     """Decorator: ``func(coordinates, **kwargs)`` becomes a :class:`CoordinatesMap` of ``func`` over the frames
     (coordinates.py:464-468)."""

@@ -32,7 +32,7 @@ from .utils import bin_rule, runningmean  # noqa: F401
 
 __all__ = ['log_indices', 'correlation', 'subensemble_correlation', 'multi_subensemble_correlation',
            'shifted_correlation', 'msd', 'isf', 'van_hove_self', 'non_gaussian', 'rotational_autocorrelation',
-           'chi4', 'shifted_correlation_multi']
+           'chi4', 'shifted_correlation_multi', 'overlap']
 
 
 # --------------------------------------------------------------------------------------------
@@ -151,6 +151,113 @@ def rotational_autocorrelation(onset, frame, order=2):
     """Legendre polynomial ``P_order`` of the scalar products of the vectors in ``onset`` and ``frame``,
     averaged (correlation.py:223-236).  The frames hold vectors (e.g. unit bond vectors)."""
     return _pair_value(_Spec('rotational_autocorrelation', order=order), onset, frame)
+
+
+def overlap(onset, frame, crds_tree, radius):
+    """Overlap with a reference configuration (correlation.py:288-312): the fraction -- relative to the size of
+    the tree of frame ``onset.step`` -- of the atoms of ``frame`` that have a tree atom within ``radius``.
+
+    ``crds_tree`` is a :class:`mdevaluate_b200.coordinates.CoordinatesKDTree`.  Through ``shifted_correlation``
+    (``partial(overlap, crds_tree=..., radius=...)``) the whole schedule is one call of ``mdb_overlap``."""
+    tree = crds_tree[onset.step]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return np.int64(tree.count_within(frame, radius)) / tree.n
+
+
+def _overlap_pair(tree, frame, radius):
+    """One tree against one frame (both host arrays): ``mdb_overlap`` with a single (origin, lag) pair."""
+    frame = np.asarray(frame)
+    if frame.ndim != 2 or frame.shape[1] != 3:
+        raise ValueError('frame must be an (N, 3) array')
+    if tree.n == 0 or len(frame) == 0:
+        return 0
+    tree_store, _ = _store_from_host_frames([tree.data])
+    store, _ = _store_from_host_frames([frame])
+    counts, _, _, bad = engine.overlap_counts(tree_store, np.zeros(1, np.int32), store, np.zeros((1, 1), np.int32),
+                                              radius, tree.boxsize)
+    if bad:
+        raise ValueError('Some input data are outside of the periodic box (cKDTree needs 0 <= x < boxsize).')
+    return int(counts[0, 0])
+
+
+def _overlap_request(function):
+    """``(tree, radius)`` if ``function`` is ``overlap`` with its tree and radius bound, else None."""
+    kwargs = {}
+    fn = function
+    while isinstance(fn, functools.partial):
+        if fn.args:
+            return None
+        merged = dict(fn.keywords)
+        merged.update(kwargs)
+        kwargs = merged
+        fn = fn.func
+    module = getattr(fn, '__module__', '') or ''
+    if getattr(fn, '__name__', None) != 'overlap' or not (fn is overlap or module.endswith('correlation')
+                                                          or module.endswith('md_oracle')):
+        return None
+    extra = set(kwargs) - {'crds_tree', 'radius'}
+    if extra:
+        raise TypeError('overlap() got unexpected keyword arguments %s' % sorted(extra))
+    if 'crds_tree' not in kwargs or 'radius' not in kwargs:
+        raise TypeError("overlap() needs 'crds_tree' and 'radius' bound with functools.partial")
+    from .coordinates import CoordinatesKDTree
+    if not isinstance(kwargs['crds_tree'], CoordinatesKDTree):
+        raise NotImplementedError('overlap on the B200 path needs a mdevaluate_b200.coordinates.CoordinatesKDTree; '
+                                  'there is no CPU fallback')
+    return kwargs['crds_tree'], float(kwargs['radius'])
+
+
+MAX_OVERLAP_TREE_ATOMS = 1 << 27      # tree atoms (origins x atoms) one mdb_overlap call sorts; more: origin batches
+
+
+def _overlap_schedule(frames, tree, radius, frame_ids):
+    """The overlap of every (origin, lag) of a schedule: values (S, L) float64."""
+    from .coordinates import Coordinates
+    if getattr(frames, 'comm', None) is not None:
+        raise NotImplementedError('overlap needs every atom of the reference configuration on one GPU: '
+                                  'atom-sharded coordinates are not supported')
+    store, rows, _, _, _ = _provider(frames, frame_ids)
+    # the step of the origin frames (CoordinateFrame.step, coordinates.py:266): the frame number for Coordinates
+    if isinstance(frames, Coordinates):
+        steps = np.asarray(frame_ids[:, 0], dtype=np.int64)
+    else:
+        steps = np.array([int(frames[int(i)].step) for i in frame_ids[:, 0]], dtype=np.int64)
+    tree_frames = tree.frames
+    if isinstance(tree_frames, Coordinates):
+        n_tree_frames = len(tree_frames)
+        if ((steps < -n_tree_frames) | (steps >= n_tree_frames)).any():
+            raise IndexError('frame out of range')
+        steps = np.where(steps < 0, steps + n_tree_frames, steps)
+    tree_store, tree_rows, _, _, tree_comm = _provider(tree_frames, steps[:, None])
+    if tree_comm is not None:
+        raise NotImplementedError('overlap needs every atom of the reference configuration on one GPU')
+    select = None
+    sizes_host = None
+    if tree.has_selector:
+        picked = [_selector_mask(tree.selector(tree_frames[int(i)]), tree_store.n_atoms) for i in steps]
+        masks = np.stack([m for m, _ in picked])
+        sizes_host = np.array([c for _, c in picked])
+        torch = _lib.require_cuda()
+        pitch = (masks.shape[1] + 3) // 4 * 4
+        host = np.zeros((masks.shape[0], pitch), dtype=np.uint8)
+        host[:, :masks.shape[1]] = masks
+        select = torch.from_numpy(host).to(tree_store.device)
+    S = len(steps)
+    batch = max(1, MAX_OVERLAP_TREE_ATOMS // max(1, tree_store.n_atoms))
+    counts = np.empty(rows.shape, dtype=np.int64)
+    sizes = np.empty(S, dtype=np.int64)
+    for s0 in range(0, S, batch):
+        s1 = min(S, s0 + batch)
+        cnt, n_tree, _, bad = engine.overlap_counts(tree_store, tree_rows[s0:s1, 0], store, rows[s0:s1], radius,
+                                                    tree.boxsize, None if select is None else select[s0:s1])
+        if bad:
+            raise ValueError('Some input data are outside of the periodic box (cKDTree needs 0 <= x < boxsize).')
+        counts[s0:s1] = cnt
+        sizes[s0:s1] = n_tree
+    if sizes_host is not None and not np.array_equal(sizes, sizes_host):      # pragma: no cover
+        raise CudaPathError('tree sizes on the device differ from the selector\'s')
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return counts / sizes[:, None]
 
 
 _KNOWN = {'msd': msd, 'isf': isf, 'van_hove_self': van_hove_self, 'non_gaussian': non_gaussian,
@@ -627,7 +734,7 @@ def _fixed_checksum(function, version_nr):
     function.__checksum__ = lambda: fixed
 
 
-for _f in (log_indices, correlation, msd, isf, van_hove_self, non_gaussian, rotational_autocorrelation):
+for _f in (log_indices, correlation, msd, isf, van_hove_self, non_gaussian, rotational_autocorrelation, overlap):
     _fixed_checksum(_f, 1)
 del _f
 
@@ -722,6 +829,14 @@ def shifted_correlation(function, frames, index_distribution=log_indices, correl
             hit = _cached_call(call_key, res_key, frames, average)
             if hit is not None:
                 return hit
+    request = _overlap_request(function)
+    if request is not None:
+        if not plain:
+            raise NotImplementedError('overlap is evaluated with the default correlation strategy only')
+        start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
+        frame_ids = _frame_ids(start_frames, idx, len(frames))
+        values = _overlap_schedule(frames, request[0], request[1], frame_ids)
+        return _times(frames, idx), _average(values, len(start_frames), average)
     spec = _kernel_spec(function)
     start_frames, idx = _schedule(frames, index_distribution, segments, window, skip)
     frame_ids = _frame_ids(start_frames, idx, len(frames))

@@ -18,7 +18,7 @@ LIB = os.path.join(OUT_DIR, 'libmdevaluate_b200.so')
 # in parallel (0 direct-load kernels, 1-3 bulk kernels without / with byte / with packed image counts)
 UNITS = [('abi.cu', 'abi.o', []), ('corr_host.cu', 'corr_host.o', []), ('comm.cu', 'comm.o', []),
          ('nojump_kernels.cu', 'nojump_kernels.o', []), ('dense_kernels.cu', 'dense_kernels.o', []),
-         ('vector_kernels.cu', 'vector_kernels.o', [])] + [
+         ('vector_kernels.cu', 'vector_kernels.o', []), ('overlap_kernels.cu', 'overlap_kernels.o', [])] + [
     ('corr_kernels.cu', 'corr_kernels_%d.o' % part, ['-DMDB_CORR_PART=%d' % part]) for part in range(4)]
 SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ['common.cuh', 'corr_core.cuh', os.path.join('..', '..', 'include', 'mdevaluate_b200.h')]

@@ -29,7 +29,7 @@ __all__ = [
     "log_indices", "lin_indices", "schedule", "pairwise", "shifted_correlation",
     "msd", "isf", "van_hove_self", "non_gaussian", "histogram", "runningmean",
     "chi4", "jump_table", "image_counts", "unwrap_frame", "TimedFrame",
-    "ArrayTrajectory", "UnwrappedTrajectory",
+    "ArrayTrajectory", "UnwrappedTrajectory", "nearest_distances", "NearestTree", "FrameTrees", "overlap",
 ]
 
 
@@ -246,6 +246,78 @@ def non_gaussian(onset, frame):
 def chi4(n_atoms, fqt):
     """examples/plot_chi4.py:29-37: ``len(OW[0]) * Fqt.var(axis=0)`` on the (S, L) ISF."""
     return n_atoms * np.asarray(fqt).var(axis=0)
+
+
+# --------------------------------------------------------------------------- #
+# overlap with a reference configuration (correlation.py:288-312 on coordinates.CoordinatesKDTree, :415-455)
+# --------------------------------------------------------------------------- #
+def nearest_distances(points, queries, boxsize=None, chunk=256):
+    """Distance of every query point to its nearest tree point: what ``scipy.spatial.cKDTree(points,
+    boxsize=boxsize).query(queries)[0]`` returns (k=1, p=2), restated by brute force.
+
+    scipy (1.18.1 here; the reference pins no version, ``setup.py:26``) is a third-party dependency of the reference,
+    not part of its tree.  Its arithmetic, from ckdtree/src (``distance_base.h``, ``distance.h``, ``query.cxx``):
+    everything in float64; ``s = dx*dx; s += dy*dy; s += dz*dz`` (no fused multiply-add); a periodic tree wraps the
+    query point, ``x - floor(x / L) * L`` (``BoxDist1D::wrap_position``), and every difference, ``d < -L/2: d + L;
+    d > L/2: d - L`` (``wrap_distance``); the result is ``sqrt(min s)``.  ``tests/test_oracle_golden.py`` checks this
+    function against scipy itself, bit for bit.
+    """
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    queries = np.ascontiguousarray(queries, dtype=np.float64)
+    out = np.full(len(queries), np.inf)
+    if len(points) == 0:
+        return out
+    box = None
+    if boxsize is not None:
+        box = np.broadcast_to(np.asarray(boxsize, dtype=np.float64), (3,))
+        periodic = box > 0
+        safe = np.where(periodic, box, 1.0)
+        wrapped = queries - np.floor(queries / safe) * safe
+        wrapped = np.where(wrapped >= safe, wrapped - safe, wrapped)
+        wrapped = np.where(wrapped < 0, wrapped + safe, wrapped)
+        queries = np.where(periodic, wrapped, queries)
+        half = 0.5 * box
+    for c0 in range(0, len(queries), chunk):
+        d = queries[c0:c0 + chunk, None, :] - points[None, :, :]
+        if box is not None:
+            d = np.where(periodic & (d < -half), d + box, np.where(periodic & (d > half), d - box, d))
+        s = d[..., 0] * d[..., 0]
+        s = s + d[..., 1] * d[..., 1]
+        s = s + d[..., 2] * d[..., 2]
+        out[c0:c0 + chunk] = np.sqrt(s.min(axis=1))
+    return out
+
+
+class NearestTree:
+    """Stands for one ``cKDTree``: ``.n`` points and ``.query(x)[0]`` nearest distances."""
+
+    def __init__(self, points, boxsize=None):
+        self.data = np.asarray(points, dtype=np.float64)
+        self.n = len(self.data)
+        self.boxsize = boxsize
+
+    def query(self, x):
+        return nearest_distances(self.data, x, self.boxsize), None
+
+
+class FrameTrees:
+    """coordinates.CoordinatesKDTree (coordinates.py:415-455): ``trees[i]`` is the tree of
+    ``frames[i][selector(frames[i])]``."""
+
+    def __init__(self, frames, selector=None, boxsize=None):
+        self.frames = frames
+        self.selector = selector if selector is not None else (lambda x: slice(None))
+        self.boxsize = boxsize
+
+    def __getitem__(self, index):
+        frame = self.frames[index]
+        return NearestTree(np.asarray(frame)[self.selector(frame)], self.boxsize)
+
+
+def overlap(onset, frame, crds_tree, radius):
+    """mdevaluate/correlation.py:288-312."""
+    tree = crds_tree[onset.step]
+    return (tree.query(frame)[0] <= radius).sum() / tree.n
 
 
 # --------------------------------------------------------------------------- #

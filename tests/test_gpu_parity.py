@@ -1124,3 +1124,113 @@ def test_multi_subensembles_in_one_pass(md, monkeypatch):
                                                   correlation=orc.multi_subensemble_pairwise(overlapping))
     np.testing.assert_array_equal(n_ov, n_ov_ref)
     close(ov, np.asarray(ov_ref))
+
+
+def _half_selector(frame):
+    return np.where(np.asarray(frame)[:, 0] < 0.75)[0]
+
+
+def test_overlap_equals_the_reference(golden, md):
+    """correlation.overlap through shifted_correlation (correlation.py:288-312 on coordinates.CoordinatesKDTree,
+    coordinates.py:415-455): integer counts / tree size, so the values are IDENTICAL to the reference + scipy's
+    cKDTree (tests/golden/overlap.npz) -- open tree, periodic tree, tree of a per-origin selection, nojump frames."""
+    from mdevaluate_b200._cuda import engine
+    from mdevaluate_b200.coordinates import CoordinatesKDTree
+    g = golden('overlap')
+    c = md.correlation
+    coords = md.Coordinates(md.MemoryReader(g['pos'], g['box'], g['times']))
+    box_len = float(g['box'][0])
+    kw = dict(segments=8, window=0.4)
+    launches = engine.launches()
+    for radius in (0.03, 0.06):
+        t, r = c.shifted_correlation(partial(c.overlap, crds_tree=CoordinatesKDTree(coords), radius=radius), coords, **kw)
+        np.testing.assert_array_equal(t, g['t'])
+        np.testing.assert_array_equal(r, g['open_%g' % radius])
+        tree = CoordinatesKDTree(coords, boxsize=box_len)
+        _, r = c.shifted_correlation(partial(c.overlap, crds_tree=tree, radius=radius), coords, **kw)
+        np.testing.assert_array_equal(r, g['periodic_%g' % radius])
+    assert engine.launches() > launches
+    tree = CoordinatesKDTree(coords, selector=_half_selector, boxsize=box_len)
+    _, r = c.shifted_correlation(partial(c.overlap, crds_tree=tree, radius=0.05), coords, **kw)
+    np.testing.assert_array_equal(r, g['selector_0.05'])
+    _, r = c.shifted_correlation(partial(c.overlap, crds_tree=CoordinatesKDTree(coords.nojump), radius=0.05),
+                                 coords.nojump, average=True, **kw)
+    np.testing.assert_array_equal(r, g['nojump_avg_0.05'])
+    # called like a plain function (one tree, one frame), as the reference allows
+    onset, frame = coords[3], coords[90]
+    for tree, key in ((CoordinatesKDTree(coords), 'dist_open'), (CoordinatesKDTree(coords, boxsize=box_len), 'dist_periodic')):
+        for radius in (0.02, 0.05, float(np.sort(g[key])[200])):      # the last one: a distance that occurs exactly
+            assert c.overlap(onset, frame, tree, radius) == (g[key] <= radius).sum() / len(onset)
+    assert tree.cache_info.currsize == 1
+    tree.clear_cache()
+    assert tree.cache_info.currsize == 0
+
+
+def test_overlap_edge_cases(md):
+    """Radii from nothing to everything, a radius beyond half the periodic box (one or two cells per dimension), an
+    empty tree, atoms outside a periodic box (cKDTree raises ValueError), frames far outside an open tree's bounds --
+    against the oracle's brute force in cKDTree's arithmetic."""
+    import oracle.md_oracle as orc
+    from mdevaluate_b200.coordinates import CoordinatesKDTree, DeviceTree
+    c = md.correlation
+    rng = np.random.default_rng(5)
+    n, length = 3000, 2.0
+    pts = (rng.random((n, 3)) * length).astype(np.float32)
+    qry = (pts + rng.normal(0, 0.08, (n, 3))).astype(np.float32)
+    qry[:50] += 7.0                                     # far outside an open tree; wrapped back by a periodic one
+    for box in (None, length, np.array([length, 0.0, length])):
+        want = orc.nearest_distances(pts, qry, box)
+        tree = DeviceTree(pts, box)
+        for radius in (0.0, 1e-9, 0.01, 0.05, 0.31, 0.9, 1.5, 5.0, 100.0, -1.0):
+            assert tree.count_within(qry, radius) == int((want <= radius).sum()), (box, radius)
+    # float64 points and frames
+    pts64 = rng.random((800, 3)) * length
+    qry64 = pts64 + rng.normal(0, 0.05, (800, 3))
+    want = orc.nearest_distances(pts64, qry64)
+    assert DeviceTree(pts64).count_within(qry64, 0.07) == int((want <= 0.07).sum())
+    # one tree atom, no tree atom
+    assert DeviceTree(pts[:1]).count_within(qry, 0.3) == int((orc.nearest_distances(pts[:1], qry) <= 0.3).sum())
+    assert DeviceTree(pts[:0]).count_within(qry, 0.3) == 0
+    with pytest.raises(ValueError):
+        DeviceTree(pts + 1.0, length).count_within(qry, 0.1)
+    # all atoms in a plane (zero extent along z)
+    flat = pts.copy()
+    flat[:, 2] = 0.5
+    want = orc.nearest_distances(flat, qry)
+    assert DeviceTree(flat).count_within(qry, 0.2) == int((want <= 0.2).sum())
+    # an empty selection in shifted_correlation: 0 / 0 like the reference
+    pos, box3, times = md.synthetic.random_walk(200, 60, seed=3, sigma=0.02, box=1.2)
+    coords = md.Coordinates.from_arrays(pos, box3, times)
+    tree = CoordinatesKDTree(coords, selector=lambda f: np.zeros(len(f), dtype=bool))
+    _, r = c.shifted_correlation(partial(c.overlap, crds_tree=tree, radius=0.1), coords, segments=3, window=0.3)
+    assert np.isnan(r).all()
+
+
+@pytest.mark.parametrize('n_atoms', [100_000])
+def test_overlap_at_size(md, n_atoms):
+    """Water-like density (33.4 atoms / nm^3), radius 0.11 nm: the schedule's counts against the oracle on a sample of
+    (origin, lag) pairs, the trivial lag 0 (every atom overlaps itself) and the decay with the lag."""
+    import oracle.md_oracle as orc
+    from mdevaluate_b200.coordinates import CoordinatesKDTree
+    from mdevaluate_b200.synthetic import random_walk, box_length
+    c = md.correlation
+    pos, box, times = random_walk(n_atoms, 120, seed=9, sigma=0.02, box=box_length(n_atoms))
+    coords = md.Coordinates.from_arrays(pos, box, times)
+    tree = CoordinatesKDTree(coords, boxsize=float(box[0]))
+    t, r = c.shifted_correlation(partial(c.overlap, crds_tree=tree, radius=0.11), coords, segments=4, window=0.5)
+    assert r.shape[0] == 4 and np.all(r[:, 0] == 1.0)
+    mean = r.mean(axis=0)
+    assert np.all(np.diff(mean)[:8] <= 0) and np.all(np.diff(mean)[2:8] < 0) and 0.0 < mean[-1] < mean[3]
+    start, idx = orc.schedule(len(coords), 4, 0.5)[0], orc.log_indices(0, 60)
+    sub = slice(0, 2000)
+    for s, l in ((0, 1), (2, 7), (3, len(idx) - 1)):
+        want = orc.nearest_distances(pos[start[s]], pos[start[s] + idx[l]][sub], float(box[0]))
+        orc_count = int((want <= 0.11).sum())
+        one = md.coordinates.DeviceTree(pos[start[s]], float(box[0])).count_within(pos[start[s] + idx[l]][sub], 0.11)
+        assert one == orc_count, (s, l)
+    # the whole frame pairs: sums of sub-blocks add up (atoms are independent queries)
+    s, l = 1, 5
+    whole = int(round(r[s, l] * n_atoms))
+    parts = sum(md.coordinates.DeviceTree(pos[start[s]], float(box[0])).count_within(pos[start[s] + idx[l]][a:a + 25000], 0.11)
+                for a in range(0, n_atoms, 25000))
+    assert whole == parts

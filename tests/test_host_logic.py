@@ -316,3 +316,32 @@ def test_vectors_map_on_raw_frames_matches_the_reference(golden):
     for k, i in enumerate((5, 100)):
         np.testing.assert_array_equal(np.asarray(unnormed[i]), g['vec_raw_unnormed'][k])
     assert vec[10:]._slice == slice(10, None) and vec.description.startswith('vectors')
+
+
+def test_overlap_request_and_tree_cache():
+    """Host side of correlation.overlap: the partial is recognised, its arguments are checked like a Python call, the
+    tree class keeps the reference's constructor and LRU cache (coordinates.py:415-461) -- no device needed."""
+    from functools import partial
+    import mdevaluate_b200 as md
+    from mdevaluate_b200 import correlation as c
+    from mdevaluate_b200.coordinates import CoordinatesKDTree, DeviceTree
+    pos, box, times = md.synthetic.random_walk(30, 12, seed=1, sigma=0.02, box=1.0)
+    coords = md.Coordinates.from_arrays(pos, box, times)
+    tree = CoordinatesKDTree(coords, selector=lambda f: np.arange(5), boxsize=1.0, maxcache=4)
+    assert c._overlap_request(partial(c.msd)) is None
+    got = c._overlap_request(partial(partial(c.overlap, crds_tree=tree), radius=0.1))
+    assert got[0] is tree and got[1] == 0.1
+    with pytest.raises(TypeError):
+        c._overlap_request(partial(c.overlap, crds_tree=tree))
+    with pytest.raises(TypeError):
+        c._overlap_request(partial(c.overlap, crds_tree=tree, radius=0.1, q=3))
+    with pytest.raises(NotImplementedError):
+        c._overlap_request(partial(c.overlap, crds_tree=object(), radius=0.1))
+    node = tree[3]
+    assert isinstance(node, DeviceTree) and node.n == 5 and tree[3] is node
+    np.testing.assert_array_equal(node.data, np.asarray(coords[3])[:5])
+    assert tree.cache_info.hits == 1 and tree.cache_info.currsize == 1
+    tree.clear_cache()
+    assert tree.cache_info.currsize == 0
+    assert md.checksum.checksum(tree) == md.checksum.checksum(CoordinatesKDTree(coords, selector=tree.selector, boxsize=1.0))
+    assert md.checksum.checksum(tree) != md.checksum.checksum(CoordinatesKDTree(coords, boxsize=1.0))

@@ -190,3 +190,45 @@ def test_rotational_autocorrelation_golden(golden):
                                            window=0.5)
             same(r, g['rot%d_%s' % (order, tag)])
         same(t, g['rot_t'])
+
+
+def _half_selector(frame):
+    return np.where(np.asarray(frame)[:, 0] < 0.75)[0]
+
+
+def test_overlap_golden(golden):
+    """correlation.overlap on a CoordinatesKDTree (correlation.py:288-312, coordinates.py:415-455): the oracle's brute
+    force restatement of cKDTree's nearest distance equals the reference + scipy bit for bit -- open and periodic
+    trees, a tree of a selection, nojump frames."""
+    g = golden('overlap')
+    pos, box, times = g['pos'], g['box'], g['times']
+    raw = orc.ArrayTrajectory(pos, box.astype(np.float64), times)
+    kw = dict(segments=8, window=0.4)
+    np.testing.assert_array_equal(orc.nearest_distances(raw[3], raw[90]), g['dist_open'])
+    np.testing.assert_array_equal(orc.nearest_distances(raw[3], raw[90], float(box[0])), g['dist_periodic'])
+    for radius in (0.03, 0.06):
+        t, r = orc.shifted_correlation(partial(orc.overlap, crds_tree=orc.FrameTrees(raw), radius=radius), raw, **kw)
+        np.testing.assert_array_equal(t, g['t'])
+        np.testing.assert_array_equal(r, g['open_%g' % radius])
+        trees = orc.FrameTrees(raw, boxsize=float(box[0]))
+        _, r = orc.shifted_correlation(partial(orc.overlap, crds_tree=trees, radius=radius), raw, **kw)
+        np.testing.assert_array_equal(r, g['periodic_%g' % radius])
+    trees = orc.FrameTrees(raw, selector=_half_selector, boxsize=float(box[0]))
+    _, r = orc.shifted_correlation(partial(orc.overlap, crds_tree=trees, radius=0.05), raw, **kw)
+    np.testing.assert_array_equal(r, g['selector_0.05'])
+    unw = orc.UnwrappedTrajectory(pos, box, times)
+    _, r = orc.shifted_correlation(partial(orc.overlap, crds_tree=orc.FrameTrees(unw), radius=0.05), unw, average=True,
+                                   **kw)
+    np.testing.assert_array_equal(r, g['nojump_avg_0.05'])
+
+
+def test_nearest_distances_equal_scipy():
+    """The restatement against scipy's cKDTree itself (the third-party code the reference calls), where scipy is
+    installed: points outside a periodic box, a box periodic in two dimensions only, float32 input."""
+    spatial = pytest.importorskip('scipy.spatial')
+    rng = np.random.default_rng(8)
+    for n, length, box in ((1500, 2.0, None), (1500, 2.0, 2.0), (600, 1.0, np.array([1.0, 0.0, 1.0]))):
+        pts = (rng.random((n, 3)) * length).astype(np.float32)
+        qry = (pts + rng.normal(0, 0.05, (n, 3))).astype(np.float32)
+        want = spatial.cKDTree(pts, boxsize=box).query(qry)[0]
+        np.testing.assert_array_equal(orc.nearest_distances(pts, qry, box), want)
