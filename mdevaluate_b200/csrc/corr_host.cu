@@ -589,9 +589,16 @@ extern "C" int mdb_corr_plan_launch(mdb_corr_plan *pl, void *stream, int32_t tim
     pl->host_ns[0] = steady_ns();
     LaunchTiming tm;
     if (time_slot >= 0) {
+        // events are created in groups of 64 slots the first time a slot of the group is used (all 2048
+        // cudaEventCreate calls at once cost a millisecond -- inside whatever the caller was timing)
         if (!pl->have_events) {
-            for (int i = 0; i < 2 * MDB_PLAN_TIME_SLOTS; ++i) MDB_CUDA_CHECK(cudaEventCreate(&pl->events[i]));
+            for (int i = 0; i < 2 * MDB_PLAN_TIME_SLOTS; ++i) pl->events[i] = nullptr;
             pl->have_events = true;
+        }
+        if (!pl->events[2 * time_slot]) {
+            const int first = time_slot & ~63;
+            for (int i = 2 * first; i < 2 * (first + 64); ++i)
+                if (!pl->events[i]) MDB_CUDA_CHECK(cudaEventCreate(&pl->events[i]));
         }
         tm.start = pl->events[2 * time_slot];
         tm.stop = pl->events[2 * time_slot + 1];
@@ -673,7 +680,7 @@ extern "C" int mdb_corr_plan_run(mdb_corr_plan *pl, void *stream, int32_t time_s
 
 extern "C" int mdb_corr_plan_kernel_ms(mdb_corr_plan *pl, int32_t time_slot, float *ms) {
     if (!pl || !ms) return fail(MDB_ERR_ARGUMENT, "NULL argument");
-    if (time_slot < 0 || time_slot >= MDB_PLAN_TIME_SLOTS || !pl->have_events)
+    if (time_slot < 0 || time_slot >= MDB_PLAN_TIME_SLOTS || !pl->have_events || !pl->events[2 * time_slot + 1])
         return fail(MDB_ERR_ARGUMENT, "no timed run in that slot");
     MDB_CUDA_CHECK(cudaEventSynchronize(pl->events[2 * time_slot + 1]));
     MDB_CUDA_CHECK(cudaEventElapsedTime(ms, pl->events[2 * time_slot], pl->events[2 * time_slot + 1]));
@@ -733,7 +740,8 @@ extern "C" int mdb_corr_plan_destroy(mdb_corr_plan *pl) {
     if (!pl) return MDB_OK;
     if (pl->pending && pl->last_stream) cudaStreamSynchronize(pl->last_stream);
     if (pl->have_events)
-        for (int i = 0; i < 2 * MDB_PLAN_TIME_SLOTS; ++i) cudaEventDestroy(pl->events[i]);
+        for (int i = 0; i < 2 * MDB_PLAN_TIME_SLOTS; ++i)
+            if (pl->events[i]) cudaEventDestroy(pl->events[i]);
     if (pl->device_block) cudaFree(pl->device_block);
     if (pl->host_block) cudaFreeHost(pl->host_block);
     delete pl;
