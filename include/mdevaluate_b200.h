@@ -63,7 +63,8 @@ typedef struct mdb_tuning {
     int32_t scan_direct;     /* 1: register-load variant of the jump scan instead of the bulk-copy ring       */
     int32_t dense_stage_cta; /* 1: CTA-wide staging loop of the float64 dense kernel instead of warp-per-row  */
     int32_t dense_float64;   /* 1: dense schedules through the float64 tile (default: float32 offsets, v2)    */
-    int32_t reserved[1];
+    int32_t dense_variant;   /* bit 0: general origin loop even when every frame is an origin (no rotating row
+                              * window); bit 1: float64 staging even when the box lengths are float32 numbers   */
 } mdb_tuning;
 
 /* coordinate element type */
@@ -408,7 +409,8 @@ typedef struct mdb_overlap_args {
     int32_t n_atoms;
     const void *images;
     int32_t image_format;
-    int32_t reserved1;
+    int32_t file_order;          /* 1: query the atoms in file order even when the tree holds all of them
+                                  * (default: in the order of the origin's sorted tree, which coalesces)   */
     int64_t img_pitch;
     const double *box;
     double box_const[3];

@@ -38,7 +38,7 @@ class Tuning:
     """Explicit kernel switches (``mdb_tuning`` of the C ABI); 0 = the measured default.  Process-wide, read at every
     launch / plan creation.  ``engine.tuning.isf_float64 = 1`` e.g. sends the ISF through the float64 chain."""
     FIELDS = ('ring_stages', 'atom_blocks', 'isf_float64', 'hist_float64', 'scan_direct', 'dense_stage_cta',
-              'dense_float64')
+              'dense_float64', 'dense_variant')
 
     def __init__(self):
         for f in self.FIELDS:
@@ -664,6 +664,9 @@ def _fill_frame_rows(a, prefix, store):
         setattr(a, prefix + 'box', store.box.data_ptr())
 
 
+overlap_file_order = False      # measurement switch: query atoms in file order instead of the tree's cell order
+
+
 def overlap_counts(tree_store, tree_rows, store, rows, radius, boxsize=None, tree_select=None, stream=None):
     """``mdb_overlap``: for every (origin, lag) the number of atoms of frame ``rows[s, l]`` of ``store`` that have an
     atom of the tree of origin s -- row ``tree_rows[s]`` of ``tree_store``, restricted to ``tree_select[s]`` (uint8
@@ -694,6 +697,7 @@ def overlap_counts(tree_store, tree_rows, store, rows, radius, boxsize=None, tre
         a.ref_select = tree_select.data_ptr()
         a.ref_sel_pitch = tree_select.stride(0)
     a.n_origins, a.n_lags = S, L
+    a.file_order = 1 if overlap_file_order else 0
     a.radius = float(radius)
     if boxsize is not None:
         b = np.broadcast_to(np.asarray(boxsize, dtype=np.float64), (3,))

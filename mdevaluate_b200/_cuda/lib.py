@@ -46,7 +46,7 @@ class Tuning(C.Structure):
     """mdb_tuning: explicit kernel switches, 0 = the measured default."""
     _fields_ = [('ring_stages', C.c_int32), ('atom_blocks', C.c_int32), ('isf_float64', C.c_int32),
                 ('hist_float64', C.c_int32), ('scan_direct', C.c_int32), ('dense_stage_cta', C.c_int32),
-                ('dense_float64', C.c_int32), ('reserved', C.c_int32 * 1)]
+                ('dense_float64', C.c_int32), ('dense_variant', C.c_int32)]
 
 
 class CorrArgs(C.Structure):
@@ -112,7 +112,7 @@ class OverlapArgs(C.Structure):
         ('ref_img_pitch', C.c_int64), ('ref_box', C.c_void_p), ('ref_box_const', C.c_double * 3),
         ('ref_rows', C.c_void_p), ('ref_select', C.c_void_p), ('ref_sel_pitch', C.c_int64),
         ('coords', C.c_void_p), ('pitch', C.c_int64), ('coord_type', C.c_int32), ('n_atoms', C.c_int32),
-        ('images', C.c_void_p), ('image_format', C.c_int32), ('reserved1', C.c_int32), ('img_pitch', C.c_int64),
+        ('images', C.c_void_p), ('image_format', C.c_int32), ('file_order', C.c_int32), ('img_pitch', C.c_int64),
         ('box', C.c_void_p), ('box_const', C.c_double * 3), ('rows', C.c_void_p),
         ('n_origins', C.c_int32), ('n_lags', C.c_int32), ('radius', C.c_double), ('boxsize', C.c_double * 3),
         ('counts', C.c_void_p), ('tree_sizes', C.c_void_p), ('bounds', C.c_void_p), ('out_of_box', C.c_void_p),

@@ -56,6 +56,9 @@ struct DenseDev {
     int ks;                 // origins per block
     int n_sblocks, n_lblocks, n_splits, tiles_per_split, n_tiles;
     double *partial;        // [n_splits][L][2]
+    int stage_f32;          // v2: the box is a float32 number in every dimension -> offsets without the float64 pipe
+    float neg_box_f[3];     // -box as float32 (exact when stage_f32)
+    uint32_t magic23;       // 0x4B000000 as a register operand (image_float, common.cuh)
 };
 
 __device__ __forceinline__ int row_of(const DenseDev &p, int frame) {
@@ -409,11 +412,90 @@ __device__ __forceinline__ void stage_rows_v2(const DenseDev &p, int lane, int w
     }
 }
 
+// The same staging WITHOUT float64 and without conversions, for a box whose lengths are float32 numbers (what a
+// reader of float32 trajectories delivers).  offset = (x - n L) - (xr - nr L) = x - xr - k L with k = n - nr:
+// k = 0 (nearly every value): fl(x - xr) is the exact difference rounded once -- bit-identical to the float64 chain
+// followed by its float32 rounding.  k != 0: the operand on the far side of the boundary is moved first (k > 0:
+// (x - kL) - xr, k < 0: x - (xr + kL)), one FMA each, exact by Sterbenz when the moved operand lies in [L/2, L] and
+// good to ulp(offset) otherwise -- the construction of process_tile_f32d in corr_kernels.cu.  Image counts become
+// floats by one byte-permute.  About 6 instructions per value instead of 11, none on the XU or FP64 pipes (which the
+// ISF's rsqrt needs): profiles/r2_ncu_dense_v2.txt had the staging at 36 % of all instructions.
+template <bool IMG, bool FULL>
+__device__ __forceinline__ void stage_rows_v2_f32(const DenseDev &p, int lane, int warp, int atom0, int ns, int n_rows,
+                                                  int f_origin0, int f_partner0, float *s_rows) {
+    const int t = lane & 15, half = lane >> 4;
+    const long long e0 = 3ll * atom0 + 12 * t, e_end = 3ll * p.n_atoms;
+    const float *src0 = p.coords + e0;
+    const uint8_t *img0 = IMG ? p.images + e0 : nullptr;
+    const uint32_t magic = p.magic23;
+    auto load = [&](long long row, float (&x)[12], uint32_t (&n)[3]) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            n[q] = 0x80808080u;
+            if (FULL || e0 + 4 * q < e_end) {
+                v = __ldg(reinterpret_cast<const float4 *>(src0 + row * p.pitch) + q);
+                if (IMG) n[q] = __ldg(reinterpret_cast<const uint32_t *>(img0 + row * p.img_pitch) + q);
+            }
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    };
+    float xr[12];
+    uint32_t nr[3];
+    load(row_of(p, f_origin0), xr, nr);
+    f32x2 fr[6];                                               // the reference's image counts as floats 2^23 + byte
+#pragma unroll
+    for (int k = 0; k < 12; k += 2)
+        fr[k / 2] = pack2(image_float(nr[k >> 2], k & 3, magic), image_float(nr[(k + 1) >> 2], (k + 1) & 3, magic));
+    for (int rb = 2 * warp + half; rb < n_rows; rb += 16 * kV2RowBatch) {
+        float x[kV2RowBatch][12];
+        uint32_t n[kV2RowBatch][3];
+#pragma unroll
+        for (int u = 0; u < kV2RowBatch; ++u) {
+            const int r = min(rb + 16 * u, n_rows - 1);
+            const int frame = (r < ns) ? f_origin0 + r * p.ostep : f_partner0 + (r - ns);
+            load(row_of(p, frame), x[u], n[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kV2RowBatch; ++u) {
+            const int r = min(rb + 16 * u, n_rows - 1);
+            float w[12];
+#pragma unroll
+            for (int k = 0; k < 12; k += 2) {                  // packed pairs: components (k, k + 1) % 3
+                const f32x2 xv = pack2(x[u][k], x[u][k + 1]), rv = pack2(xr[k], xr[k + 1]);
+                f32x2 off;
+                if (IMG) {
+                    const f32x2 nb = pack2(p.neg_box_f[k % 3], p.neg_box_f[(k + 1) % 3]);
+                    const f32x2 dn = sub2(pack2(image_float(n[u][k >> 2], k & 3, magic),
+                                                image_float(n[u][(k + 1) >> 2], (k + 1) & 3, magic)), fr[k / 2]);
+                    float d0, d1;
+                    unpack2(dn, d0, d1);
+                    const f32x2 up = pack2(fmaxf(d0, 0.0f), fmaxf(d1, 0.0f));   // images this row's value is moved by
+                    const f32x2 dw = sub2(up, dn);                              // images the reference is moved by
+                    off = sub2(fma2(up, nb, xv), fma2(dw, nb, rv));
+                } else {
+                    off = sub2(xv, rv);
+                }
+                unpack2(off, w[k], w[k + 1]);
+            }
+            float4 *dst = reinterpret_cast<float4 *>(s_rows + (size_t)r * kV2RowFloats) + t;      // atoms 4t..4t+3
+            dst[0] = make_float4(w[0], w[3], w[6], w[9]);                        // x of the four atoms
+            dst[kTileAtoms / 4] = make_float4(w[1], w[4], w[7], w[10]);          // y
+            dst[2 * (kTileAtoms / 4)] = make_float4(w[2], w[5], w[8], w[11]);    // z
+        }
+    }
+}
+
 __device__ __forceinline__ f32x2 lds_pair(const float *ptr) {
     return *reinterpret_cast<const f32x2 *>(ptr);
 }
 
-template <bool IMG, int FLAGS>
+// STEP1 (every frame an origin, BASELINE config 5): origin a and lag slot m meet partner row a + m of the warp's
+// slice, so consecutive origins share three of their four partner rows.  The four rows live in registers as a
+// rotating window: per origin ONE new partner row and the origin row are read from shared memory -- 6 LDS.64 per 8
+// evaluations instead of 15.  That matters because the general loop is bound by shared-memory bandwidth, not by
+// arithmetic: 15 x 256 B per origin and warp against 28 packed FP32 instructions (profiles/r2_ncu_dense_v2.txt).
+template <bool IMG, int FLAGS, bool STEP1>
 __global__ void __launch_bounds__(kDenseThreads, 3) dense_corr_kernel_v2(const DenseDev p) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;
     constexpr bool kSinc = (FLAGS & MDB_SUM_SINC) != 0;
@@ -443,7 +525,12 @@ __global__ void __launch_bounds__(kDenseThreads, 3) dense_corr_kernel_v2(const D
             const int f_partner0 = f_origin0 + p.i0 + lam;
             const int n_rows = ns + (ns - 1) * p.ostep + nl;
             __syncthreads();                               // the previous block is done with the rows
-            if (atom0 + kTileAtoms <= p.n_atoms)
+            if (p.stage_f32) {
+                if (atom0 + kTileAtoms <= p.n_atoms)
+                    stage_rows_v2_f32<IMG, true>(p, lane, j, atom0, ns, n_rows, f_origin0, f_partner0, s_rows_f);
+                else
+                    stage_rows_v2_f32<IMG, false>(p, lane, j, atom0, ns, n_rows, f_origin0, f_partner0, s_rows_f);
+            } else if (atom0 + kTileAtoms <= p.n_atoms)
                 stage_rows_v2<IMG, true>(p, lane, j, atom0, ns, n_rows, f_origin0, f_partner0, s_rows_f);
             else
                 stage_rows_v2<IMG, false>(p, lane, j, atom0, ns, n_rows, f_origin0, f_partner0, s_rows_f);
@@ -456,25 +543,57 @@ __global__ void __launch_bounds__(kDenseThreads, 3) dense_corr_kernel_v2(const D
             const float *ro = s_rows_f + 2 * lane;
             const float *rp = s_rows_f + (size_t)(ns + kV2Slots * j) * kV2RowFloats + 2 * lane;
             const int partner_stride = p.ostep * kV2RowFloats;
-#pragma unroll 2
-            for (int a = 0; a < ns; ++a) {
-                const f32x2 ox = lds_pair(ro), oy = lds_pair(ro + kTileAtoms), oz = lds_pair(ro + 2 * kTileAtoms);
+            auto evaluate = [&](const f32x2 &ox, const f32x2 &oy, const f32x2 &oz, const f32x2 &px, const f32x2 &py,
+                                const f32x2 &pz, int m) {
+                const f32x2 dx = sub2(ox, px), dy = sub2(oy, py), dz = sub2(oz, pz);
+                const f32x2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                if constexpr (kR2) part2[m] = add2(part2[m], r2);
+                if constexpr (kSinc) {
+                    float y0, y1, v0, v1;
+                    unpack2(mul2(r2, q2), y0, y1);
+                    sinc_of_square_x2(y0, y1, v0, v1);
+                    parts[m] = add2(parts[m], pack2(v0, v1));
+                }
+            };
+            if constexpr (STEP1) {
+                static_assert(kV2Slots == 4, "the rotating window holds four partner rows");
+                f32x2 wx[4], wy[4], wz[4];
 #pragma unroll
-                for (int m = 0; m < kV2Slots; ++m) {
-                    const float *rq = rp + m * kV2RowFloats;
-                    const f32x2 dx = sub2(ox, lds_pair(rq)), dy = sub2(oy, lds_pair(rq + kTileAtoms)),
-                                dz = sub2(oz, lds_pair(rq + 2 * kTileAtoms));
-                    const f32x2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-                    if constexpr (kR2) part2[m] = add2(part2[m], r2);
-                    if constexpr (kSinc) {
-                        float y0, y1, v0, v1;
-                        unpack2(mul2(r2, q2), y0, y1);
-                        sinc_of_square_x2(y0, y1, v0, v1);
-                        parts[m] = add2(parts[m], pack2(v0, v1));
+                for (int i = 0; i < 3; ++i) {
+                    wx[i] = lds_pair(rp + i * kV2RowFloats);
+                    wy[i] = lds_pair(rp + i * kV2RowFloats + kTileAtoms);
+                    wz[i] = lds_pair(rp + i * kV2RowFloats + 2 * kTileAtoms);
+                }
+                rp += 3 * kV2RowFloats;                    // the next row the window takes in
+                for (int a = 0; a < ns; a += 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (a + k < ns) {
+                            wx[(k + 3) & 3] = lds_pair(rp);
+                            wy[(k + 3) & 3] = lds_pair(rp + kTileAtoms);
+                            wz[(k + 3) & 3] = lds_pair(rp + 2 * kTileAtoms);
+                            const f32x2 ox = lds_pair(ro), oy = lds_pair(ro + kTileAtoms),
+                                        oz = lds_pair(ro + 2 * kTileAtoms);
+#pragma unroll
+                            for (int m = 0; m < kV2Slots; ++m)
+                                evaluate(ox, oy, oz, wx[(k + m) & 3], wy[(k + m) & 3], wz[(k + m) & 3], m);
+                            ro += kV2RowFloats;
+                            rp += kV2RowFloats;
+                        }
                     }
                 }
-                ro += kV2RowFloats;
-                rp += partner_stride;
+            } else {
+#pragma unroll 2
+                for (int a = 0; a < ns; ++a) {
+                    const f32x2 ox = lds_pair(ro), oy = lds_pair(ro + kTileAtoms), oz = lds_pair(ro + 2 * kTileAtoms);
+#pragma unroll
+                    for (int m = 0; m < kV2Slots; ++m) {
+                        const float *rq = rp + m * kV2RowFloats;
+                        evaluate(ox, oy, oz, lds_pair(rq), lds_pair(rq + kTileAtoms), lds_pair(rq + 2 * kTileAtoms), m);
+                    }
+                    ro += kV2RowFloats;
+                    rp += partner_stride;
+                }
             }
 #pragma unroll
             for (int m = 0; m < kV2Slots; ++m) {
@@ -604,6 +723,12 @@ extern "C" int mdb_dense_corr(const mdb_dense_args *a, void *stream) {
     p.tiles_per_split = pl.tiles_per_split;
     p.n_tiles = pl.n_tiles;
     p.partial = static_cast<double *>(a->workspace);
+    p.stage_f32 = (a->tuning.dense_variant & 2) ? 0 : 1;
+    for (int d = 0; d < 3; ++d) {
+        p.neg_box_f[d] = -(float)a->box_const[d];
+        if ((double)(float)a->box_const[d] != a->box_const[d]) p.stage_f32 = 0;
+    }
+    p.magic23 = 0x4B000000u;
 
     const unsigned blocks = (unsigned)((long long)pl.n_lblocks * pl.n_splits);
     auto launch = [&](auto kern) -> int {
@@ -618,7 +743,9 @@ extern "C" int mdb_dense_corr(const mdb_dense_args *a, void *stream) {
     if (pl.v2) {
         auto pick2 = [&](auto flags_c) -> int {
             constexpr int F = decltype(flags_c)::value;
-            return img ? launch(dense_corr_kernel_v2<true, F>) : launch(dense_corr_kernel_v2<false, F>);
+            if (a->origin_step == 1 && !(a->tuning.dense_variant & 1))
+                return img ? launch(dense_corr_kernel_v2<true, F, true>) : launch(dense_corr_kernel_v2<false, F, true>);
+            return img ? launch(dense_corr_kernel_v2<true, F, false>) : launch(dense_corr_kernel_v2<false, F, false>);
         };
         switch (a->flags) {
             case MDB_SUM_R2: rc = pick2(std::integral_constant<int, MDB_SUM_R2>{}); break;

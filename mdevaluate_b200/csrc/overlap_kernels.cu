@@ -62,6 +62,7 @@ struct OvDev {
     int periodic;
     double boxsize[3], half_box[3];
     int max_cells;           // per origin
+    int tree_order;          // query the atoms in the order of the origin's sorted tree (see overlap_query_kernel)
     // workspace
     unsigned long long *bounds_key;   // [S][6] order-preserving keys of min xyz / max xyz
     int *tree_n;                      // [S]
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kOvThreads) overlap_scatter_kernel(const OvDev
         const long long c = (long long)s * p.max_cells + cell;
         // cell_count was zeroed after the scan and now counts the atoms already placed
         const int at = p.cell_start[c] + atomicAdd(&p.cell_count[c], 1);
-        p.sorted[at] = make_double4(x[0], x[1], x[2], 0.0);
+        p.sorted[at] = make_double4(x[0], x[1], x[2], (double)a);
     }
 }
 
@@ -288,6 +289,11 @@ __device__ __forceinline__ int neighbours(int c, int n, bool periodic, int out[3
     return k;
 }
 
+// tree_order: when the tree holds every atom of the correlated trajectory (no selection, same atom count), thread k of
+// a pair takes the atom that sits at position k of the origin's SORTED tree instead of atom k of the file.  An atom
+// rarely moves further than a cell within the window, so the lanes of a warp -- neighbours in the tree's cell order
+// -- walk the same few cells and their candidate loads coalesce; the price is a gather of the query positions
+// (12 B at a random place of a row that stays in L2 while its pair is evaluated).
 template <bool PERIODIC>
 __global__ void __launch_bounds__(kOvThreads) overlap_query_kernel(const OvDev p, const long long n_work, const int n_blocks_per_pair) {
     __shared__ int s_hits[kOvThreads / 32];
@@ -297,9 +303,10 @@ __global__ void __launch_bounds__(kOvThreads) overlap_query_kernel(const OvDev p
         const int s = (int)(pair / p.L);
         const Grid g = p.grids[s];
         const long long row = p.rows[pair];
-        const int a = ab * kOvThreads + threadIdx.x;
+        int a = ab * kOvThreads + threadIdx.x;
         bool hit = false;
         if (a < p.n_atoms && p.tree_n[s] > 0 && p.threshold >= 0.0) {
+            if (p.tree_order) a = (int)__ldg(&p.sorted[p.cell_start[(long long)s * p.max_cells] + a].w);
             double x[3];
             position(p.qry, row, a, x);
             bool reachable = true;
@@ -461,6 +468,7 @@ extern "C" int mdb_overlap(const mdb_overlap_args *a, void *stream) {
         if (b > 0.0) p.periodic = 1;
     }
     p.max_cells = lay.max_cells;
+    p.tree_order = (a->n_ref == a->n_atoms && !a->ref_select && !a->file_order) ? 1 : 0;
     char *w = static_cast<char *>(a->workspace);
     p.bounds_key = reinterpret_cast<unsigned long long *>(w + lay.bounds);
     p.tree_n = reinterpret_cast<int *>(w + lay.tree_n);

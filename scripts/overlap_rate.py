@@ -36,6 +36,20 @@ for label, frames, tree in (('raw frames, periodic tree', coords, CoordinatesKDT
     evals = N * r.shape[0] * r.shape[1]
     print('%-28s S=%d L=%d  %8.2f ms  %.3e atom*origin*lag evals/s   overlap(lag 1)=%.4f  (last lag)=%.4f'
           % (label, r.shape[0], r.shape[1], best, evals / (best * 1e-3), r[:, 1].mean(), r[:, -1].mean()), flush=True)
+# the same with the atoms queried in file order (scattered candidate loads)
+engine.overlap_file_order = True
+tree = CoordinatesKDTree(coords, boxsize=float(box[0]))
+fn = partial(c.overlap, crds_tree=tree, radius=radius)
+c.shifted_correlation(fn, coords, segments=S)
+torch.cuda.synchronize()
+ev[0].record()
+t, r2 = c.shifted_correlation(fn, coords, segments=S)
+ev[1].record()
+torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1])
+print('%-28s S=%d L=%d  %8.2f ms  %.3e atom*origin*lag evals/s' % ('periodic tree, file order', r2.shape[0], r2.shape[1], ms,
+                                                                  N * r2.size / (ms * 1e-3)))
+engine.overlap_file_order = False
 # the host: scipy's cKDTree as the reference uses it, one (origin, lag) pair
 try:
     from scipy.spatial import cKDTree

@@ -1166,7 +1166,7 @@ def test_overlap_equals_the_reference(golden, md):
     assert tree.cache_info.currsize == 0
 
 
-def test_overlap_edge_cases(md):
+def test_overlap_edge_cases(md, monkeypatch):
     """Radii from nothing to everything, a radius beyond half the periodic box (one or two cells per dimension), an
     empty tree, atoms outside a periodic box (cKDTree raises ValueError), frames far outside an open tree's bounds --
     against the oracle's brute force in cKDTree's arithmetic."""
@@ -1178,11 +1178,17 @@ def test_overlap_edge_cases(md):
     pts = (rng.random((n, 3)) * length).astype(np.float32)
     qry = (pts + rng.normal(0, 0.08, (n, 3))).astype(np.float32)
     qry[:50] += 7.0                                     # far outside an open tree; wrapped back by a periodic one
+    from mdevaluate_b200._cuda import engine
     for box in (None, length, np.array([length, 0.0, length])):
         want = orc.nearest_distances(pts, qry, box)
         tree = DeviceTree(pts, box)
         for radius in (0.0, 1e-9, 0.01, 0.05, 0.31, 0.9, 1.5, 5.0, 100.0, -1.0):
             assert tree.count_within(qry, radius) == int((want <= radius).sum()), (box, radius)
+        # the atoms queried in file order instead of the tree's cell order (what a tree of a selection gets)
+        monkeypatch.setattr(engine, 'overlap_file_order', True)
+        for radius in (0.05, 0.31):
+            assert tree.count_within(qry, radius) == int((want <= radius).sum()), (box, radius)
+        monkeypatch.setattr(engine, 'overlap_file_order', False)
     # float64 points and frames
     pts64 = rng.random((800, 3)) * length
     qry64 = pts64 + rng.normal(0, 0.05, (800, 3))
