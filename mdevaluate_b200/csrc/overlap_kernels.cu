@@ -294,61 +294,85 @@ __device__ __forceinline__ int neighbours(int c, int n, bool periodic, int out[3
 // rarely moves further than a cell within the window, so the lanes of a warp -- neighbours in the tree's cell order
 // -- walk the same few cells and their candidate loads coalesce; the price is a gather of the query positions
 // (12 B at a random place of a row that stays in L2 while its pair is evaluated).
+constexpr int kOvChunk = 64;      // warp passes (32 atoms each) of one (origin, lag) pair that a warp takes in a row
+
 template <bool PERIODIC>
-__global__ void __launch_bounds__(kOvThreads) overlap_query_kernel(const OvDev p, const long long n_work, const int n_blocks_per_pair) {
-    __shared__ int s_hits[kOvThreads / 32];
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const long long pair = w / n_blocks_per_pair;
-        const int ab = (int)(w - pair * n_blocks_per_pair);
+__global__ void __launch_bounds__(kOvThreads) overlap_query_kernel(const OvDev p, const long long n_chunks,
+                                                                   const int chunks_per_pair) {
+    // A WARP takes chunks of 2048 atoms of one pair, round robin over all warps of the grid (pairs at long lags cost
+    // more than pairs at short ones: fine-grained turns keep the warps level); hits are counted in a register and
+    // go out as one atomic per chunk -- no block-wide barrier anywhere.
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = (long long)blockIdx.x * (kOvThreads / 32) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (kOvThreads / 32);
+    for (long long c = warp_id; c < n_chunks; c += n_warps) {
+        const long long pair = c / chunks_per_pair;
+        const int first = (int)(c - pair * chunks_per_pair) * (kOvChunk * 32);
         const int s = (int)(pair / p.L);
         const Grid g = p.grids[s];
         const long long row = p.rows[pair];
-        int a = ab * kOvThreads + threadIdx.x;
-        bool hit = false;
-        if (a < p.n_atoms && p.tree_n[s] > 0 && p.threshold >= 0.0) {
-            if (p.tree_order) a = (int)__ldg(&p.sorted[p.cell_start[(long long)s * p.max_cells] + a].w);
-            double x[3];
-            position(p.qry, row, a, x);
-            bool reachable = true;
+        const int *start = p.cell_start + (long long)s * p.max_cells;
+        const bool any_tree = p.tree_n[s] > 0 && p.threshold >= 0.0;
+        const int seg0 = p.tree_order ? start[0] : 0;
+        int hits = 0;
+        for (int a0 = first; a0 < min(p.n_atoms, first + kOvChunk * 32); a0 += 32) {
+            int a = a0 + lane;
+            bool hit = false;
+            if (a < p.n_atoms && any_tree) {
+                if (p.tree_order) a = (int)__ldg(&p.sorted[seg0 + a].w);
+                double x[3];
+                position(p.qry, row, a, x);
+                bool reachable = true;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const bool per = PERIODIC && p.boxsize[d] > 0.0;
-                if (per) x[d] = wrap_position(x[d], p.boxsize[d]);
-                else {
-                    const double top = g.lo[d] + (double)g.n[d] / g.inv[d];     // >= the largest tree coordinate
-                    if (!(x[d] >= g.lo[d] - p.reach && x[d] <= top + p.reach)) reachable = false;
+                for (int d = 0; d < 3; ++d) {
+                    const bool per = PERIODIC && p.boxsize[d] > 0.0;
+                    if (per) x[d] = wrap_position(x[d], p.boxsize[d]);
+                    else {
+                        const double top = g.lo[d] + (double)g.n[d] / g.inv[d];     // >= the largest tree coordinate
+                        if (!(x[d] >= g.lo[d] - p.reach && x[d] <= top + p.reach)) reachable = false;
+                    }
+                }
+                if (reachable) {
+                    int cx[3], cy[3], cz[3];
+                    const int nx = neighbours(cell_coord(g, 0, x[0]), g.n[0], PERIODIC && p.boxsize[0] > 0.0, cx);
+                    const int ny = neighbours(cell_coord(g, 1, x[1]), g.n[1], PERIODIC && p.boxsize[1] > 0.0, cy);
+                    const int nz = neighbours(cell_coord(g, 2, x[2]), g.n[2], PERIODIC && p.boxsize[2] > 0.0, cz);
+                    // consecutive z cells are consecutive in the sorted array: one run, two where the wrap splits it
+                    int z_lo[2], z_hi[2], n_runs = 1;
+                    z_lo[0] = cz[0];
+                    z_hi[0] = cz[0];
+                    z_lo[1] = z_hi[1] = 0;
+                    for (int i = 1; i < nz; ++i) {
+                        if (cz[i] == z_hi[n_runs - 1] + 1) z_hi[n_runs - 1] = cz[i];
+                        else if (n_runs < 2) { z_lo[1] = z_hi[1] = cz[i]; n_runs = 2; }
+                        else z_hi[1] = cz[i];      // not reached: three cells make at most two runs
+                    }
+                    for (int ix = 0; ix < nx && !hit; ++ix) {
+                        // the bounds of all runs of this x layer first (independent loads), then the scans
+                        int begin[3][2], end[3][2];
+#pragma unroll
+                        for (int iy = 0; iy < 3; ++iy)
+#pragma unroll
+                            for (int r = 0; r < 2; ++r) {
+                                begin[iy][r] = end[iy][r] = 0;
+                                if (iy < ny && r < n_runs) {
+                                    const int base = (cx[ix] * g.n[1] + cy[iy]) * g.n[2];
+                                    begin[iy][r] = start[base + z_lo[r]];
+                                    end[iy][r] = start[base + z_hi[r] + 1];
+                                }
+                            }
+#pragma unroll
+                        for (int iy = 0; iy < 3; ++iy)
+#pragma unroll
+                            for (int r = 0; r < 2; ++r)
+                                if (!hit && begin[iy][r] < end[iy][r])
+                                    hit = any_within<PERIODIC>(p, p.sorted, begin[iy][r], end[iy][r], x);
+                    }
                 }
             }
-            if (reachable) {
-                int cx[3], cy[3], cz[3];
-                const int nx = neighbours(cell_coord(g, 0, x[0]), g.n[0], PERIODIC && p.boxsize[0] > 0.0, cx);
-                const int ny = neighbours(cell_coord(g, 1, x[1]), g.n[1], PERIODIC && p.boxsize[1] > 0.0, cy);
-                const int nz = neighbours(cell_coord(g, 2, x[2]), g.n[2], PERIODIC && p.boxsize[2] > 0.0, cz);
-                const int *start = p.cell_start + (long long)s * p.max_cells;
-                for (int ix = 0; ix < nx && !hit; ++ix)
-                    for (int iy = 0; iy < ny && !hit; ++iy) {
-                        const int base = (cx[ix] * g.n[1] + cy[iy]) * g.n[2];
-                        // consecutive z cells are consecutive in the sorted array: one run unless the wrap splits it
-                        int iz = 0;
-                        while (iz < nz && !hit) {
-                            int jz = iz;
-                            while (jz + 1 < nz && cz[jz + 1] == cz[jz] + 1) ++jz;
-                            hit = any_within<PERIODIC>(p, p.sorted, start[base + cz[iz]], start[base + cz[jz] + 1], x);
-                            iz = jz + 1;
-                        }
-                    }
-            }
+            hits += __popc(__ballot_sync(0xffffffffu, hit));
         }
-        const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_hits[threadIdx.x >> 5] = __popc(ballot);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int total = 0;
-#pragma unroll
-            for (int i = 0; i < kOvThreads / 32; ++i) total += s_hits[i];
-            if (total) atomicAdd(&p.counts[pair], (unsigned long long)total);
-        }
+        if (lane == 0 && hits) atomicAdd(&p.counts[pair], (unsigned long long)hits);
     }
 }
 
@@ -501,13 +525,14 @@ extern "C" int mdb_overlap(const mdb_overlap_args *a, void *stream) {
     MDB_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w + lay.scan_temp, temp, p.cell_count, p.cell_start, (int)n_cells_all, st));
     MDB_CUDA_CHECK(cudaMemsetAsync(p.cell_count, 0, n_cells_all * 4, st));
     overlap_scatter_kernel<<<ref_grid, kOvThreads, 0, st>>>(p);
-    const int blocks_per_pair = (p.n_atoms + kOvThreads - 1) / kOvThreads;
-    const long long n_work = (long long)p.S * p.L * blocks_per_pair;
-    if (n_work > 0) {
+    const int chunks_per_pair = (p.n_atoms + kOvChunk * 32 - 1) / (kOvChunk * 32);
+    const long long n_chunks = (long long)p.S * p.L * chunks_per_pair;
+    if (n_chunks > 0) {
         const long long want = (long long)sms * 8;
-        const int grid = (int)(n_work < want ? n_work : want);
-        if (p.periodic) overlap_query_kernel<true><<<grid, kOvThreads, 0, st>>>(p, n_work, blocks_per_pair);
-        else overlap_query_kernel<false><<<grid, kOvThreads, 0, st>>>(p, n_work, blocks_per_pair);
+        const long long blocks = (n_chunks + kOvThreads / 32 - 1) / (kOvThreads / 32);
+        const int grid = (int)(blocks < want ? blocks : want);
+        if (p.periodic) overlap_query_kernel<true><<<grid, kOvThreads, 0, st>>>(p, n_chunks, chunks_per_pair);
+        else overlap_query_kernel<false><<<grid, kOvThreads, 0, st>>>(p, n_chunks, chunks_per_pair);
     }
     MDB_CUDA_CHECK(cudaGetLastError());
     if (a->tree_sizes) MDB_CUDA_CHECK(cudaMemcpyAsync(a->tree_sizes, p.tree_n, (size_t)p.S * 4, cudaMemcpyDeviceToDevice, st));
