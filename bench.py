@@ -635,16 +635,21 @@ def measure_e2e(a, torch, md, c, parallel, res, store, stream, starts, idx, kw, 
     floor_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
     del sink
     barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.e2e_steps + 1)]
     ev[0].record()
-    for _ in range(a.e2e_steps):
+    marks[0].record()
+    for i in range(a.e2e_steps):
         t, x4_e2e = e2e_step()
+        marks[i + 1].record()
     ev[1].record()
     barrier()
     e2e_ms = max_over_ranks(ev[0].elapsed_time(ev[1])) / a.e2e_steps
+    each_ms = [max_over_ranks(marks[i].elapsed_time(marks[i + 1])) for i in range(a.e2e_steps)]
     S, L = len(starts), len(idx)
     h2d = int(len(ids)) * n3 * 4 + list_bytes
     return {'value': evals_step / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d * world,
             'd2h_bytes_per_step': int(S * L * 3 * 8) * world, 'ms_per_step': e2e_ms, 'steps': a.e2e_steps,
+            'ms_each_step': each_ms,
             'h2d_GBps_per_gpu': h2d / (e2e_ms * 1e-3) / 1e9, 'matches_resident': bool(np.array_equal(x4, x4_e2e)),
             'h2d_floor': {'ms': floor_ms, 'GBps_per_gpu': len(ids) * n3 * 4 / (floor_ms * 1e-3) / 1e9,
                           'GBps_all_gpus': world * len(ids) * n3 * 4 / (floor_ms * 1e-3) / 1e9,
