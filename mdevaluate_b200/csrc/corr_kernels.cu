@@ -619,12 +619,23 @@ __device__ __forceinline__ void process_tile_f32d(const CorrDev &p, Ring &ring, 
         float rawt[12];
         uint32_t wt[6];
         fetch_raw<IMG>(ring, full0, empty0, stages, stage_bytes, tid, rawt, wt);
+        float dv[12];
+        // Between an origin and a lag frame few atoms change their image: when NO atom of the warp did (the image
+        // words of the two rows are equal in every lane) the displacement is x0 - xt -- exactly what the general
+        // formula below gives for k = 0 (fma(+0, -L, x) = x), so the results are bit-identical; it saves 48 of the
+        // 155 (ISF) instructions per 4 evaluations.  Warp-uniform, so there is no divergence.
+        bool same = wt[0] == w0[0];
+        if (IMG == IMG_BYTES) same = same && wt[1] == w0[1] && wt[2] == w0[2];
+        if (__all_sync(0xffffffffu, same)) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                unpack2(sub2(x0[j], pack2(rawt[2 * j], rawt[2 * j + 1])), dv[2 * j], dv[2 * j + 1]);
+        } else {
         uint32_t kd[3];
         if (IMG == IMG_PACKED) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) kd[d] = o[d] - packed_dim(wt[0], d);     // bytes: 64 + 4^d (n0 - nt)
         }
-        float dv[12];
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             f32x2 dn;                                                            // (scaled) n0 - nt, exact
@@ -644,6 +655,7 @@ __device__ __forceinline__ void process_tile_f32d(const CorrDev &p, Ring &ring, 
             const f32x2 om = fma2(up, neg_box[j % 3], x0[j]);
             const f32x2 tm = fma2(dw, neg_box[j % 3], pack2(rawt[2 * j], rawt[2 * j + 1]));
             unpack2(sub2(om, tm), dv[2 * j], dv[2 * j + 1]);
+        }
         }
         float r2[4];
 #pragma unroll
