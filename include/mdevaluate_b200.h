@@ -63,8 +63,10 @@ typedef struct mdb_tuning {
     int32_t scan_direct;     /* 1: register-load variant of the jump scan instead of the bulk-copy ring       */
     int32_t dense_stage_cta; /* 1: CTA-wide staging loop of the float64 dense kernel instead of warp-per-row  */
     int32_t dense_float64;   /* 1: dense schedules through the float64 tile (default: float32 offsets, v2)    */
-    int32_t dense_variant;   /* bit 0: general origin loop even when every frame is an origin (no rotating row
-                              * window); bit 1: float64 staging even when the box lengths are float32 numbers   */
+    int32_t variant;         /* measurement switches, 0 = the product path.  bit 0: dense kernel, general origin loop
+                              * even when every frame is an origin (no rotating row window); bit 1: dense kernel,
+                              * float64 staging even when the box lengths are float32 numbers; bit 2: float32-
+                              * displacement kernels without the no-image-change shortcut                      */
 } mdb_tuning;
 
 /* coordinate element type */

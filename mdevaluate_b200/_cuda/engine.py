@@ -38,7 +38,7 @@ class Tuning:
     """Explicit kernel switches (``mdb_tuning`` of the C ABI); 0 = the measured default.  Process-wide, read at every
     launch / plan creation.  ``engine.tuning.isf_float64 = 1`` e.g. sends the ISF through the float64 chain."""
     FIELDS = ('ring_stages', 'atom_blocks', 'isf_float64', 'hist_float64', 'scan_direct', 'dense_stage_cta',
-              'dense_float64', 'dense_variant')
+              'dense_float64', 'variant')
 
     def __init__(self):
         for f in self.FIELDS:

@@ -46,7 +46,7 @@ class Tuning(C.Structure):
     """mdb_tuning: explicit kernel switches, 0 = the measured default."""
     _fields_ = [('ring_stages', C.c_int32), ('atom_blocks', C.c_int32), ('isf_float64', C.c_int32),
                 ('hist_float64', C.c_int32), ('scan_direct', C.c_int32), ('dense_stage_cta', C.c_int32),
-                ('dense_float64', C.c_int32), ('dense_variant', C.c_int32)]
+                ('dense_float64', C.c_int32), ('variant', C.c_int32)]
 
 
 class CorrArgs(C.Structure):

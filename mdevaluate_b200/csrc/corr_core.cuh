@@ -59,6 +59,7 @@ struct CorrDev {
     const double *edges;
     double *partial;         // [S*L][n_ablocks][3]
     unsigned long long *hist;
+    int no_shortcut;             // tuning.variant bit 2: always the general displacement formula (measurement)
     unsigned long long *stamp;   // plans: the first CTA stores %globaltimer here when it starts (timeline), or nullptr
 };
 

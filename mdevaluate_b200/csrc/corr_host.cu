@@ -188,6 +188,7 @@ CorrDev device_args(const mdb_corr_args *a, const Plan &plan) {
     const bool hist_flags = (a->flags == MDB_HIST || a->flags == (MDB_SUM_R2 | MDB_SUM_R4 | MDB_HIST)) &&
                             a->bin_mode == MDB_BINS_UNIFORM;
     p.f32d = box_f32 && ((a->flags == MDB_SUM_SINC && !a->tuning.isf_float64) || (hist_flags && !a->tuning.hist_float64));
+    p.no_shortcut = (a->tuning.variant & 4) ? 1 : 0;
     p.q2f = (float)p.q2;
     {
         const int dims[6] = {0, 1, 2, 0, 1, 2};

@@ -626,7 +626,7 @@ __device__ __forceinline__ void process_tile_f32d(const CorrDev &p, Ring &ring, 
         // 155 (ISF) instructions per 4 evaluations.  Warp-uniform, so there is no divergence.
         bool same = wt[0] == w0[0];
         if (IMG == IMG_BYTES) same = same && wt[1] == w0[1] && wt[2] == w0[2];
-        if (__all_sync(0xffffffffu, same)) {
+        if (__all_sync(0xffffffffu, same && !p.no_shortcut)) {
 #pragma unroll
             for (int j = 0; j < 6; ++j)
                 unpack2(sub2(x0[j], pack2(rawt[2 * j], rawt[2 * j + 1])), dv[2 * j], dv[2 * j + 1]);

@@ -723,7 +723,7 @@ extern "C" int mdb_dense_corr(const mdb_dense_args *a, void *stream) {
     p.tiles_per_split = pl.tiles_per_split;
     p.n_tiles = pl.n_tiles;
     p.partial = static_cast<double *>(a->workspace);
-    p.stage_f32 = (a->tuning.dense_variant & 2) ? 0 : 1;
+    p.stage_f32 = (a->tuning.variant & 2) ? 0 : 1;
     for (int d = 0; d < 3; ++d) {
         p.neg_box_f[d] = -(float)a->box_const[d];
         if ((double)(float)a->box_const[d] != a->box_const[d]) p.stage_f32 = 0;
@@ -743,7 +743,7 @@ extern "C" int mdb_dense_corr(const mdb_dense_args *a, void *stream) {
     if (pl.v2) {
         auto pick2 = [&](auto flags_c) -> int {
             constexpr int F = decltype(flags_c)::value;
-            if (a->origin_step == 1 && !(a->tuning.dense_variant & 1))
+            if (a->origin_step == 1 && !(a->tuning.variant & 1))
                 return img ? launch(dense_corr_kernel_v2<true, F, true>) : launch(dense_corr_kernel_v2<false, F, true>);
             return img ? launch(dense_corr_kernel_v2<true, F, false>) : launch(dense_corr_kernel_v2<false, F, false>);
         };
