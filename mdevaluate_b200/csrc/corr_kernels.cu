@@ -384,12 +384,11 @@ __device__ __forceinline__ void cta_epilogue(const CorrDev &p, const CtaWork &w,
         p.partial[((((long long)w.s * p.L + w.l0 + k) * p.n_ablocks + w.ab) * n_seg + seg) * 3 + comp] = v;
     }
     if (kHist && seg == 0) {
+        // the chunk's tables [lag][bin] are one contiguous piece of the [origin][lag][bin] result
+        unsigned long long *out = p.hist + ((long long)w.s * p.L + w.l0) * p.n_bins;
         for (int i = tid; i < w.nl * p.n_bins; i += kThreads) {
             const unsigned int cnt = s_hist[i];
-            if (cnt) {
-                const int k = i / p.n_bins, b = i - k * p.n_bins;
-                atomicAdd(&p.hist[((long long)w.s * p.L + w.l0 + k) * p.n_bins + b], (unsigned long long)cnt);
-            }
+            if (cnt) atomicAdd(&out[i], (unsigned long long)cnt);
         }
     }
     if (n_seg > 1) sync();                 // s_red is reused by the next sub-ensemble
