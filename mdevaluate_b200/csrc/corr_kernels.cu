@@ -534,34 +534,20 @@ struct Ring {
     }
 };
 
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-
-// Take the calling thread's 4 atoms out of the current stage and release the stage.  `stages` carries the 32-bit
-// shared address of the first stage (not a generic pointer).
+// Take the calling thread's 4 atoms out of the current stage and release the stage.
 template <int IMG>
-__device__ __forceinline__ void fetch_raw(Ring &ring, uint32_t full0, uint32_t empty0, uint32_t stages,
+__device__ __forceinline__ void fetch_raw(Ring &ring, uint32_t full0, uint32_t empty0, const unsigned char *stages,
                                           int stage_bytes, int tid, float (&raw)[12], uint32_t (&wds)[6]) {
     mbar_wait(full0 + 8 * ring.stage, ring.phase);
-    // 32-bit shared addresses and explicit ld.shared: through generic pointers ptxas rebuilt the shared-window
-    // address of the stage (S2R SR_CgaCtaId, LEA ...) in every pass of the loop (ncu source view of round 2)
-    const uint32_t src = stages + ring.stage * (uint32_t)stage_bytes;
-    const float4 a = lds_f4(src + 48u * (uint32_t)tid), b = lds_f4(src + 48u * (uint32_t)tid + 16u),
-                 c = lds_f4(src + 48u * (uint32_t)tid + 32u);
+    const unsigned char *src = stages + (size_t)ring.stage * stage_bytes;
+    const float4 *c4 = reinterpret_cast<const float4 *>(src) + 3 * tid;
+    const float4 a = c4[0], b = c4[1], c = c4[2];
     wds[0] = wds[1] = wds[2] = wds[3] = wds[4] = wds[5] = 0u;
     if (IMG == IMG_BYTES) {
-        const uint32_t iw = src + (uint32_t)kCoordTileBytes + 12u * (uint32_t)tid;
-        wds[0] = lds_u32(iw); wds[1] = lds_u32(iw + 4u); wds[2] = lds_u32(iw + 8u);
+        const uint32_t *iw = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes) + 3 * tid;
+        wds[0] = iw[0]; wds[1] = iw[1]; wds[2] = iw[2];
     }
-    if (IMG == IMG_PACKED) wds[0] = lds_u32(src + (uint32_t)kCoordTileBytes + 4u * (uint32_t)tid);
+    if (IMG == IMG_PACKED) wds[0] = reinterpret_cast<const uint32_t *>(src + kCoordTileBytes)[tid];
     raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
     raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
     raw[8] = c.x; raw[9] = c.y; raw[10] = c.z; raw[11] = c.w;
@@ -576,7 +562,7 @@ __device__ __forceinline__ void fetch_raw(Ring &ring, uint32_t full0, uint32_t e
 // ... and unwrap to float64.
 template <int IMG, bool BOXC>
 __device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
-                                            uint32_t stages, int stage_bytes, int tid,
+                                            const unsigned char *stages, int stage_bytes, int tid,
                                             const double *bx, double (&u)[12], float (&raw)[12]) {
     uint32_t wds[6];
     fetch_raw<IMG>(ring, full0, empty0, stages, stage_bytes, tid, raw, wds);
@@ -599,7 +585,7 @@ __device__ __forceinline__ void fetch_group(const CorrDev &p, Ring &ring, uint32
 // difference are 64 + 4^d k.
 template <int IMG, int FLAGS, bool MASKED>
 __device__ __forceinline__ void process_tile_f32d(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
-                                                  uint32_t stages, int stage_bytes, int tid,
+                                                  const unsigned char *stages, int stage_bytes, int tid,
                                                   uint32_t vmask, int nl, double *s_acc, unsigned int *s_hist,
                                                   uint32_t trash) {
     constexpr bool kR2 = (FLAGS & MDB_SUM_R2) != 0;          // with R4: alpha_2 next to the histogram
@@ -744,7 +730,7 @@ struct HasF32d {
 // instruction cache); per-lag accumulators live in shared memory, one private column per thread.
 template <int IMG, int FLAGS, bool MASKED, bool BOXC>
 __device__ __forceinline__ void process_tile(const CorrDev &p, Ring &ring, uint32_t full0, uint32_t empty0,
-                                             uint32_t stages, int stage_bytes, int tid, uint32_t vmask,
+                                             const unsigned char *stages, int stage_bytes, int tid, uint32_t vmask,
                                              int nl,
                                              const double (*s_box)[3], double *s_acc, unsigned int *s_hist,
                                              const double *s_edges, uint32_t trash) {
@@ -831,9 +817,7 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
     const int g_end = min(p.n_groups, g_begin + p.groups_per_block);
     const int n_tiles = (g_end - g_begin + kThreads - 1) / kThreads;
     const int n_units = w.nl + 1;   // origin + lag rows per tile
-    uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]), stages32 = smem_u32(smem_raw);
-    // opaque to the compiler from here on: held in registers instead of being rebuilt in every pass of the hot loop
-    asm volatile("" : "+r"(full0), "+r"(empty0), "+r"(stages32));
+    const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
     Ring ring{0u, 0u, (uint32_t)n_stages};
 
     if (tid >= kThreads) {
@@ -876,11 +860,11 @@ __global__ void __launch_bounds__(kBulkThreads, MDB_BULK_CTAS_PER_SM) corr_bulk_
     for (int t = 0; t < n_tiles; ++t) {
         const int g_last = g_begin + t * kThreads + kThreads - 1;          // last group of this tile
         if (4 * g_last + 3 < p.n_atoms && p.select == nullptr) {
-            process_tile<IMG, FLAGS, false, BOXC>(p, ring, full0, empty0, stages32, kStageBytes, tid, 0xfu, w.nl, s_box,
+            process_tile<IMG, FLAGS, false, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, 0xfu, w.nl, s_box,
                                                   s_acc, s_hist, s_edges, trash);
         } else {
             const uint32_t vmask = group_mask(p, w.s, g_begin + t * kThreads + tid);
-            process_tile<IMG, FLAGS, true, BOXC>(p, ring, full0, empty0, stages32, kStageBytes, tid, vmask, w.nl, s_box,
+            process_tile<IMG, FLAGS, true, BOXC>(p, ring, full0, empty0, smem_raw, kStageBytes, tid, vmask, w.nl, s_box,
                                                  s_acc, s_hist, s_edges, trash);
         }
     }

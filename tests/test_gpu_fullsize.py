@@ -208,3 +208,49 @@ def test_config3_van_hove_and_alpha2_full_size():
     np.testing.assert_allclose(got_a2[:, 1:], ref_a2[:, 1:], rtol=1e-5, atol=1e-7)
     del coords, block, store, sub_store
     torch.cuda.empty_cache()
+
+
+def test_van_hove_counts_are_complete_and_reproducible_at_size():
+    """One million atoms, 20 origins x 72 lags, twelve runs of the histogram kernel: every (origin, lag) table holds
+    exactly N counts and every run gives the same table.  A stage of the copy ring that is released before every lane
+    has read it shows up here as a few lost counts per 10^9 samples in some runs (it did, for a candidate of round 2
+    that read the stages with hand-written ld.shared; the bench's multi-GPU count check caught it)."""
+    import torch
+    import mdevaluate_b200 as md
+    from mdevaluate_b200._cuda import engine
+    from mdevaluate_b200.synthetic import random_walk_device, box_length
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip('needs ~25 GB of free HBM (free: %.0f GB)' % (free / 1e9))
+    n, t_frames = 1000000, 1200
+    block, box, times = random_walk_device(n, t_frames, seed=5, box=box_length(n), pitch=engine.row_pitch(n))
+    coords = md.Coordinates.from_arrays(block, box, times, n_atoms=n).nojump
+    c = md.correlation
+    store = coords._resident().store_for(np.arange(t_frames), nojump=True)
+    starts, idx = c._schedule(coords, c.log_indices, 20, 0.5, None)
+    rows = store.rows_for(starts[:, None] + idx[None, :])
+    first = {}
+    for rep in range(12):
+        for name, fn in (('vh', partial(c.van_hove_self, bins=np.linspace(0, 3.0, 501))),):
+            plan = engine.CorrPlan(store, rows, c._kernel_spec(fn).corr)
+            _, hist = plan.run()
+            hist = np.array(hist)
+            plan.close()
+            assert (hist.sum(axis=-1) == n).all(), 'run %d lost %d counts' % (rep, n * hist.shape[0] * hist.shape[1] - hist.sum())
+            if name in first:
+                assert np.array_equal(hist, first[name]), 'run %d differs from run 0' % rep
+            first.setdefault(name, hist)
+    # the fused pass (histogram + alpha_2 sums) on the same rows
+    spec = engine.CorrSpec(1 | 2 | 8, n_bins=500, bin_mode=c._kernel_spec(partial(c.van_hove_self, bins=np.linspace(0, 3.0, 501))).corr.bin_mode,
+                           dx=3.0 / 500)
+    for rep in range(6):
+        plan = engine.CorrPlan(store, rows, spec)
+        _, hist = plan.run()
+        hist = np.array(hist)
+        plan.close()
+        assert np.array_equal(hist, first['vh']), 'fused run %d differs from the histogram kernel' % rep
+    del coords, block, store
+    torch.cuda.empty_cache()
