@@ -212,9 +212,9 @@ def test_config3_van_hove_and_alpha2_full_size():
 
 def test_van_hove_counts_are_complete_and_reproducible_at_size():
     """One million atoms, 20 origins x 72 lags, twelve runs of the histogram kernel: every (origin, lag) table holds
-    exactly N counts and every run gives the same table.  A stage of the copy ring that is released before every lane
-    has read it shows up here as a few lost counts per 10^9 samples in some runs (it did, for a candidate of round 2
-    that read the stages with hand-written ld.shared; the bench's multi-GPU count check caught it)."""
+    exactly N counts and every run gives the same table.  A candidate of round 2 that read the ring stages with
+    hand-written ld.shared lost a few counts per 10^9 samples in some runs at this size (the bench's multi-GPU count
+    check caught it; smaller cases were exact): this test is the guard against that class of hazard."""
     import torch
     import mdevaluate_b200 as md
     from mdevaluate_b200._cuda import engine
