@@ -19,17 +19,25 @@ store = coords._resident().store_for(np.arange(T), nojump=True)
 starts, idx = c._schedule(coords, c.log_indices, 20, 0.5, None)
 rows = store.rows_for(starts[:, None] + idx[None, :])
 print('lib', _l.LIB_PATH, 'N', N, 'S', len(starts), 'L', len(idx), 'packed' if store.packed is not None else 'bytes')
-for name, fn in (('van_hove', partial(c.van_hove_self, bins=bins)),):
+variants = [('packed counts, float32 displacements', {}), ('byte counts', {'use_packed': False}),
+            ('float64 chain', {'hist_float64': 1})]
+for label, tune in variants if '--all' in sys.argv else variants[:1]:
+  for k_, v_ in tune.items():
+    setattr(engine.tuning, k_, v_)
+  print(label, flush=True)
+  for name, fn in (('van_hove', partial(c.van_hove_self, bins=bins)),):
     spec = c._kernel_spec(fn)
     first = None
     for rep in range(12):
-        plan = engine.CorrPlan(store, rows, spec.corr)
-        s, h = plan.run()
-        h = np.array(h)
-        plan.close()
-        tot = int(h.sum())
-        if first is None:
-            first = h
-        diff = int(np.abs(h - first).sum())
-        per_pair = h.sum(axis=-1)
-        print('  rep %2d total %d  (N*S*L = %d)  pairs short of N: %d  |diff to rep 0| %d' % (rep, tot, N * h.shape[0] * h.shape[1], int((per_pair != N).sum()), diff), flush=True)
+          plan = engine.CorrPlan(store, rows, spec.corr)
+          s, h = plan.run()
+          h = np.array(h)
+          plan.close()
+          tot = int(h.sum())
+          if first is None:
+              first = h
+          diff = int(np.abs(h - first).sum())
+          per_pair = h.sum(axis=-1)
+          print('  rep %2d total %d  (N*S*L = %d)  pairs short of N: %d  |diff to rep 0| %d' % (rep, tot, N * h.shape[0] * h.shape[1], int((per_pair != N).sum()), diff), flush=True)
+  for k_ in tune:
+    setattr(engine.tuning, k_, True if k_ == 'use_packed' else 0)
